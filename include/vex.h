@@ -1,0 +1,157 @@
+/*
+ * vex.h -- C ABI of libvex.so: the B200 (sm_100a) kernels behind the visual-expert decoder layer.
+ *
+ * The reference (function2-llx/MMMM) has no native code and no FFI on this path: the layer is eager
+ * PyTorch in mmmm/models/cogvlm/modeling_cogvlm.py:30-340 and its "operator interface" is the
+ * torch.nn.Module surface of CogVLMDecoderLayer.forward (:295-340).  This header therefore defines the
+ * boundary a maintainer binds instead of the ATen calls; every entry point names the reference lines
+ * it replaces.  The Python mirror of the reference interface (mmmm_b200/modeling_cogvlm.py) binds these
+ * symbols with ctypes and registers them as torch.library custom ops.
+ *
+ * Conventions
+ *   - plain C, raw DEVICE pointers and sizes, no torch types; all activations are bf16 (uint16_t bits)
+ *   - every call is asynchronous on `stream` (a cudaStream_t), never synchronises, never allocates or
+ *     frees caller memory; outputs are pre-allocated by the caller
+ *   - token counts live ON THE DEVICE (`counts`, written by vex_partition); grids are sized from the
+ *     host-known upper bound rows_cap = B*L, so the path has no host sync and is CUDA-graph capturable
+ *   - return 0 on success, a negative VEX_E_* code otherwise (vex_error_string); CUDA launch errors are
+ *     reported as VEX_E_CUDA with the cudaError_t available from vex_last_cuda_error()
+ *
+ * Row orders:
+ *   flat   : b*L + l, the reference's [B, L] layout
+ *   token  : rank among rows with padding_mask == True  (== order of hidden_states[padding_mask])
+ *   sorted : vision-expert rows first (ascending flat order == order of x[vision_token_mask]),
+ *            then language-expert rows (order of x[language_token_mask]); no padding between them
+ */
+#ifndef VEX_H_
+#define VEX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VEX_ABI_VERSION 1
+
+#define VEX_OK 0
+#define VEX_E_INVALID (-1)     /* bad argument (null pointer, size, alignment) */
+#define VEX_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
+#define VEX_E_CUDA (-3)        /* CUDA runtime / driver error, see vex_last_cuda_error */
+#define VEX_E_NO_DEVICE (-4)   /* not an sm_100 device */
+
+typedef void* vexStream; /* cudaStream_t */
+
+int vex_abi_version(void);
+const char* vex_error_string(int code);
+int vex_last_cuda_error(void);
+/* 0 if the current device can run the kernels (compute capability 10.x), VEX_E_NO_DEVICE otherwise */
+int vex_device_check(void);
+
+/* indices into the device `counts` array written by vex_partition */
+#define VEX_COUNT_VISION 0
+#define VEX_COUNT_LANGUAGE 1
+#define VEX_COUNT_VALID 2
+#define VEX_COUNT_MAXLEN 3
+#define VEX_NUM_COUNTS 4
+
+/* K1 -- token-type partition + compaction.
+ * Replaces get_expert_mask (modeling_cogvlm.py:58-70) and every boolean-mask index / nonzero derived
+ * from it (:96-97, :244-245, :278-279, :307, :326) and _to_tensor_list (:100-104).
+ *   vision[b,l]   = tt[b,l]==1 && tt[b,l+1]==1 (l < L-1; last column false), && padding_mask
+ *   language[b,l] = !vision_raw && padding_mask
+ * Requires L > 1 (the L == 1 decode rule of :67 is out of scope).  All index outputs have B*L entries;
+ * entries past the respective count are -1.
+ *   sorted_to_flat [s] : flat position of sorted row s       ([0,Tv) == nonzero(vision), [Tv,Tv+Tl) == nonzero(language))
+ *   flat_to_sorted [f] : inverse, -1 for padded positions
+ *   sorted_to_token[s] : token rank of sorted row s
+ *   token_to_sorted[t] : inverse
+ *   token_to_flat  [t] : flat position of token t            (== nonzero(padding_mask))
+ *   cu_seqlens   [B+1] : prefix sums of valid tokens per sample
+ *   counts         [4] : Tv, Tl, T, max valid length of a sample
+ *   scratch      [4*B] : int32 workspace
+ */
+int vex_partition(const int64_t* token_type_ids, const uint8_t* padding_mask, int B, int L,
+                  int32_t* sorted_to_flat, int32_t* flat_to_sorted, int32_t* sorted_to_token,
+                  int32_t* token_to_sorted, int32_t* token_to_flat, int32_t* cu_seqlens, int32_t* counts,
+                  int32_t* scratch, vexStream stream);
+
+/* K2 -- fused RMSNorm with gather.  Replaces RMSNorm.forward (:36-41) + hidden_states[padding_mask]
+ * (:307, :326): y[r] = bf16( w * ( f32(x[src[r]]) * rsqrt(mean(f32(x)^2) + eps) ) ) for r < *n_rows.
+ *   x [*, H] bf16 rows addressed through row_src (NULL = identity); y [rows_cap, H] bf16
+ *   weight: bf16 (weight_is_fp32 == 0) or fp32; n_rows: device int32 (e.g. counts + VEX_COUNT_VALID)
+ *   H in {256, 512, ..., 1536, 2048, 4096} (whole row kept in registers by one warp).
+ */
+int vex_rmsnorm_gather(const void* x, const void* weight, int weight_is_fp32, float eps,
+                       const int32_t* row_src, const int32_t* n_rows, void* y, int rows_cap, int H,
+                       vexStream stream);
+
+/* K5 -- standalone SiLU gate: out = bf16(bf16(silu(gate)) * up), rows < *n_rows.  Replaces
+ * act_fn(gate_proj(x)) * up_proj(x) (:55) when the SwiGLU epilogue of vex_grouped_gemm is not used. */
+int vex_silu_mul(const void* gate, const void* up, void* out, const int32_t* n_rows, int rows_cap, int I,
+                 vexStream stream);
+
+/* K6 -- standalone residual add + scatter to the reference layout:
+ * out[dst[r]] = bf16(f32(residual[dst[r]]) + f32(y[r])), r < *n_rows.  Replaces out[mask] = ... and
+ * residual + hidden_states (:278-279/:96-97 and :321/:330) when the GEMM epilogue does not fuse it. */
+int vex_residual_scatter(const void* y, const void* residual, const int32_t* row_dst, const int32_t* n_rows,
+                         void* out, int rows_cap, int H, vexStream stream);
+
+/* Rows with padding_mask == False: out[f] = x[f] (residual + 0).  The reference leaves these rows
+ * uninitialised (torch.empty, :277); copying keeps the output deterministic and NaN-free. */
+int vex_copy_padded_rows(const void* x, const int32_t* flat_to_sorted, void* out, int n_flat, int H,
+                         vexStream stream);
+
+/* K3 -- grouped (two-expert) bf16 GEMM on tcgen05/TMEM fed by TMA, fp32 accumulate:
+ *     out = A_sorted . W_e^T  (+ T_e . Blora_e^T)       e = expert of the row (sorted order)
+ * Replaces the routed nn.Linear calls (:244-245, :278-279, :96-97 via MLP.forward :54-56) and the PEFT
+ * lora.Linear delta (scripts/cli.py:82-88).  `mode` selects the fused epilogue. */
+#define VEX_EPI_PLAIN 0    /* out[map(r)] = bf16(acc) */
+#define VEX_EPI_ROPE 1     /* QKV: rotary on columns < 2*hidden (heads of 128), scatter to token order
+                              (apply_rotary_pos_emb_index_bhs :188-193 fused) */
+#define VEX_EPI_SWIGLU 2   /* gate/up pair: out = silu(A.Wg^T) * (A.Wu^T)  (MLP.forward :55 fused) */
+#define VEX_EPI_RESIDUAL 3 /* out[map(r)] = bf16(acc) + residual[map(r)]  (:321, :330 fused) */
+
+typedef struct vexGemmArgs {
+  const void* a;            /* [rows_cap, K] bf16, sorted row order, row stride lda elements */
+  int64_t lda;
+  const void* w[2][2];      /* [expert][half]: weight [N, K] bf16 row-major (nn.Linear layout).
+                               half 1 is only used by VEX_EPI_SWIGLU (w[e][0] = gate_proj, w[e][1] = up_proj) */
+  int64_t ldw;
+  const void* lora_t[2];    /* per half: T = scaling * (A_sorted . lora_A^T) [rows_cap, r] bf16, or NULL */
+  int64_t ldt;
+  const void* lora_b[2][2]; /* [expert][half]: lora_B [N, r] bf16 row-major, or NULL (adapter absent) */
+  int32_t lora_r;           /* 0 = no LoRA; multiple of 8, <= 64 */
+  void* out;                /* bf16, row stride ldo */
+  int64_t ldo;
+  const int32_t* counts;    /* device: rows of expert 0 (vision), rows of expert 1 (language) */
+  const int32_t* row_map;   /* device [rows_cap]: output row of sorted row r, NULL = identity */
+  const void* residual;     /* VEX_EPI_RESIDUAL: bf16, same layout as out */
+  const void* rope_cos;     /* VEX_EPI_ROPE: [rope_len, 128] bf16 tables (RotaryEmbedding :162-170) */
+  const void* rope_sin;
+  const int64_t* position_ids; /* VEX_EPI_ROPE: int64 [B*L] (flat) */
+  const int32_t* sorted_to_flat;
+  int32_t rope_len;
+  int32_t rope_cols;        /* VEX_EPI_ROPE: columns [0, rope_cols) are rotated (2*hidden) */
+  int32_t rows_cap;         /* upper bound on total rows (B*L) */
+  int32_t N;                /* output features per weight (for SWIGLU: intermediate size) */
+  int32_t K;
+  int32_t mode;
+  int32_t single_expert;    /* 1: counts[0] rows all use w[0][*] (plain dense GEMM) */
+  float alpha;              /* VEX_EPI_PLAIN: out = bf16(alpha * acc) (LoRA scaling folded into T) */
+} vexGemmArgs;
+
+int vex_grouped_gemm(const vexGemmArgs* args, vexStream stream);
+
+/* K4 -- causal block-diagonal (varlen) flash attention over the token-order QKV buffer.
+ * Replaces attention_fn's prefill branch (:106-128): per sample, token i attends to tokens j <= i of
+ * the same sample (causality by token rank, not position_ids), scale = 128^-0.5, fp32 softmax.
+ *   qkv [T, 3, heads, 128] bf16 (q and k already rotated), out rows scattered through out_row_map
+ *   (token_to_sorted; NULL = identity) into [rows_cap, heads*128] bf16. */
+int vex_attention(const void* qkv, const int32_t* cu_seqlens, int B, int max_len_cap, int heads,
+                  const int32_t* out_row_map, void* out, float scale, vexStream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VEX_H_ */

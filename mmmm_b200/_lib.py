@@ -1,0 +1,87 @@
+"""ctypes binding of libvex.so (include/vex.h).  There is no CPU or PyTorch fallback: if the
+library cannot be built/loaded, importing callers fail loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+from . import build as _build
+
+_lock = threading.Lock()
+_lib = None
+
+VEX_OK = 0
+EPI_PLAIN, EPI_ROPE, EPI_SWIGLU, EPI_RESIDUAL = 0, 1, 2, 3
+COUNT_VISION, COUNT_LANGUAGE, COUNT_VALID, COUNT_MAXLEN, NUM_COUNTS = 0, 1, 2, 3, 4
+
+# every symbol include/vex.h declares (tests/test_abi.py checks the header against this list)
+SYMBOLS = [
+    "vex_abi_version", "vex_error_string", "vex_last_cuda_error", "vex_device_check", "vex_partition",
+    "vex_rmsnorm_gather", "vex_silu_mul", "vex_residual_scatter", "vex_copy_padded_rows", "vex_grouped_gemm",
+    "vex_attention",
+]
+
+
+class GemmArgs(C.Structure):
+    """Mirror of ``struct vexGemmArgs`` (include/vex.h)."""
+    _fields_ = [
+        ("a", C.c_void_p), ("lda", C.c_int64),
+        ("w", (C.c_void_p * 2) * 2), ("ldw", C.c_int64),
+        ("lora_t", C.c_void_p * 2), ("ldt", C.c_int64),
+        ("lora_b", (C.c_void_p * 2) * 2), ("lora_r", C.c_int32),
+        ("out", C.c_void_p), ("ldo", C.c_int64),
+        ("counts", C.c_void_p), ("row_map", C.c_void_p), ("residual", C.c_void_p),
+        ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("position_ids", C.c_void_p),
+        ("sorted_to_flat", C.c_void_p), ("rope_len", C.c_int32), ("rope_cols", C.c_int32),
+        ("rows_cap", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("mode", C.c_int32),
+        ("single_expert", C.c_int32), ("alpha", C.c_float),
+    ]
+
+
+class VexError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB
+        if not _build.is_fresh():
+            if os.path.isfile(_build.NVCC):
+                path = _build.build()
+            elif not os.path.isfile(path):
+                raise VexError("libvex.so is missing and nvcc is unavailable: the CUDA extension is required "
+                               "(there is no CPU fallback)")
+        L = C.CDLL(path)
+        p, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+        L.vex_abi_version.restype = C.c_int
+        L.vex_error_string.restype = C.c_char_p
+        L.vex_error_string.argtypes = [C.c_int]
+        L.vex_last_cuda_error.restype = C.c_int
+        L.vex_device_check.restype = C.c_int
+        L.vex_partition.argtypes = [p, p, i32, i32, p, p, p, p, p, p, p, p, p]
+        L.vex_rmsnorm_gather.argtypes = [p, p, i32, f32, p, p, p, i32, i32, p]
+        L.vex_silu_mul.argtypes = [p, p, p, p, i32, i32, p]
+        L.vex_residual_scatter.argtypes = [p, p, p, p, p, i32, i32, p]
+        L.vex_copy_padded_rows.argtypes = [p, p, p, i32, i32, p]
+        L.vex_grouped_gemm.argtypes = [C.POINTER(GemmArgs), p]
+        L.vex_attention.argtypes = [p, p, i32, i32, i32, p, p, f32, p]
+        for name in SYMBOLS:
+            fn = getattr(L, name)
+            if name not in ("vex_error_string",):
+                fn.restype = C.c_int
+        _lib = L
+        return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != VEX_OK:
+        L = lib()
+        msg = L.vex_error_string(rc).decode()
+        extra = f" (cudaError {L.vex_last_cuda_error()})" if rc == -3 else ""
+        raise VexError(f"{what}: {msg}{extra}")

@@ -1,0 +1,610 @@
+// K3 -- grouped (two-expert) bf16 GEMM for sm_100a: TMA -> shared memory -> tcgen05.mma -> TMEM -> fused
+// epilogue.  out[rows of expert e] = A . W_e^T (+ T . Blora_e^T).
+//
+// What it replaces in the reference: the routed nn.Linear calls of VisionExpertAttention / VisionExpertMLP
+// (modeling_cogvlm.py:244-245, :278-279, :96-97 through MLP.forward :54-56), the PEFT LoRA delta on top of them
+// (scripts/cli.py:82-88, conf/lora.yaml), and -- through the epilogue modes -- rotary (:188-193), SiLU-gate
+// (:55) and residual add + scatter (:321/:330 + the boolean-mask assignments).
+//
+// Design (one CTA per SM, persistent, 256 threads, warp-specialised):
+//   warp 0 / lane 0 : TMA producer.  Per 64-wide k-block one A box (128 rows) and two B half-boxes (BN/2 rows
+//                     each; for SwiGLU the halves come from gate_proj and up_proj so that accumulator columns
+//                     [0,128) and [128,256) hold matching gate/up outputs -- no repacked weight copy).
+//   warp 1 / lane 0 : MMA issuer, 4 x tcgen05.mma (M128 x BN x K16) per k-block, accumulators double-buffered
+//                     in TMEM (2 x BN columns) so the epilogue of tile i overlaps the mainloop of tile i+1.
+//                     LoRA is a K-extension: after the K loop the A operand switches to T = s*X.A^T and the B
+//                     operand to lora_B through separate tensor maps (lora_B changes every optimiser step, so
+//                     it cannot be folded into a static weight copy).
+//   warp 2          : TMEM allocate / free.
+//   warps 4..7      : epilogue.  tcgen05.ld (one row per thread) -> mode math with the reference's bf16
+//                     rounding points -> swizzled per-warp staging in shared memory -> coalesced 16-byte
+//                     global stores through the row map (scatter), masked by the live row count.
+// Ragged M without host sync: expert row counts are read from device memory; the tile list
+// (expert, m-tile, n-tile) is derived from them by every role identically; m-tiles are anchored at the
+// start of each expert's segment, TMA reads that run past the segment are harmless (row-independent math)
+// and the stores are masked.  Tiles are rasterised in groups of 16 m-tiles (n fastest within a group) so a
+// wave of 148 CTAs shares ~16 A tiles and ~9 B tiles in L2.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace vex {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+constexpr int GROUP_M = 16;
+
+struct alignas(64) GemmTmaps {
+  CUtensorMap a;         // activations [rows_cap, K]
+  CUtensorMap w[2][2];   // [expert][half] weights [N, K]
+  CUtensorMap t[2];      // [half] LoRA T = s * X.A^T [rows_cap, r]
+  CUtensorMap lb[2][2];  // [expert][half] lora_B [N, r]
+};
+
+struct GemmDev {
+  const int32_t* counts;
+  const int32_t* row_map;
+  __nv_bfloat16* out;
+  const __nv_bfloat16* residual;
+  const __nv_bfloat16* rope_cos;
+  const __nv_bfloat16* rope_sin;
+  const int64_t* position_ids;
+  const int32_t* sorted_to_flat;
+  int64_t ldo;
+  float alpha;
+  int rope_len, rope_cols;
+  int rows_cap, N, K, mode, single_expert;
+  int lora_steps;  // 64-wide k-blocks along r (0 = no LoRA)
+  int lora_mask;   // bit e: expert e has an adapter
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = BN == 256 ? 4 : 8;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int HALF_B = B_BYTES / 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int PANEL = BN >= 128 ? 128 : BN;  // epilogue panel width (columns)
+  static constexpr int PANEL_BYTES = PANEL * 2;       // staging row pitch
+  static constexpr int EPI_WARP_BYTES = 32 * PANEL_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int NUM_BARS = 2 * STAGES + 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * EPI_WARP_BYTES + NUM_BARS * 8 + 16 + 1024;
+};
+
+struct TileCoord {
+  int e, m, n;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(int tile, int mt0, int mt1, int n_tiles) {
+  TileCoord c;
+  int mt_e = mt0;
+  c.e = 0;
+  const int t0 = mt0 * n_tiles;
+  if (tile >= t0) {
+    c.e = 1;
+    tile -= t0;
+    mt_e = mt1;
+  }
+  const int per_group = GROUP_M * n_tiles;
+  const int g = tile / per_group;
+  const int r = tile - g * per_group;
+  const int m_lo = g * GROUP_M;
+  const int gm = min(GROUP_M, mt_e - m_lo);
+  c.n = r / gm;
+  c.m = m_lo + (r - c.n * gm);
+  return c;
+}
+
+__device__ __forceinline__ float silu_acc(float x) { return x / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+
+// 32 fp32 accumulator values of this thread's row -> bf16 -> swizzled staging (4 x 16 B pieces)
+__device__ __forceinline__ void stage_piece32(uint32_t stage_row_addr, int first_piece, int lane,
+                                              const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int piece = first_piece + i;
+    const uint32_t addr = stage_row_addr + static_cast<uint32_t>((piece ^ (lane & 7)) << 4);
+    st_shared_v4(addr, pack_bf16(v[8 * i + 0], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                 pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+  }
+}
+
+__device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* p, float (&o)[32]) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 u = __ldg(q + i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      o[8 * i + 2 * j] = bf16_lo(w[j]);
+      o[8 * i + 2 * j + 1] = bf16_hi(w[j]);
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    k3_grouped_gemm(const __grid_constant__ GemmTmaps tm, const GemmDev p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte aligned tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + 4 * Cfg::EPI_WARP_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + Cfg::NUM_BARS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_base_smem, Cfg::TMEM_COLS);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm.a);
+    tma_prefetch_desc(&tm.w[0][0]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  // ---- tile list, derived identically by every role from the device-side counts ----
+  const int cnt0 = min(max(p.counts[0], 0), p.rows_cap);
+  const int cnt1 = p.single_expert ? 0 : min(max(p.counts[1], 0), p.rows_cap - cnt0);
+  const int mt0 = (cnt0 + BM - 1) / BM;
+  const int mt1 = (cnt1 + BM - 1) / BM;
+  const bool swiglu = p.mode == VEX_EPI_SWIGLU;
+  const int n_span = swiglu ? BN / 2 : BN;  // output columns per tile
+  const int n_tiles = (p.N + n_span - 1) / n_span;
+  const int total_tiles = (mt0 + mt1) * n_tiles;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    // =============================== TMA producer ===============================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord c = decode_tile(tile, mt0, mt1, n_tiles);
+      const int row0 = (c.e ? cnt0 : 0) + c.m * BM;
+      const int nrow0 = c.n * n_span;
+      const int nrow1 = swiglu ? nrow0 : nrow0 + BN / 2;
+      const CUtensorMap* w0 = &tm.w[c.e][0];
+      const CUtensorMap* w1 = swiglu ? &tm.w[c.e][1] : w0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sb = sa + Cfg::A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+        tma_load_2d(sa, &tm.a, &full_bar[stage], kb * BK, row0);
+        tma_load_2d(sb, w0, &full_bar[stage], kb * BK, nrow0);
+        tma_load_2d(sb + Cfg::HALF_B, w1, &full_bar[stage], kb * BK, nrow1);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if ((p.lora_mask >> c.e) & 1) {
+        const int halves = swiglu ? 2 : 1;
+        for (int h = 0; h < halves; ++h) {
+          for (int ls = 0; ls < p.lora_steps; ++ls) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + Cfg::A_BYTES;
+            if (swiglu) {
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::HALF_B);
+              tma_load_2d(sa, &tm.t[h], &full_bar[stage], ls * BK, row0);
+              tma_load_2d(sb, &tm.lb[c.e][h], &full_bar[stage], ls * BK, nrow0);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+              tma_load_2d(sa, &tm.t[0], &full_bar[stage], ls * BK, row0);
+              tma_load_2d(sb, &tm.lb[c.e][0], &full_bar[stage], ls * BK, nrow0);
+              tma_load_2d(sb + Cfg::HALF_B, &tm.lb[c.e][0], &full_bar[stage], ls * BK, nrow1);
+            }
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // =============================== MMA issuer ===============================
+    constexpr uint32_t idesc_full = umma_idesc_bf16(BM, BN);
+    constexpr uint32_t idesc_half = umma_idesc_bf16(BM, BN / 2);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord c = decode_tile(tile, mt0, mt1, n_tiles);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+      uint32_t accumulate = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint64_t da = umma_desc_kmajor_sw128(sa);
+        const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // +32 bytes per K=16 step inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+          umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc_full, accumulate);
+          accumulate = 1;
+        }
+        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if ((p.lora_mask >> c.e) & 1) {
+        const int halves = swiglu ? 2 : 1;
+        for (int h = 0; h < halves; ++h) {
+          for (int ls = 0; ls < p.lora_steps; ++ls) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint64_t da = umma_desc_kmajor_sw128(sa);
+            const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::A_BYTES);
+            const uint32_t d_half = d_tmem + static_cast<uint32_t>(swiglu ? h * (BN / 2) : 0);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_ss(d_half, da + 2 * k, db + 2 * k, swiglu ? idesc_half : idesc_full, 1u);
+            umma_commit(&empty_bar[stage]);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+      umma_commit(&tmem_full[acc]);  // accumulator of this tile complete -> epilogue
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // =============================== epilogue ===============================
+    constexpr int PANEL = Cfg::PANEL;
+    constexpr int PITCH = Cfg::PANEL_BYTES;
+    constexpr int LPR = PITCH / 16;  // lanes per staged row during write-out
+    constexpr int RPI = 32 / LPR;    // rows per write-out iteration
+    const int ew = warp - 4;         // == warp % 4: the TMEM lane quarter this warp may read
+    const uint32_t stage_base = smem_u32(epi_smem + ew * Cfg::EPI_WARP_BYTES);
+    const uint32_t stage_row = stage_base + static_cast<uint32_t>(lane * PITCH);
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+
+    // coalesced write-out of one staged panel: out[g, col0 + ...] for the 32 rows of this warp
+    auto write_panel = [&](int g_row, int col0, bool add_residual) {
+#pragma unroll 4
+      for (int it = 0; it < 32 / RPI; ++it) {
+        const int rr = it * RPI + lane / LPR;
+        const int piece = lane % LPR;
+        const int g = __shfl_sync(0xffffffffu, g_row, rr);
+        const int col = col0 + piece * 8;
+        if (g >= 0 && col < p.N) {
+          uint4 v = ld_shared_v4(stage_base + static_cast<uint32_t>(rr * PITCH + ((piece ^ (rr & 7)) << 4)));
+          const int64_t off = static_cast<int64_t>(g) * p.ldo + col;
+          if (add_residual) {
+            const uint4 r4 = ld_stream(p.residual + off);
+            const uint32_t a[4] = {v.x, v.y, v.z, v.w}, b[4] = {r4.x, r4.y, r4.z, r4.w};
+            uint32_t* vp = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              vp[j] = pack_bf16(bf16_lo(a[j]) + bf16_lo(b[j]), bf16_hi(a[j]) + bf16_hi(b[j]));
+          }
+          *reinterpret_cast<uint4*>(p.out + off) = v;
+        }
+      }
+    };
+
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord c = decode_tile(tile, mt0, mt1, n_tiles);
+      const int r_local = c.m * BM + ew * 32 + lane;
+      const bool valid = r_local < (c.e ? cnt1 : cnt0);
+      const int s_row = (c.e ? cnt0 : 0) + r_local;
+      int g_row = -1;
+      int pos = 0;
+      if (valid) {
+        g_row = p.row_map ? p.row_map[s_row] : s_row;
+        if (p.mode == VEX_EPI_ROPE) {
+          const int64_t pz = p.position_ids[p.sorted_to_flat[s_row]];
+          pos = static_cast<int>(min(max(pz, int64_t(0)), int64_t(p.rope_len - 1)));
+        }
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc = t_lane + static_cast<uint32_t>(acc * BN);
+      uint32_t raw[32];
+      float v[32];
+
+      if (p.mode == VEX_EPI_SWIGLU) {
+        if constexpr (BN == 256) {
+#pragma unroll 1
+          for (int q = 0; q < 4; ++q) {
+            uint32_t raw_u[32];
+            tmem_ld_32x32b_x32(t_acc + q * 32, raw);
+            tmem_ld_32x32b_x32(t_acc + 128 + q * 32, raw_u);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float g = bf16r(__uint_as_float(raw[j]));    // gate_proj output, bf16 like the eager Linear
+              const float u = bf16r(__uint_as_float(raw_u[j]));  // up_proj output
+              v[j] = bf16r(silu_acc(g)) * u;                     // silu -> bf16, product -> bf16 (on store)
+            }
+            stage_piece32(stage_row, q * 4, lane, v);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          write_panel(g_row, c.n * 128, false);
+          __syncwarp();
+        }
+      } else {
+        constexpr int NPANEL = BN / PANEL;
+#pragma unroll 1
+        for (int pn = 0; pn < NPANEL; ++pn) {
+          const int col0 = c.n * BN + pn * PANEL;
+          if (p.mode == VEX_EPI_ROPE && col0 < p.rope_cols) {
+            if constexpr (PANEL == 128) {
+              // one head: pairs (j, j + 64); thread owns the whole row so both halves are local
+#pragma unroll 1
+              for (int q = 0; q < 2; ++q) {
+                uint32_t raw_hi[32];
+                tmem_ld_32x32b_x32(t_acc + pn * PANEL + q * 32, raw);
+                tmem_ld_32x32b_x32(t_acc + pn * PANEL + 64 + q * 32, raw_hi);
+                const __nv_bfloat16* cr = p.rope_cos + static_cast<int64_t>(pos) * 128 + q * 32;
+                const __nv_bfloat16* sr = p.rope_sin + static_cast<int64_t>(pos) * 128 + q * 32;
+                uint4 ct[4], st[4];  // packed bf16 table entries for columns q*32 .. q*32+31
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  ct[i] = __ldg(reinterpret_cast<const uint4*>(cr) + i);
+                  st[i] = __ldg(reinterpret_cast<const uint4*>(sr) + i);
+                }
+                tmem_ld_wait();
+                // x1 = q[j], x2 = q[j + 64] as the eager bf16 Linear would have produced them
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  raw[j] = __float_as_uint(bf16r(__uint_as_float(raw[j])));
+                  raw_hi[j] = __float_as_uint(bf16r(__uint_as_float(raw_hi[j])));
+                }
+                // first half: q*cos + rotate_half(q)*sin, rotate_half(q)[j] = -q[j + 64]; every product and the
+                // sum are rounded to bf16 like the eager ops (the sum is rounded by the bf16 pack)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const uint32_t cw = reinterpret_cast<const uint32_t*>(ct)[j >> 1];
+                  const uint32_t sw = reinterpret_cast<const uint32_t*>(st)[j >> 1];
+                  const float cj = (j & 1) ? bf16_hi(cw) : bf16_lo(cw);
+                  const float sj = (j & 1) ? bf16_hi(sw) : bf16_lo(sw);
+                  v[j] = bf16r(__uint_as_float(raw[j]) * cj) - bf16r(__uint_as_float(raw_hi[j]) * sj);
+                }
+                stage_piece32(stage_row, q * 4, lane, v);
+                // second half uses the table entries of column j + 64 (equal to column j for the reference's
+                // cat(freqs, freqs) table, but read them anyway)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  ct[i] = __ldg(reinterpret_cast<const uint4*>(cr + 64) + i);
+                  st[i] = __ldg(reinterpret_cast<const uint4*>(sr + 64) + i);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const uint32_t cw = reinterpret_cast<const uint32_t*>(ct)[j >> 1];
+                  const uint32_t sw = reinterpret_cast<const uint32_t*>(st)[j >> 1];
+                  const float cj = (j & 1) ? bf16_hi(cw) : bf16_lo(cw);
+                  const float sj = (j & 1) ? bf16_hi(sw) : bf16_lo(sw);
+                  v[j] = bf16r(__uint_as_float(raw_hi[j]) * cj) + bf16r(__uint_as_float(raw[j]) * sj);
+                }
+                stage_piece32(stage_row, 8 + q * 4, lane, v);
+              }
+            }
+          } else {
+#pragma unroll 1
+            for (int q = 0; q < PANEL / 32; ++q) {
+              tmem_ld_32x32b_x32(t_acc + pn * PANEL + q * 32, raw);
+              tmem_ld_wait();
+              if (p.mode == VEX_EPI_PLAIN) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+              }
+              stage_piece32(stage_row, q * 4, lane, v);
+            }
+          }
+          if (pn == NPANEL - 1) {  // every TMEM read of this accumulator is done: hand it back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          } else {
+            __syncwarp();
+          }
+          write_panel(g_row, col0, p.mode == VEX_EPI_RESIDUAL);
+          __syncwarp();
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// 2D bf16 row-major [rows, cols] with row stride ld (elements); box = 64 columns x box_rows, 128B swizzle
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return VEX_E_CUDA;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16 != 0) return VEX_E_INVALID;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    g_last_cuda_error = static_cast<int>(r);
+    return VEX_E_CUDA;
+  }
+  return VEX_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int BN>
+static int launch_gemm(const GemmTmaps& tm, const GemmDev& dev, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    VEX_CUDA_TRY(cudaFuncSetAttribute(k3_grouped_gemm<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      GemmCfg<BN>::SMEM_BYTES));
+    configured = true;
+  }
+  k3_grouped_gemm<BN><<<num_sms(), GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, s>>>(tm, dev);
+  VEX_LAUNCH_CHECK();
+  return VEX_OK;
+}
+
+}  // namespace vex
+
+extern "C" int vex_grouped_gemm(const vexGemmArgs* a, vexStream stream) {
+  using namespace vex;
+  if (!a || !a->a || !a->out || !a->counts || !a->w[0][0]) return VEX_E_INVALID;
+  if (a->rows_cap <= 0 || a->N <= 0 || a->K <= 0) return VEX_E_INVALID;
+  if (a->N % 8 != 0 || a->K % 8 != 0 || a->ldo % 8 != 0 || a->lda % 8 != 0 || a->ldw % 8 != 0)
+    return VEX_E_UNSUPPORTED;
+  if (a->mode < VEX_EPI_PLAIN || a->mode > VEX_EPI_RESIDUAL) return VEX_E_INVALID;
+  const bool swiglu = a->mode == VEX_EPI_SWIGLU;
+  if (!a->single_expert && !a->w[1][0]) return VEX_E_INVALID;
+  if (swiglu && (!a->w[0][1] || (!a->single_expert && !a->w[1][1]))) return VEX_E_INVALID;
+  if (a->mode == VEX_EPI_RESIDUAL && !a->residual) return VEX_E_INVALID;
+  if (a->mode == VEX_EPI_ROPE) {
+    if (!a->rope_cos || !a->rope_sin || !a->position_ids || !a->sorted_to_flat || a->rope_len <= 0)
+      return VEX_E_INVALID;
+    if (a->rope_cols % 128 != 0) return VEX_E_UNSUPPORTED;  // heads of 128
+  }
+  const bool small_n = a->N <= 64 && a->mode == VEX_EPI_PLAIN;
+  const int BN = small_n ? 64 : 256;
+  const int half_rows = swiglu ? 128 : BN / 2;
+
+  GemmTmaps tm;
+  std::memset(&tm, 0, sizeof(tm));
+  int rc;
+  if ((rc = make_tmap_2d(&tm.a, a->a, a->rows_cap, a->K, a->lda, BM)) != VEX_OK) return rc;
+  const int n_exp = a->single_expert ? 1 : 2;
+  for (int e = 0; e < n_exp; ++e)
+    for (int h = 0; h < (swiglu ? 2 : 1); ++h)
+      if ((rc = make_tmap_2d(&tm.w[e][h], a->w[e][h], a->N, a->K, a->ldw, half_rows)) != VEX_OK) return rc;
+
+  GemmDev dev;
+  std::memset(&dev, 0, sizeof(dev));
+  if (a->lora_r > 0) {
+    if (a->lora_r % 8 != 0 || a->ldt % 8 != 0) return VEX_E_UNSUPPORTED;
+    if (small_n) return VEX_E_UNSUPPORTED;
+    dev.lora_steps = ceil_div(a->lora_r, BK);
+    for (int h = 0; h < (swiglu ? 2 : 1); ++h) {
+      bool any = false;
+      for (int e = 0; e < n_exp; ++e) {
+        if (!a->lora_b[e][h]) continue;
+        if (swiglu && !a->lora_b[e][1 - h]) return VEX_E_UNSUPPORTED;  // gate and up adapters come in pairs
+        any = true;
+        dev.lora_mask |= 1 << e;
+        if ((rc = make_tmap_2d(&tm.lb[e][h], a->lora_b[e][h], a->N, a->lora_r, a->lora_r, half_rows)) != VEX_OK)
+          return rc;
+      }
+      if (any) {
+        if (!a->lora_t[h]) return VEX_E_INVALID;
+        if ((rc = make_tmap_2d(&tm.t[h], a->lora_t[h], a->rows_cap, a->lora_r, a->ldt, BM)) != VEX_OK) return rc;
+      }
+    }
+    if (dev.lora_mask == 0) dev.lora_steps = 0;
+  }
+  dev.counts = a->counts;
+  dev.row_map = a->row_map;
+  dev.out = static_cast<__nv_bfloat16*>(a->out);
+  dev.residual = static_cast<const __nv_bfloat16*>(a->residual);
+  dev.rope_cos = static_cast<const __nv_bfloat16*>(a->rope_cos);
+  dev.rope_sin = static_cast<const __nv_bfloat16*>(a->rope_sin);
+  dev.position_ids = a->position_ids;
+  dev.sorted_to_flat = a->sorted_to_flat;
+  dev.ldo = a->ldo;
+  dev.alpha = a->alpha;
+  dev.rope_len = a->rope_len;
+  dev.rope_cols = a->rope_cols;
+  dev.rows_cap = a->rows_cap;
+  dev.N = a->N;
+  dev.K = a->K;
+  dev.mode = a->mode;
+  dev.single_expert = a->single_expert;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return small_n ? launch_gemm<64>(tm, dev, s) : launch_gemm<256>(tm, dev, s);
+}

@@ -1,0 +1,22 @@
+// K4 entry point: argument checks and implementation choice for the causal varlen attention.
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace vex {
+int launch_attention_mma(const void* qkv, const int32_t* cu_seqlens, int B, int max_len_cap, int heads,
+                         const int32_t* out_row_map, void* out, float scale, cudaStream_t s);
+#ifdef VEX_HAVE_ATTN_TC
+int launch_attention_tc(const void* qkv, const int32_t* cu_seqlens, int B, int max_len_cap, int heads,
+                        const int32_t* out_row_map, void* out, float scale, int rows_cap, cudaStream_t s);
+#endif
+}  // namespace vex
+
+extern "C" int vex_attention(const void* qkv, const int32_t* cu_seqlens, int B, int max_len_cap, int heads,
+                             const int32_t* out_row_map, void* out, float scale, vexStream stream) {
+  if (!qkv || !cu_seqlens || !out || B <= 0 || max_len_cap <= 0 || heads <= 0) return VEX_E_INVALID;
+  if (B > 65535 || heads > 65535) return VEX_E_UNSUPPORTED;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return vex::launch_attention_mma(qkv, cu_seqlens, B, max_len_cap, heads, out_row_map, out, scale, s);
+}

@@ -1,0 +1,244 @@
+"""Tensor-level wrappers of the C ABI (include/vex.h), registered as ``torch.library`` custom ops
+(namespace ``vex``).  Every op launches hand-written sm_100a kernels from libvex.so on the current
+CUDA stream; outputs are pre-allocated by the caller and mutated in place.  CPU tensors are an
+error -- there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import EPI_PLAIN, EPI_RESIDUAL, EPI_ROPE, EPI_SWIGLU, GemmArgs  # noqa: F401
+
+_BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a tensor")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (libvex has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------ K1
+@torch.library.custom_op("vex::partition", mutates_args=(
+        "sorted_to_flat", "flat_to_sorted", "sorted_to_token", "token_to_sorted", "token_to_flat", "cu_seqlens",
+        "counts", "scratch"))
+def partition(token_type_ids: torch.Tensor, padding_mask: torch.Tensor, sorted_to_flat: torch.Tensor,
+              flat_to_sorted: torch.Tensor, sorted_to_token: torch.Tensor, token_to_sorted: torch.Tensor,
+              token_to_flat: torch.Tensor, cu_seqlens: torch.Tensor, counts: torch.Tensor,
+              scratch: torch.Tensor) -> None:
+    """K1 (vex_partition): replaces get_expert_mask + boolean-mask nonzero (modeling_cogvlm.py:58-70)."""
+    _dev(token_type_ids, "token_type_ids", torch.int64)
+    _dev(padding_mask, "padding_mask", torch.bool)
+    if token_type_ids.dim() != 2 or token_type_ids.shape != padding_mask.shape:
+        raise ValueError("token_type_ids and padding_mask must both be [B, L]")
+    B, L = token_type_ids.shape
+    for name, t, n in (("sorted_to_flat", sorted_to_flat, B * L), ("flat_to_sorted", flat_to_sorted, B * L),
+                       ("sorted_to_token", sorted_to_token, B * L), ("token_to_sorted", token_to_sorted, B * L),
+                       ("token_to_flat", token_to_flat, B * L), ("cu_seqlens", cu_seqlens, B + 1),
+                       ("counts", counts, _lib.NUM_COUNTS), ("scratch", scratch, 4 * B)):
+        _dev(t, name, torch.int32)
+        if t.numel() < n:
+            raise ValueError(f"{name} needs at least {n} int32 elements")
+    rc = _lib.lib().vex_partition(token_type_ids.data_ptr(), padding_mask.data_ptr(), B, L,
+                                  sorted_to_flat.data_ptr(), flat_to_sorted.data_ptr(), sorted_to_token.data_ptr(),
+                                  token_to_sorted.data_ptr(), token_to_flat.data_ptr(), cu_seqlens.data_ptr(),
+                                  counts.data_ptr(), scratch.data_ptr(), _stream())
+    _lib.check(rc, "vex_partition")
+
+
+# ------------------------------------------------------------------------------------------ K2
+@torch.library.custom_op("vex::rmsnorm_gather", mutates_args=("out",))
+def rmsnorm_gather(x: torch.Tensor, weight: torch.Tensor, eps: float, row_src: Optional[torch.Tensor],
+                   n_rows: torch.Tensor, out: torch.Tensor) -> None:
+    """K2 (vex_rmsnorm_gather): RMSNorm.forward (modeling_cogvlm.py:36-41) fused with the row gather."""
+    _dev(x, "x", _BF16)
+    _dev(out, "out", _BF16)
+    _dev(weight, "weight")
+    if weight.dtype not in (_BF16, torch.float32):
+        raise TypeError("RMSNorm weight must be bf16 or fp32")
+    H = x.shape[-1]
+    if weight.numel() != H or out.shape[-1] != H:
+        raise ValueError("hidden size mismatch")
+    if row_src is not None:
+        _dev(row_src, "row_src", torch.int32)
+    _dev(n_rows, "n_rows", torch.int32)
+    rows_cap = out.numel() // H
+    rc = _lib.lib().vex_rmsnorm_gather(x.data_ptr(), weight.data_ptr(), int(weight.dtype == torch.float32),
+                                       float(eps), _ptr(row_src), n_rows.data_ptr(), out.data_ptr(), rows_cap, H,
+                                       _stream())
+    _lib.check(rc, "vex_rmsnorm_gather")
+
+
+# ------------------------------------------------------------------------------------------ K5 / K6
+@torch.library.custom_op("vex::silu_mul", mutates_args=("out",))
+def silu_mul(gate: torch.Tensor, up: torch.Tensor, n_rows: torch.Tensor, out: torch.Tensor) -> None:
+    """K5 (vex_silu_mul): act_fn(gate) * up (modeling_cogvlm.py:55)."""
+    for n, t in (("gate", gate), ("up", up), ("out", out)):
+        _dev(t, n, _BF16)
+    if gate.shape != up.shape or gate.shape != out.shape:
+        raise ValueError("gate/up/out shapes differ")
+    I = gate.shape[-1]
+    rc = _lib.lib().vex_silu_mul(gate.data_ptr(), up.data_ptr(), out.data_ptr(), _dev(n_rows, "n_rows",
+                                 torch.int32).data_ptr(), gate.numel() // I, I, _stream())
+    _lib.check(rc, "vex_silu_mul")
+
+
+@torch.library.custom_op("vex::residual_scatter", mutates_args=("out",))
+def residual_scatter(y: torch.Tensor, residual: torch.Tensor, row_dst: Optional[torch.Tensor],
+                     n_rows: torch.Tensor, out: torch.Tensor) -> None:
+    """K6 (vex_residual_scatter): out[dst[r]] = residual[dst[r]] + y[r] (modeling_cogvlm.py:278-279 + :321)."""
+    for n, t in (("y", y), ("residual", residual), ("out", out)):
+        _dev(t, n, _BF16)
+    H = y.shape[-1]
+    if residual.shape[-1] != H or out.shape != residual.shape:
+        raise ValueError("shape mismatch")
+    rc = _lib.lib().vex_residual_scatter(y.data_ptr(), residual.data_ptr(), _ptr(row_dst),
+                                         _dev(n_rows, "n_rows", torch.int32).data_ptr(), out.data_ptr(),
+                                         y.numel() // H, H, _stream())
+    _lib.check(rc, "vex_residual_scatter")
+
+
+@torch.library.custom_op("vex::copy_padded_rows", mutates_args=("out",))
+def copy_padded_rows(x: torch.Tensor, flat_to_sorted: torch.Tensor, out: torch.Tensor) -> None:
+    """Rows with padding_mask == False: out = x (the reference leaves them uninitialised, :277)."""
+    _dev(x, "x", _BF16)
+    _dev(out, "out", _BF16)
+    _dev(flat_to_sorted, "flat_to_sorted", torch.int32)
+    H = x.shape[-1]
+    rc = _lib.lib().vex_copy_padded_rows(x.data_ptr(), flat_to_sorted.data_ptr(), out.data_ptr(), x.numel() // H, H,
+                                         _stream())
+    _lib.check(rc, "vex_copy_padded_rows")
+
+
+# ------------------------------------------------------------------------------------------ K3
+def grouped_gemm_raw(a: torch.Tensor, w: Sequence[Optional[torch.Tensor]], out: torch.Tensor, counts: torch.Tensor,
+                     mode: int, *, row_map: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+                     lora_t: Sequence[Optional[torch.Tensor]] = (None, None),
+                     lora_b: Sequence[Optional[torch.Tensor]] = (None, None, None, None), lora_r: int = 0,
+                     rope: Optional[tuple] = None, rope_cols: int = 0, single_expert: bool = False,
+                     alpha: float = 1.0, n_out: Optional[int] = None) -> None:
+    """K3 (vex_grouped_gemm).  ``w`` = [vision_w0, vision_w1, language_w0, language_w1] ([N, K] each; the *_w1
+    entries are up_proj for SWIGLU, else None).  ``lora_b`` likewise; ``lora_t`` = [T_half0, T_half1].
+    ``rope`` = (cos [S,128], sin [S,128], position_ids int64 [B*L], sorted_to_flat int32)."""
+    _dev(a, "a", _BF16)
+    _dev(out, "out", _BF16)
+    _dev(counts, "counts", torch.int32)
+    K = a.shape[-1]
+    rows_cap = a.numel() // K
+    w = list(w) + [None] * (4 - len(w))
+    args = GemmArgs()
+    args.a, args.lda = a.data_ptr(), K
+    N = None
+    for i, wt in enumerate(w):
+        if wt is None:
+            continue
+        _dev(wt, f"w[{i}]", _BF16)
+        if wt.dim() != 2 or wt.shape[1] != K:
+            raise ValueError(f"w[{i}] must be [N, {K}], got {tuple(wt.shape)}")
+        N = wt.shape[0] if N is None else N
+        if wt.shape[0] != N:
+            raise ValueError("all weights of one grouped GEMM must share N")
+        args.w[i // 2][i % 2] = wt.data_ptr()
+    if N is None:
+        raise ValueError("no weights given")
+    args.ldw = K
+    if lora_r:
+        for h, t in enumerate(lora_t):
+            if t is not None:
+                _dev(t, f"lora_t[{h}]", _BF16)
+                args.lora_t[h] = t.data_ptr()
+                args.ldt = t.shape[-1]
+        lora_b = list(lora_b) + [None] * (4 - len(lora_b))
+        for i, bt in enumerate(lora_b):
+            if bt is None:
+                continue
+            _dev(bt, f"lora_b[{i}]", _BF16)
+            if tuple(bt.shape) != (N, lora_r):
+                raise ValueError(f"lora_b[{i}] must be [{N}, {lora_r}]")
+            args.lora_b[i // 2][i % 2] = bt.data_ptr()
+        args.lora_r = lora_r
+    args.out, args.ldo = out.data_ptr(), out.shape[-1]
+    args.counts = counts.data_ptr()
+    args.row_map = _ptr(None if row_map is None else _dev(row_map, "row_map", torch.int32))
+    if residual is not None:
+        _dev(residual, "residual", _BF16)
+        if residual.shape[-1] != out.shape[-1]:
+            raise ValueError("residual/out layout mismatch")
+        args.residual = residual.data_ptr()
+    elif mode == EPI_RESIDUAL:
+        args.residual = out.data_ptr()  # in place: out[row] += acc (each 16-byte piece is read then written once)
+    if rope is not None:
+        cos, sin, pos, s2f = rope
+        _dev(cos, "cos", _BF16), _dev(sin, "sin", _BF16)
+        _dev(pos, "position_ids", torch.int64), _dev(s2f, "sorted_to_flat", torch.int32)
+        if cos.shape[-1] != 128 or cos.shape != sin.shape:
+            raise ValueError("rotary tables must be [S, 128]")
+        args.rope_cos, args.rope_sin = cos.data_ptr(), sin.data_ptr()
+        args.position_ids, args.sorted_to_flat = pos.data_ptr(), s2f.data_ptr()
+        args.rope_len, args.rope_cols = cos.shape[0], rope_cols
+    args.rows_cap, args.N, args.K, args.mode = rows_cap, (n_out or N), K, mode
+    args.single_expert = int(single_expert)
+    args.alpha = alpha
+    rc = _lib.lib().vex_grouped_gemm(C.byref(args), _stream())
+    _lib.check(rc, "vex_grouped_gemm")
+
+
+@torch.library.custom_op("vex::grouped_gemm", mutates_args=("out",))
+def grouped_gemm(a: torch.Tensor, w_vision: torch.Tensor, w_language: Optional[torch.Tensor], out: torch.Tensor,
+                 counts: torch.Tensor, row_map: Optional[torch.Tensor], alpha: float) -> None:
+    """Plain grouped GEMM as a registered op (the fused-epilogue variants are reached through
+    ``vex::visual_expert_layer``): out[map(r)] = bf16(alpha * a[r] . w_e^T)."""
+    grouped_gemm_raw(a, [w_vision, None, w_language, None], out, counts, EPI_PLAIN, row_map=row_map, alpha=alpha,
+                     single_expert=w_language is None)
+
+
+@torch.library.custom_op("vex::grouped_gemm_fused", mutates_args=("out",))
+def grouped_gemm_fused(a: torch.Tensor, w: List[Optional[torch.Tensor]], out: torch.Tensor, counts: torch.Tensor,
+                       mode: int, row_map: Optional[torch.Tensor], residual: Optional[torch.Tensor],
+                       lora_t: List[Optional[torch.Tensor]], lora_b: List[Optional[torch.Tensor]], lora_r: int,
+                       rope: List[torch.Tensor], rope_cols: int, single_expert: bool, alpha: float) -> None:
+    """K3 with a fused epilogue (``mode`` = EPI_*), LoRA K-extension and scatter; see ``grouped_gemm_raw``."""
+    grouped_gemm_raw(a, w, out, counts, mode, row_map=row_map, residual=residual, lora_t=lora_t, lora_b=lora_b,
+                     lora_r=lora_r, rope=tuple(rope) if len(rope) else None, rope_cols=rope_cols,
+                     single_expert=single_expert, alpha=alpha)
+
+
+# ------------------------------------------------------------------------------------------ K4
+@torch.library.custom_op("vex::attention", mutates_args=("out",))
+def attention(qkv: torch.Tensor, cu_seqlens: torch.Tensor, batch: int, max_len_cap: int, heads: int,
+              out_row_map: Optional[torch.Tensor], out: torch.Tensor, scale: float) -> None:
+    """K4 (vex_attention): causal block-diagonal attention over token-order QKV [T, 3, heads, 128]
+    (attention_fn prefill branch, modeling_cogvlm.py:106-128)."""
+    _dev(qkv, "qkv", _BF16)
+    _dev(out, "out", _BF16)
+    _dev(cu_seqlens, "cu_seqlens", torch.int32)
+    if qkv.shape[-1] != 3 * heads * 128:
+        raise ValueError("qkv rows must be [3 * heads * 128] wide (head_dim 128 only)")
+    if out_row_map is not None:
+        _dev(out_row_map, "out_row_map", torch.int32)
+    rc = _lib.lib().vex_attention(qkv.data_ptr(), cu_seqlens.data_ptr(), batch, max_len_cap, heads,
+                                  _ptr(out_row_map), out.data_ptr(), float(scale), _stream())
+    _lib.check(rc, "vex_attention")
+
+
+for _op in (partition, rmsnorm_gather, silu_mul, residual_scatter, copy_padded_rows, grouped_gemm, grouped_gemm_fused,
+            attention):
+    _op.register_fake(lambda *a, **k: None)

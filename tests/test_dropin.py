@@ -1,0 +1,131 @@
+"""CPU-side checks of the drop-in boundary: module tree / state-dict keys equal the
+reference's, parameters move over without copies, PEFT-style wrappers are read through, errors are loud."""
+import pytest
+import torch
+from torch import nn
+
+from mmmm_b200.modeling_cogvlm import CogVLMDecoderLayer, VexConfig, swap_decoder_layers
+from mmmm_b200.peft_compat import MockLoraLinear, attach_mock_lora, resolve_linear, resolve_norm
+from oracle import reference_loader as RL
+
+EXPECTED_KEYS = {
+    "self_attn.rotary_emb.inv_freq": (64,),
+    "self_attn.vision_expert_query_key_value.weight": (768, 256),
+    "self_attn.vision_expert_dense.weight": (256, 256),
+    "self_attn.language_expert_query_key_value.weight": (768, 256),
+    "self_attn.language_expert_dense.weight": (256, 256),
+    "mlp.language_mlp.gate_proj.weight": (320, 256),
+    "mlp.language_mlp.up_proj.weight": (320, 256),
+    "mlp.language_mlp.down_proj.weight": (256, 320),
+    "mlp.vision_mlp.gate_proj.weight": (320, 256),
+    "mlp.vision_mlp.up_proj.weight": (320, 256),
+    "mlp.vision_mlp.down_proj.weight": (256, 320),
+    "input_layernorm.weight": (256,),
+    "post_attention_layernorm.weight": (256,),
+}
+CFG = dict(hidden_size=256, intermediate_size=320, num_attention_heads=2)
+
+
+def test_state_dict_keys_and_shapes():
+    layer = CogVLMDecoderLayer(VexConfig(**CFG))
+    got = {k: tuple(v.shape) for k, v in layer.state_dict().items()}
+    assert got == EXPECTED_KEYS
+    assert type(layer).__name__ == "CogVLMDecoderLayer"          # _no_split_modules (:347)
+    assert type(layer.input_layernorm.weight).__name__ == "NoWeightDecayParameter"
+
+
+@pytest.mark.skipif(not RL.reference_available(), reason="/root/reference not present")
+def test_same_tree_as_live_reference_and_swap():
+    M = RL.load_reference()
+    cfg = M.CogVLMConfig(num_hidden_layers=2, vocab_size=32, vision_config={}, **CFG)
+    cfg.lora_lang = True
+    model = M.CogVLMModel(cfg)
+    ref_layer = model.layers[0]
+    ours = CogVLMDecoderLayer(cfg)                                  # accepts the reference's config object
+    assert {k: tuple(v.shape) for k, v in ours.state_dict().items()} == \
+           {k: tuple(v.shape) for k, v in ref_layer.state_dict().items()}
+    assert [n for n, _ in ours.named_modules()] == [n for n, _ in ref_layer.named_modules()]
+    ours.load_state_dict(ref_layer.state_dict(), strict=True)
+    keys_before = list(model.state_dict().keys())
+    ptrs = {k: v.data_ptr() for k, v in model.state_dict().items()}
+    swap_decoder_layers(model)
+    assert all(isinstance(l, CogVLMDecoderLayer) for l in model.layers)
+    assert list(model.state_dict().keys()) == keys_before
+    assert {k: v.data_ptr() for k, v in model.state_dict().items()} == ptrs   # moved, not copied
+    # the LoRA target hooks select the same module names as the reference's (mmmm/utils.py:19-43 semantics)
+    t_attn, _ = ours.self_attn.get_lora_modules("model.layers.0.self_attn")
+    assert sorted(t_attn) == sorted(f"model.layers.0.self_attn.{n}" for n in (
+        "vision_expert_query_key_value", "vision_expert_dense", "language_expert_query_key_value",
+        "language_expert_dense"))
+    t_mlp, _ = ours.mlp.get_lora_modules("mlp")
+    assert len(t_mlp) == 6
+    ours.self_attn.config.lora_lang = False
+    assert len(ours.self_attn.get_lora_modules("a")[0]) == 2 and len(ours.mlp.get_lora_modules("m")[0]) == 3
+    ours.self_attn.config.lora_lang = True
+
+
+def test_mock_peft_wrapping_and_resolver():
+    layer = CogVLMDecoderLayer(VexConfig(**CFG))
+    base_w = layer.self_attn.vision_expert_dense.weight
+    attach_mock_lora(layer, r=16, b_std=0.02)
+    keys = set(layer.state_dict().keys())
+    # PEFT's in-module key names
+    assert "self_attn.vision_expert_dense.base_layer.weight" in keys
+    assert "self_attn.vision_expert_dense.lora_A.default.weight" in keys
+    assert "self_attn.vision_expert_dense.lora_B.default.weight" in keys
+    assert "input_layernorm.modules_to_save.default.weight" in keys
+    assert "input_layernorm.original_module.weight" in keys
+    spec = resolve_linear(layer.self_attn.vision_expert_dense)
+    assert spec.weight is base_w and spec.r == 16 and spec.scaling == 8 / 4
+    assert spec.lora_A.shape == (16, 256) and spec.lora_B.shape == (256, 16)
+    m = layer.self_attn.vision_expert_dense
+    m.disable_adapters = True
+    assert resolve_linear(m).lora_A is None
+    m.disable_adapters, m.merged = False, True
+    assert resolve_linear(m).lora_A is None
+    m.merged = False
+    m.active_adapters = ["default", "other"]
+    m.lora_A["other"], m.lora_B["other"] = nn.Linear(256, 16, bias=False), nn.Linear(16, 256, bias=False)
+    with pytest.raises(NotImplementedError):
+        resolve_linear(m)
+    wrapped = layer.input_layernorm
+    assert resolve_norm(wrapped) is wrapped.modules_to_save["default"]
+    wrapped.disable_adapters = True
+    assert resolve_norm(wrapped) is wrapped.original_module
+    # the mock computes PEFT's formula (used by bench/tests as the eager LoRA reference)
+    lin = nn.Linear(8, 4, bias=False)
+    ml = MockLoraLinear(lin, r=8, b_std=0.1)
+    x = torch.randn(3, 8)
+    want = lin(x) + (x @ ml.lora_A["default"].weight.T @ ml.lora_B["default"].weight.T) * ml.scaling["default"]
+    torch.testing.assert_close(ml(x), want)
+
+
+def test_errors_are_loud_on_cpu():
+    layer = CogVLMDecoderLayer(VexConfig(**CFG))
+    h = torch.zeros(1, 4, 256, dtype=torch.bfloat16)
+    ids = torch.zeros(1, 4, dtype=torch.long)
+    pm = torch.ones(1, 4, dtype=torch.bool)
+    with pytest.raises(ValueError, match="no CPU path"):
+        layer(h, ids, ids, pm)
+    with pytest.raises(NotImplementedError, match="past_key_value"):
+        layer(h, ids, ids, pm, past_key_value=(h, h))
+    with pytest.raises(TypeError):
+        layer(h)
+    with pytest.raises(ValueError, match="head_dim"):
+        CogVLMDecoderLayer(VexConfig(hidden_size=256, intermediate_size=256, num_attention_heads=4))
+
+
+def test_rotary_module_keeps_reference_table_semantics():
+    from oracle import oracle_layer as O
+    from mmmm_b200.modeling_cogvlm import RotaryEmbedding
+    rot = RotaryEmbedding(128, max_position_embeddings=64)
+    cos, sin = rot.tables(300, torch.device("cpu"), torch.float32)
+    c_ref, s_ref = O.rotary_tables(O.default_inv_freq(128), 300)
+    assert torch.equal(cos[:300], c_ref) and torch.equal(sin[:300], s_ref)
+    rot = rot.to(torch.bfloat16)                                   # bf16-true: table rebuilt in bf16 (quirk 2)
+    cos, _ = rot.tables(300, torch.device("cpu"), torch.bfloat16)
+    c_ref, _ = O.rotary_tables(O.default_inv_freq(128).bfloat16(), 300)
+    assert cos.dtype == torch.bfloat16 and torch.equal(cos[:300], c_ref)
+    assert torch.equal(cos[256], cos[257])
+    c3, s3 = rot(torch.zeros(1, dtype=torch.bfloat16), seq_len=10)  # reference forward signature
+    assert c3.shape == (10, 1, 128)

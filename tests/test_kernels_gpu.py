@@ -1,0 +1,319 @@
+"""GPU parity tests of the individual kernels, called through the C ABI (ctypes -> libvex.so) via the
+registered torch.library ops, against the oracle (oracle/oracle_layer.py) or a plain fp32 restatement
+of the same op on identical seeded inputs.  Integer/index work is bit-exact; floating point within the
+tolerance written in each test."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle_layer as O  # noqa: E402
+
+
+def _ops():
+    from mmmm_b200 import ops
+    return ops
+
+
+def _plan(tt, pm):
+    from mmmm_b200.plan import build_plan
+    return build_plan(tt.cuda(), pm.cuda())
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-6))
+
+
+# ------------------------------------------------------------------------------------------ K1
+def _routing_cases(golden_dir):
+    from mmmm_b200.inputs import make_ids
+    g = torch.load(os.path.join(golden_dir, "routing.pt"), weights_only=False)
+    cases = [(c["token_type_ids"], c["padding_mask"]) for c in g["routing"] if c["token_type_ids"].shape[1] > 1]
+    gen = torch.Generator().manual_seed(0)
+    for B, L in [(1, 2), (2, 257), (7, 1000), (64, 1485), (3, 5000)]:
+        tt = (torch.rand(B, L, generator=gen) < 0.7).long()
+        pm = torch.rand(B, L, generator=gen) < 0.85
+        cases.append((tt, pm))
+    tt, _, pm = make_ids(8, 1225, 256, ragged=True, seed=4)
+    cases.append((tt, pm))
+    tt, _, pm = make_ids(2, 2048, 512)
+    cases.append((tt, pm))
+    cases.append((torch.ones(2, 9, dtype=torch.long), torch.zeros(2, 9, dtype=torch.bool)))  # nothing valid
+    cases.append((torch.ones(2, 9, dtype=torch.long), torch.ones(2, 9, dtype=torch.bool)))   # all vision-typed
+    return cases
+
+
+def test_k1_partition_bit_exact(golden_dir):
+    for tt, pm in _routing_cases(golden_dir):
+        want = O.routing_plan(tt, pm)
+        plan = _plan(tt, pm)
+        c = plan.counts.cpu().tolist()
+        assert c[0] == want.vision_idx.numel() and c[1] == want.language_idx.numel()
+        assert c[2] == want.valid_idx.numel()
+        assert c[3] == int(pm.sum(1).max())
+        assert torch.equal(plan.vision_idx().cpu(), want.vision_idx)
+        assert torch.equal(plan.language_idx().cpu(), want.language_idx)
+        assert torch.equal(plan.valid_idx().cpu(), want.valid_idx)
+        assert torch.equal(plan.cu_seqlens.cpu().long(), want.cu_seqlens)
+        T, n = c[2], tt.numel()
+        s2f, f2s = plan.sorted_to_flat.cpu().long(), plan.flat_to_sorted.cpu().long()
+        s2t, t2s, t2f = plan.sorted_to_token.cpu().long(), plan.token_to_sorted.cpu().long(), plan.token_to_flat.cpu().long()
+        assert (s2f[T:] == -1).all() and (s2t[T:] == -1).all() and (t2s[T:] == -1).all() and (t2f[T:] == -1).all()
+        assert torch.equal(f2s[s2f[:T]], torch.arange(T))               # inverse permutations
+        assert torch.equal(t2s[s2t[:T]], torch.arange(T))
+        assert torch.equal(t2f[s2t[:T]], s2f[:T])
+        assert (f2s[~pm.reshape(-1)] == -1).all() and int((f2s >= 0).sum()) == T
+        # masks with the reference's meaning
+        from mmmm_b200.modeling_cogvlm import get_expert_mask
+        from mmmm_b200.plan import GLOBAL_PLAN_CACHE
+        GLOBAL_PLAN_CACHE.clear()
+        v, l = get_expert_mask(tt.cuda(), pm.cuda())
+        wv, wl = O.expert_masks(tt, pm)
+        assert torch.equal(v.cpu(), wv) and torch.equal(l.cpu(), wl)
+
+
+# ------------------------------------------------------------------------------------------ K2
+@pytest.mark.parametrize("H", [256, 1024, 4096])
+@pytest.mark.parametrize("wdtype", [torch.bfloat16, torch.float32])
+def test_k2_rmsnorm_gather(H, wdtype):
+    ops = _ops()
+    g = torch.Generator().manual_seed(H)
+    x = (torch.randn(300, H, generator=g) * 3).bfloat16()
+    w = (1 + 0.2 * torch.randn(H, generator=g)).to(wdtype)
+    src = torch.randperm(300, generator=g)[:211].int()
+    n = torch.tensor([200], dtype=torch.int32)
+    out = torch.full((211, H), 7.0, dtype=torch.bfloat16).cuda()
+    ops.rmsnorm_gather(x.cuda(), w.cuda(), 1e-6, src.cuda(), n.cuda(), out)
+    want = O.rms_norm(x[src[:200].long()], w, 1e-6)
+    got = out.cpu()
+    # identical formula; only the fp32 summation order differs -> at most 1 bf16 ulp on a few elements
+    torch.testing.assert_close(got[:200].float(), want.float(), rtol=8e-3, atol=1e-5)
+    assert (got[:200] != want).float().mean() < 0.02
+    assert (got[200:] == 7.0).all()  # rows past the device-side count are untouched
+
+
+# ------------------------------------------------------------------------------------------ K5 / K6
+def test_k5_silu_mul():
+    ops = _ops()
+    g = torch.Generator().manual_seed(1)
+    gate = (torch.randn(130, 11008, generator=g) * 2).bfloat16()
+    up = torch.randn(130, 11008, generator=g).bfloat16()
+    out = torch.zeros_like(gate).cuda()
+    ops.silu_mul(gate.cuda(), up.cuda(), torch.tensor([97], dtype=torch.int32).cuda(), out)
+    want = torch.nn.functional.silu(gate[:97]) * up[:97]
+    torch.testing.assert_close(out[:97].cpu().float(), want.float(), rtol=8e-3, atol=1e-6)
+    assert (out[97:] == 0).all()
+
+
+def test_k6_residual_scatter_and_copy_padded():
+    ops = _ops()
+    g = torch.Generator().manual_seed(2)
+    H, n_flat, n = 512, 90, 61
+    y = torch.randn(n_flat, H, generator=g).bfloat16()
+    res = torch.randn(n_flat, H, generator=g).bfloat16()
+    dst = torch.randperm(n_flat, generator=g)[:n_flat].int()
+    out = torch.zeros(n_flat, H, dtype=torch.bfloat16).cuda()
+    ops.residual_scatter(y.cuda(), res.cuda(), dst.cuda(), torch.tensor([n], dtype=torch.int32).cuda(), out)
+    want = torch.zeros(n_flat, H, dtype=torch.bfloat16)
+    want[dst[:n].long()] = res[dst[:n].long()] + y[:n]
+    assert torch.equal(out.cpu(), want)  # one bf16 add: bit-exact
+    f2s = torch.full((n_flat,), -1, dtype=torch.int32)
+    f2s[dst[:n].long()] = torch.arange(n, dtype=torch.int32)
+    ops.copy_padded_rows(res.cuda(), f2s.cuda(), out)
+    want[f2s < 0] = res[f2s < 0]
+    assert torch.equal(out.cpu(), want)
+
+
+# ------------------------------------------------------------------------------------------ K3
+def _gemm_problem(Tv, Tl, N, K, seed=0, cap_extra=5):
+    g = torch.Generator().manual_seed(seed)
+    cap = Tv + Tl + cap_extra
+    a = torch.randn(cap, K, generator=g).bfloat16().cuda()
+    wv = (torch.randn(N, K, generator=g) * 0.05).bfloat16().cuda()
+    wl = (torch.randn(N, K, generator=g) * 0.05).bfloat16().cuda()
+    counts = torch.tensor([Tv, Tl, Tv + Tl, 0], dtype=torch.int32).cuda()
+    return a, wv, wl, counts, cap
+
+
+def _ref_linear(a, wv, wl, Tv, Tl):
+    out = torch.zeros(a.shape[0], wv.shape[0], dtype=torch.float32, device=a.device)
+    out[:Tv] = a[:Tv].float() @ wv.float().T
+    out[Tv:Tv + Tl] = a[Tv:Tv + Tl].float() @ wl.float().T
+    return out
+
+
+GEMM_SHAPES = [  # Tv, Tl, N, K
+    (300, 100, 512, 256), (128, 128, 256, 64), (1, 1, 256, 128), (0, 77, 256, 192), (77, 0, 768, 256),
+    (129, 255, 384, 200), (1000, 517, 1024, 1024), (2500, 300, 4096, 512),
+]
+
+
+@pytest.mark.parametrize("Tv,Tl,N,K", GEMM_SHAPES)
+def test_k3_plain_grouped(Tv, Tl, N, K):
+    ops = _ops()
+    a, wv, wl, counts, cap = _gemm_problem(Tv, Tl, N, K, seed=N + K)
+    out = torch.full((cap, N), 3.0, dtype=torch.bfloat16).cuda()
+    ops.grouped_gemm(a, wv, wl, out, counts, None, 1.0)
+    want = _ref_linear(a, wv, wl, Tv, Tl)
+    T = Tv + Tl
+    torch.testing.assert_close(out[:T].float(), want[:T], rtol=1e-2, atol=1e-2)
+    assert (out[T:] == 3.0).all()  # masked rows untouched
+
+
+def test_k3_small_n_lora_a_shape():
+    """N = 64 path (the LoRA A projection) incl. alpha and single-expert mode."""
+    ops = _ops()
+    a, wv, wl, counts, cap = _gemm_problem(333, 140, 64, 1024, seed=5)
+    out = torch.zeros(cap, 64, dtype=torch.bfloat16).cuda()
+    ops.grouped_gemm(a, wv, wl, out, counts, None, 0.5)
+    want = _ref_linear(a, wv, wl, 333, 140) * 0.5
+    torch.testing.assert_close(out[:473].float(), want[:473], rtol=1e-2, atol=1e-2)
+    out.zero_()
+    ops.grouped_gemm(a, wv, None, out, counts, None, 1.0)
+    torch.testing.assert_close(out[:333].float(), want[:333] * 2, rtol=1e-2, atol=1e-2)
+    assert (out[333:] == 0).all()
+
+
+def test_k3_scatter_and_residual():
+    ops = _ops()
+    Tv, Tl, N, K = 260, 140, 512, 320
+    a, wv, wl, counts, cap = _gemm_problem(Tv, Tl, N, K, seed=9, cap_extra=40)
+    g = torch.Generator().manual_seed(3)
+    rmap = torch.randperm(cap, generator=g).int().cuda()
+    res = torch.randn(cap, N, generator=g).bfloat16().cuda()
+    out = torch.zeros(cap, N, dtype=torch.bfloat16).cuda()
+    ops.grouped_gemm_fused(a, [wv, None, wl, None], out, counts, ops.EPI_RESIDUAL, rmap, res, [None, None],
+                           [None] * 4, 0, [], 0, False, 1.0)
+    T = Tv + Tl
+    lin = _ref_linear(a, wv, wl, Tv, Tl)[:T].bfloat16()
+    want = torch.zeros_like(out)
+    want[rmap[:T].long()] = lin + res[rmap[:T].long()]
+    torch.testing.assert_close(out.float(), want.float(), rtol=1e-2, atol=2e-2)
+    # in place (residual == out)
+    out2 = res.clone()
+    ops.grouped_gemm_fused(a, [wv, None, wl, None], out2, counts, ops.EPI_RESIDUAL, rmap, None, [None, None],
+                           [None] * 4, 0, [], 0, False, 1.0)
+    want2 = res.clone()
+    want2[rmap[:T].long()] = want[rmap[:T].long()]
+    torch.testing.assert_close(out2.float(), want2.float(), rtol=1e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("r", [64, 16])
+def test_k3_lora_k_extension(r):
+    ops = _ops()
+    Tv, Tl, N, K = 200, 150, 768, 256
+    a, wv, wl, counts, cap = _gemm_problem(Tv, Tl, N, K, seed=21)
+    g = torch.Generator().manual_seed(4)
+    Av, Al = [(torch.randn(r, K, generator=g) * 0.1).bfloat16().cuda() for _ in range(2)]
+    Bv, Bl = [(torch.randn(N, r, generator=g) * 0.1).bfloat16().cuda() for _ in range(2)]
+    t = torch.zeros(cap, r, dtype=torch.bfloat16).cuda()
+    ops.grouped_gemm(a, Av, Al, t, counts, None, 1.0)
+    t_ref = _ref_linear(a, Av, Al, Tv, Tl).bfloat16()
+    torch.testing.assert_close(t[:350].float(), t_ref[:350].float(), rtol=1e-2, atol=1e-2)
+    out = torch.zeros(cap, N, dtype=torch.bfloat16).cuda()
+    ops.grouped_gemm_fused(a, [wv, None, wl, None], out, counts, ops.EPI_PLAIN, None, None, [t, None],
+                           [Bv, None, Bl, None], r, [], 0, False, 1.0)
+    want = _ref_linear(a, wv, wl, Tv, Tl) + _ref_linear(t_ref, Bv, Bl, Tv, Tl)
+    torch.testing.assert_close(out[:350].float(), want[:350], rtol=1e-2, atol=2e-2)
+    # vision-only adapter (lora_lang = False)
+    out.zero_()
+    ops.grouped_gemm_fused(a, [wv, None, wl, None], out, counts, ops.EPI_PLAIN, None, None, [t, None],
+                           [Bv, None, None, None], r, [], 0, False, 1.0)
+    want = _ref_linear(a, wv, wl, Tv, Tl)
+    want[:Tv] += t_ref[:Tv].float() @ Bv.float().T
+    torch.testing.assert_close(out[:350].float(), want[:350], rtol=1e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("lora", [False, True])
+def test_k3_swiglu(lora):
+    ops = _ops()
+    Tv, Tl, I, K, r = 300, 180, 640, 256, 64
+    g = torch.Generator().manual_seed(33)
+    cap = Tv + Tl + 9
+    a = torch.randn(cap, K, generator=g).bfloat16().cuda()
+    mk = lambda *s, sc=0.08: (torch.randn(*s, generator=g) * sc).bfloat16().cuda()
+    gv, uv, gl, ul = mk(I, K), mk(I, K), mk(I, K), mk(I, K)
+    counts = torch.tensor([Tv, Tl, Tv + Tl, 0], dtype=torch.int32).cuda()
+    T = Tv + Tl
+    gate = _ref_linear(a, gv, gl, Tv, Tl)
+    up = _ref_linear(a, uv, ul, Tv, Tl)
+    lt, lb, rr = [None, None], [None] * 4, 0
+    if lora:
+        Ag = [mk(r, K), mk(r, K)]
+        Au = [mk(r, K), mk(r, K)]
+        Bg = [mk(I, r), mk(I, r)]
+        Bu = [mk(I, r), mk(I, r)]
+        tg = torch.zeros(cap, r, dtype=torch.bfloat16).cuda()
+        tu = torch.zeros(cap, r, dtype=torch.bfloat16).cuda()
+        ops.grouped_gemm(a, Ag[0], Ag[1], tg, counts, None, 1.0)
+        ops.grouped_gemm(a, Au[0], Au[1], tu, counts, None, 1.0)
+        gate = gate + _ref_linear(tg, Bg[0], Bg[1], Tv, Tl)
+        up = up + _ref_linear(tu, Bu[0], Bu[1], Tv, Tl)
+        lt, lb, rr = [tg, tu], [Bg[0], Bu[0], Bg[1], Bu[1]], r
+    out = torch.zeros(cap, I, dtype=torch.bfloat16).cuda()
+    ops.grouped_gemm_fused(a, [gv, uv, gl, ul], out, counts, ops.EPI_SWIGLU, None, None, lt, lb, rr, [], 0,
+                           False, 1.0)
+    want = torch.nn.functional.silu(gate.bfloat16()) * up.bfloat16()
+    torch.testing.assert_close(out[:T].float(), want[:T].float(), rtol=2e-2, atol=2e-2)
+    assert (out[T:] == 0).all()
+
+
+def test_k3_rope_epilogue_scatter_to_token_order():
+    from mmmm_b200.inputs import make_ids
+    ops = _ops()
+    heads, Hd = 2, 256
+    tt, pos, pm = make_ids(3, 40, 300, ragged=True, seed=8)   # positions > 256: bf16-table collapse region
+    plan = _plan(tt, pm)
+    B, L = tt.shape
+    cap = B * L
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(cap, Hd, generator=g).bfloat16().cuda()       # sorted-order activations
+    wv = (torch.randn(3 * Hd, Hd, generator=g) * 0.06).bfloat16().cuda()
+    wl = (torch.randn(3 * Hd, Hd, generator=g) * 0.06).bfloat16().cuda()
+    cos, sin = O.rotary_tables(O.default_inv_freq(128).bfloat16(), 512)
+    out = torch.zeros(cap, 3 * Hd, dtype=torch.bfloat16).cuda()
+    ops.grouped_gemm_fused(x, [wv, None, wl, None], out, plan.counts, ops.EPI_ROPE, plan.sorted_to_token, None,
+                           [None, None], [None] * 4, 0,
+                           [cos.cuda().contiguous(), sin.cuda().contiguous(), pos.reshape(-1).cuda(), plan.sorted_to_flat],
+                           2 * Hd, False, 1.0)
+    Tv, Tl, T = plan.counts.cpu().tolist()[:3]
+    lin = _ref_linear(x, wv, wl, Tv, Tl)[:T].bfloat16().cpu()     # sorted order, eager-bf16 Linear output
+    s2f = plan.sorted_to_flat.cpu().long()[:T]
+    s2t = plan.sorted_to_token.cpu().long()[:T]
+    p = pos.reshape(-1)[s2f]
+    q, k, v = lin.split(Hd, dim=-1)
+    qh, kh = q.view(1, T, heads, 128).permute(0, 2, 1, 3), k.view(1, T, heads, 128).permute(0, 2, 1, 3)
+    qr, kr = O.apply_rotary(qh, kh, cos, sin, p[None])
+    want = torch.cat([qr.permute(0, 2, 1, 3).reshape(T, Hd), kr.permute(0, 2, 1, 3).reshape(T, Hd), v], dim=-1)
+    got = out.cpu()[s2t]
+    torch.testing.assert_close(got.float(), want.float(), rtol=2e-2, atol=2e-2)
+
+
+# ------------------------------------------------------------------------------------------ K4
+@pytest.mark.parametrize("lens", [[1], [64], [65, 3, 128], [300, 17, 1, 255], [1357], [700, 1485]])
+def test_k4_attention_vs_oracle(lens):
+    ops = _ops()
+    heads = 3
+    B, Lmax = len(lens), max(lens)
+    g = torch.Generator().manual_seed(sum(lens))
+    pm = torch.zeros(B, Lmax, dtype=torch.bool)
+    for b, n in enumerate(lens):
+        pm[b, :n] = True
+    q, k, v = [torch.randn(B, heads, Lmax, 128, generator=g).bfloat16() for _ in range(3)]
+    want = O.attention(q, k, v, pm)                     # [B, heads, L, 128]
+    T = sum(lens)
+    # token-order packed qkv [T, 3, heads, 128]
+    tok = lambda t: t.permute(0, 2, 1, 3)[pm]            # [T, heads, 128]
+    qkv = torch.stack([tok(q), tok(k), tok(v)], dim=1).reshape(T, 3 * heads * 128).contiguous()
+    qkv_buf = torch.zeros(B * Lmax, 3 * heads * 128, dtype=torch.bfloat16)
+    qkv_buf[:T] = qkv
+    cu = torch.zeros(B + 1, dtype=torch.int32)
+    cu[1:] = torch.tensor(lens).cumsum(0)
+    rmap = torch.randperm(B * Lmax, generator=g).int()
+    out = torch.zeros(B * Lmax, heads * 128, dtype=torch.bfloat16).cuda()
+    ops.attention(qkv_buf.cuda(), cu.cuda(), B, Lmax, heads, rmap.cuda(), out, 128 ** -0.5)
+    got = out.cpu()[rmap[:T].long()]
+    torch.testing.assert_close(got.float(), tok(want).reshape(T, heads * 128).float(), rtol=2e-2, atol=2e-2)

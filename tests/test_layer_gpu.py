@@ -1,0 +1,207 @@
+"""GPU parity of the whole drop-in layer against the oracle / the golden fixtures of the reference.
+
+Tolerance (from north_star): bf16 hidden states within max relative error 2e-2,
+measured as maxabs(delta) / maxabs(ref) on rows with padding_mask == True (padded rows are undefined in
+the reference), plus relative Frobenius error <= 1e-2; routing bit-exact (tests/test_kernels_gpu.py)."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle_layer as O  # noqa: E402
+
+MAX_REL, FRO_REL = 2e-2, 1e-2
+
+
+def _errs(got, ref):
+    got, ref = got.float(), ref.float()
+    return (float((got - ref).abs().max() / ref.abs().max()), float((got - ref).norm() / ref.norm()))
+
+
+def _make_layer(weights, cfg_kw, lora=None):
+    from mmmm_b200.modeling_cogvlm import CogVLMDecoderLayer, VexConfig
+    from mmmm_b200.peft_compat import attach_mock_lora
+    layer = CogVLMDecoderLayer(VexConfig(**cfg_kw))
+    sd = {k: v for k, v in weights.items()}
+    layer.load_state_dict(sd, strict=True)
+    layer = layer.to(torch.bfloat16).cuda().eval()
+    if lora is not None:
+        r = next(iter(lora.values())).A.shape[0]
+        attach_mock_lora(layer, r=r, lora_alpha=8)
+        for path, ad in lora.items():
+            mod = layer.get_submodule(path)
+            mod.lora_A["default"].weight.data.copy_(ad.A)
+            mod.lora_B["default"].weight.data.copy_(ad.B)
+            mod.scaling["default"] = ad.scaling
+    return layer
+
+
+def _run(layer, h, tt, pos, pm, **kw):
+    with torch.no_grad():
+        return layer(h.cuda(), token_type_ids=tt.cuda(), position_ids=pos.cuda(), padding_mask=pm.cuda(), **kw)
+
+
+@pytest.mark.parametrize("name", ["layer_tiny.pt", "layer_longpos.pt"])
+@pytest.mark.parametrize("fuse", [True, False])
+def test_layer_vs_reference_golden(golden_dir, name, fuse):
+    """Against outputs of the UNMODIFIED reference (bf16 run) stored by oracle/make_golden.py."""
+    case = torch.load(os.path.join(golden_dir, name), weights_only=False)
+    cfg = case["config"]
+    w = dict(case["weights"])
+    w["self_attn.rotary_emb.inv_freq"] = case["inv_freq"]
+    layer = _make_layer(w, dict(hidden_size=cfg["hidden_size"], intermediate_size=cfg["intermediate_size"],
+                                num_attention_heads=cfg["num_heads"], rms_norm_eps=cfg["rms_norm_eps"]))
+    layer.fuse_epilogue = fuse
+    tt, pos, pm = case["token_type_ids"], case["position_ids"], case["padding_mask"]
+    out, (k, v) = _run(layer, case["hidden_states"], tt, pos, pm, use_cache=True)
+    ref = case["bf16"]
+    mx, fro = _errs(out.cpu()[pm], ref["out"][pm])
+    assert mx <= MAX_REL and fro <= FRO_REL, (mx, fro)
+    pmh = pm[:, None, :].expand(k.shape[:3])
+    for got, want in ((k, ref["k"]), (v, ref["v"])):
+        assert got.shape == want.shape
+        mx, fro = _errs(got.cpu()[pmh], want[pmh])
+        assert mx <= MAX_REL and fro <= FRO_REL, (mx, fro)
+        assert (got.cpu()[~pmh] == 0).all()
+    # ours-bf16 must be no further from the fp32 reference than 1.5x the reference's own bf16 run
+    e_ours = _errs(out.cpu()[pm], case["fp32"]["out"][pm])[1]
+    e_ref = _errs(ref["out"][pm], case["fp32"]["out"][pm])[1]
+    assert e_ours <= 1.5 * e_ref + 1e-4, (e_ours, e_ref)
+    # padded rows: pass-through of the input (deterministic; the reference leaves them uninitialised)
+    assert torch.equal(out.cpu()[~pm], case["hidden_states"][~pm])
+
+
+@pytest.mark.parametrize("shape", [dict(B=2, nv=150, nt=40, H=1024, I=1408, heads=8),
+                                   dict(B=3, nv=300, nt=100, H=512, I=768, heads=4)])
+@pytest.mark.parametrize("lora", [None, 64, 16])
+def test_layer_vs_oracle_synthetic(shape, lora):
+    from mmmm_b200.inputs import make_inputs
+    H, I, heads = shape["H"], shape["I"], shape["heads"]
+    w = O.random_weights(H, I, heads, seed=3, dtype=torch.bfloat16)
+    ad = O.random_lora(H, I, r=lora, seed=4, dtype=torch.bfloat16) if lora else None
+    layer = _make_layer(w, dict(hidden_size=H, intermediate_size=I, num_attention_heads=heads), lora=ad)
+    inp = make_inputs(shape["B"], shape["nv"], shape["nt"], H, ragged=True, seed=2)
+    (out,) = _run(layer, inp.hidden_states, inp.token_type_ids, inp.position_ids, inp.padding_mask)
+    (ref,) = O.decoder_layer(w, inp.hidden_states, inp.token_type_ids, inp.position_ids, inp.padding_mask,
+                             num_heads=heads, lora=ad)
+    pm = inp.padding_mask
+    mx, fro = _errs(out.cpu()[pm], ref[pm])
+    assert mx <= MAX_REL and fro <= FRO_REL, (mx, fro)
+    if lora:  # the adapters must actually matter in this test
+        (base,) = O.decoder_layer(w, inp.hidden_states, inp.token_type_ids, inp.position_ids, pm, num_heads=heads)
+        assert _errs(base[pm], ref[pm])[1] > 5 * FRO_REL
+
+
+def test_layer_lora_vision_only_and_disabled():
+    from mmmm_b200.inputs import make_inputs
+    from mmmm_b200.peft_compat import attach_mock_lora
+    H, I, heads = 512, 768, 4
+    w = O.random_weights(H, I, heads, seed=7, dtype=torch.bfloat16)
+    ad = O.random_lora(H, I, r=32, seed=8, dtype=torch.bfloat16)
+    vis_only = {k: v for k, v in ad.items() if "vision" in k}
+    from mmmm_b200.modeling_cogvlm import CogVLMDecoderLayer, VexConfig
+    layer = CogVLMDecoderLayer(VexConfig(hidden_size=H, intermediate_size=I, num_attention_heads=heads, lora_lang=False))
+    layer.load_state_dict(w)
+    layer = layer.to(torch.bfloat16).cuda().eval()
+    attach_mock_lora(layer, r=32, lora_lang=False)
+    for path, a in vis_only.items():
+        m = layer.get_submodule(path)
+        m.lora_A["default"].weight.data.copy_(a.A)
+        m.lora_B["default"].weight.data.copy_(a.B)
+        m.scaling["default"] = a.scaling
+    inp = make_inputs(2, 200, 60, H, ragged=True, seed=5)
+    pm = inp.padding_mask
+    (out,) = _run(layer, inp.hidden_states, inp.token_type_ids, inp.position_ids, pm)
+    (ref,) = O.decoder_layer(w, inp.hidden_states, inp.token_type_ids, inp.position_ids, pm, num_heads=heads,
+                             lora=vis_only)
+    mx, fro = _errs(out.cpu()[pm], ref[pm])
+    assert mx <= MAX_REL and fro <= FRO_REL, (mx, fro)
+    for m in layer.modules():
+        if hasattr(m, "disable_adapters"):
+            m.disable_adapters = True
+    (out0,) = _run(layer, inp.hidden_states, inp.token_type_ids, inp.position_ids, pm)
+    (ref0,) = O.decoder_layer(w, inp.hidden_states, inp.token_type_ids, inp.position_ids, pm, num_heads=heads)
+    mx, fro = _errs(out0.cpu()[pm], ref0[pm])
+    assert mx <= MAX_REL and fro <= FRO_REL, (mx, fro)
+
+
+def test_two_layer_stack_shares_plan_and_matches_oracle():
+    """The caller-loop shape of llm_forward (:547-569): same id tensors for every layer -> one K1 run."""
+    from mmmm_b200.inputs import make_inputs
+    from mmmm_b200.plan import GLOBAL_PLAN_CACHE
+    H, I, heads = 512, 768, 4
+    ws = [O.random_weights(H, I, heads, seed=s, dtype=torch.bfloat16) for s in (1, 2)]
+    layers = [_make_layer(w, dict(hidden_size=H, intermediate_size=I, num_attention_heads=heads)) for w in ws]
+    inp = make_inputs(2, 120, 50, H, ragged=True, seed=9)
+    tt, pos, pm = inp.token_type_ids.cuda(), inp.position_ids.cuda(), inp.padding_mask.cuda()
+    h = inp.hidden_states.cuda()
+    GLOBAL_PLAN_CACHE.clear()
+    with torch.no_grad():
+        for layer in layers:
+            (h,) = layer(h, token_type_ids=tt, position_ids=pos, padding_mask=pm)
+            plan_id = id(GLOBAL_PLAN_CACHE._plan)
+    assert plan_id == id(GLOBAL_PLAN_CACHE._plan)
+    ref = O.decoder_stack(ws, inp.hidden_states, inp.token_type_ids, inp.position_ids, inp.padding_mask,
+                          num_heads=heads)
+    mx, fro = _errs(h.cpu()[inp.padding_mask], ref[inp.padding_mask])
+    assert mx <= 2 * MAX_REL and fro <= 2 * FRO_REL, (mx, fro)
+
+
+def test_error_behaviour_on_gpu():
+    from mmmm_b200.modeling_cogvlm import CogVLMDecoderLayer, VexConfig
+    layer = CogVLMDecoderLayer(VexConfig(hidden_size=256, intermediate_size=256, num_attention_heads=2))
+    layer = layer.to(torch.bfloat16).cuda().eval()
+    h = torch.zeros(1, 4, 256, dtype=torch.bfloat16).cuda()
+    ids = torch.zeros(1, 4, dtype=torch.long).cuda()
+    pm = torch.ones(1, 4, dtype=torch.bool).cuda()
+    with torch.no_grad():
+        with pytest.raises(NotImplementedError):
+            layer(h, ids, ids, pm, past_key_value=(h, h))
+        with pytest.raises(TypeError):
+            layer(h.float(), ids, ids, pm)
+        with pytest.raises(ValueError):
+            layer(h.cpu(), ids.cpu(), ids.cpu(), pm.cpu())
+        out = layer(h, ids, ids, attention_mask=pm)   # BASELINE's name for the 4th argument
+        assert out[0].shape == h.shape
+    with pytest.raises(NotImplementedError):           # grad-requiring call: forward-only this round
+        layer(h, ids, ids, pm)
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_full_size_c2_properties(ragged):
+    """BASELINE config 2 (B=8 x (1225 vision + 256 text), hidden 4096): too big for the CPU oracle in
+    seconds, so check size-independent properties: (1) per-sample independence -- the batch result equals
+    running each sample alone (block-diagonal attention, row-wise everything else), bit-exact;
+    (2) one full-size sample against the oracle restricted to a 1-sample problem is covered at c1 scale in
+    bench/smoke; here (3) determinism and finiteness, padded rows pass-through."""
+    from mmmm_b200.inputs import make_inputs
+    H, I, heads = 4096, 11008, 32
+    w = O.random_weights(H, I, heads, seed=0, dtype=torch.bfloat16)
+    layer = _make_layer(w, dict(hidden_size=H, intermediate_size=I, num_attention_heads=heads))
+    inp = make_inputs(8, 1225, 256, H, ragged=ragged, seed=0)
+    pm = inp.padding_mask
+    (out,) = _run(layer, inp.hidden_states, inp.token_type_ids, inp.position_ids, pm)
+    (out2,) = _run(layer, inp.hidden_states, inp.token_type_ids, inp.position_ids, pm)
+    assert torch.equal(out, out2) and torch.isfinite(out.float()).all()
+    assert torch.equal(out.cpu()[~pm], inp.hidden_states[~pm])
+    for b in (0, 5):
+        sl = slice(b, b + 1)
+        (ob,) = _run(layer, inp.hidden_states[sl], inp.token_type_ids[sl], inp.position_ids[sl], pm[sl])
+        assert torch.equal(ob.cpu()[pm[sl]], out.cpu()[sl][pm[sl]])
+
+
+def test_c1_one_sample_full_width_vs_oracle():
+    """BASELINE config 1 shape, one layer: 1225 vision + 128 text tokens, hidden 4096, against the CPU oracle
+    run in bf16 (about 10 s of CPU time)."""
+    from mmmm_b200.inputs import make_inputs
+    H, I, heads = 4096, 11008, 32
+    w = O.random_weights(H, I, heads, seed=1, dtype=torch.bfloat16)
+    layer = _make_layer(w, dict(hidden_size=H, intermediate_size=I, num_attention_heads=heads))
+    inp = make_inputs(1, 1225, 128, H, seed=1)
+    (out,) = _run(layer, inp.hidden_states, inp.token_type_ids, inp.position_ids, inp.padding_mask)
+    (ref,) = O.decoder_layer(w, inp.hidden_states, inp.token_type_ids, inp.position_ids, inp.padding_mask,
+                             num_heads=heads)
+    mx, fro = _errs(out.cpu()[0], ref[0])
+    assert mx <= MAX_REL and fro <= FRO_REL, (mx, fro)
