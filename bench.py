@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Benchmark of the visual-expert decoder layer hot path (BASELINE.json: prefill tokens/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--lora R] [--workload c2|c4s]
+
+One "step" = one forward pass of one full-width visual-expert layer (hidden 4096, 32 heads, I 11008,
+bf16) over one batch of synthetic image+text samples.  Default workload = BASELINE.json configs[1]
+("c2": batch 8 x (1225 vision + 256 text tokens) on one B200).  With N > 1 (torchrun, one rank per
+GPU) every rank runs its own batch of the same shape -- samples are independent, the forward path
+has no collective -- so per-GPU work is fixed ("scaling": "weak") and `value` is the whole-job
+tokens/s.  Rank 0 prints ONE JSON line.
+
+  value        : tokens/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e          : same metric through the public module call with HOST (pinned) inputs, H2D + D2H inside
+                 the timed region
+  roofline     : dominant kernel (the SwiGLU gate/up grouped GEMM) against the measured bf16 peak
+  cpu_baseline : the oracle restatement of the reference layer (fp32 eager PyTorch) on the host cores,
+                 bounded sample, rank 0 at N = 1 only
+--impl reference times that CPU path as the reference arm (the reference itself cannot travel to the
+GPU box: it is eager PyTorch importing packages absent from this image; oracle/oracle_layer.py is
+proven bit-identical to it in tests/test_oracle.py).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, I, HEADS = 4096, 11008, 32
+WORKLOADS = {
+    # name: (samples per GPU, vision tokens, text tokens)
+    "c2": (8, 1225, 256),    # BASELINE.json configs[1]
+    "c4s": (2, 2048, 512),   # configs[3] per-GPU shard (CT-RATE shaped, 2 samples per GPU)
+}
+GEMM_FLOP_PER_TOKEN = 2 * (H * 3 * H + H * H + 3 * H * I)  # 404 750 336
+
+
+def peaks():
+    p = dict(bf16_tflops=1590.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+    f = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(f):
+        try:
+            d = json.load(open(f))
+            p = dict(bf16_tflops=float(d["bf16_tflops"]), hbm_gbs=float(d["hbm_gbs"]),
+                     bf16_tflops_sustained=float(d.get("bf16_tflops_sustained", 0)), source="MEASURED_PEAKS.json")
+        except Exception:
+            pass
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=mx, reasons=["no samples"])
+        loaded = sorted(sm)[len(sm) // 2:]  # upper half ~ samples under load
+        return dict(sm_mhz=statistics.median(loaded), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_forward_timer(workload: str, steps: int, warmup: int, lora_r: int = 0):
+    """fp32 eager forward of ONE sample of the workload through the oracle (reference restatement)."""
+    from oracle import oracle_layer as O
+    from mmmm_b200.inputs import make_inputs
+    _, nv, nt = WORKLOADS[workload]
+    w = O.random_weights(H, I, HEADS, seed=0, dtype=torch.float32)
+    lora = O.random_lora(H, I, r=lora_r, dtype=torch.float32) if lora_r else None
+    inp = make_inputs(1, nv, nt, H, seed=0, dtype=torch.float32)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.decoder_layer(w, inp.hidden_states, inp.token_type_ids, inp.position_ids, inp.padding_mask,
+                            num_heads=HEADS, lora=lora)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    tokens = inp.num_valid_tokens
+    return tokens, times
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    tokens, times = cpu_forward_timer(args.workload, steps, warmup, args.lora)
+    ms = 1e3 * sum(times) / len(times)
+    val = tokens / (ms / 1e3)
+    cores = torch.get_num_threads()
+    b, nv, nt = WORKLOADS[args.workload]
+    sample = f"1 of {b} samples per step ({tokens} tokens: {nv} vision + {nt} text), fp32 eager, 1 layer"
+    print(json.dumps({
+        "impl": "reference", "metric": "visual-expert prefill tokens/s", "value": val, "unit": "tokens/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": config_dict(args, 0),
+        "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference = CPU eager forward of the reference layer (oracle port, bit-identical to the "
+                "unmodified reference in tests/test_oracle.py; xformers attention replaced by the equivalent "
+                "block-diagonal causal softmax)",
+    }))
+
+
+def config_dict(args, tokens_per_gpu):
+    b, nv, nt = WORKLOADS[args.workload]
+    return {"workload": f"{args.workload}: 1 visual-expert layer (hidden {H}, {HEADS} heads, I {I}) bf16 prefill, "
+                        f"batch {b} x ({nv} vision + {nt} text tokens) per GPU",
+            "samples_per_gpu": b, "seq_len": 1 + nv + 2 + 1 + nt, "tokens_per_gpu": tokens_per_gpu,
+            "lora_r": args.lora, "parallelism": f"dp{args.gpus} (samples sharded, no collective)",
+            "l2": "per-step working set (0.81 GB weights + >0.5 GB activations) exceeds the 126 MB L2; no flush needed"}
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def make_gpu_layer(device, lora_r: int):
+    """Random-init layer with the reference's init (Linear ~ N(0, 0.02)), generated on the device."""
+    from mmmm_b200.modeling_cogvlm import CogVLMDecoderLayer, VexConfig
+    from mmmm_b200.peft_compat import attach_mock_lora
+    torch.manual_seed(0)
+    with torch.device("meta"):
+        layer = CogVLMDecoderLayer(VexConfig(hidden_size=H, intermediate_size=I, num_attention_heads=HEADS))
+    layer = layer.to_empty(device=device).to(torch.bfloat16)
+    g = torch.Generator(device=device).manual_seed(0)
+    with torch.no_grad():
+        for m in layer.modules():
+            if isinstance(m, torch.nn.Linear):
+                m.weight.copy_(torch.randn(m.weight.shape, generator=g, device=device, dtype=torch.float32) * 0.02)
+        for n in (layer.input_layernorm, layer.post_attention_layernorm):
+            n.weight.copy_(1 + 0.1 * torch.randn(H, generator=g, device=device))
+        rot = layer.self_attn.rotary_emb
+        rot.inv_freq = (1.0 / (rot.base ** (torch.arange(0, 128, 2, device=device) / 128))).to(torch.bfloat16)
+    if lora_r:
+        attach_mock_lora(layer, r=lora_r, lora_alpha=8, b_std=0.02)
+    return layer.eval()
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from mmmm_b200 import ops  # noqa: F401  (loads libvex.so; raises if it is missing)
+    from mmmm_b200._lib import lib
+    from mmmm_b200.inputs import make_inputs
+    from mmmm_b200 import instrument
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torchrun (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if lib().vex_device_check() != 0:
+        raise SystemExit("no sm_100 device: the visual-expert kernels only run on B200")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    b, nv, nt = WORKLOADS[args.workload]
+    layer = make_gpu_layer(dev, args.lora)
+    host = make_inputs(b, nv, nt, H, seed=rank)
+    pin = lambda t: t.pin_memory()
+    h_host, tt_host, pos_host, pm_host = map(pin, (host.hidden_states, host.token_type_ids, host.position_ids,
+                                                   host.padding_mask))
+    out_host = torch.empty_like(h_host).pin_memory()
+    tokens = host.num_valid_tokens
+    inp = host.to(dev)
+
+    def step():
+        return layer(inp.hidden_states, token_type_ids=inp.token_type_ids, position_ids=inp.position_ids,
+                     padding_mask=inp.padding_mask)[0]
+
+    def step_e2e():
+        hs = h_host.to(dev, non_blocking=True)
+        tt = tt_host.to(dev, non_blocking=True)
+        pos = pos_host.to(dev, non_blocking=True)
+        pm = pm_host.to(dev, non_blocking=True)
+        out = layer(hs, token_type_ids=tt, position_ids=pos, padding_mask=pm)[0]
+        out_host.copy_(out, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        with torch.no_grad():
+            for _ in range(warmup):
+                fn()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            instrument.reset()
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            barrier()
+        ms = e0.elapsed_time(e1)
+        launches = instrument.launches()
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms / steps, launches
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_step, launches = timed(step, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _ = timed(step_e2e, max(3, args.steps // 2), 3)
+
+    # per-kernel breakdown of one step (CUDA events on the launching stream around every libvex call)
+    kernels = None
+    if rank == 0:
+        with torch.no_grad():
+            kernels = instrument.profile(step, iters=max(5, args.steps // 2))
+    if world > 1:
+        dist.barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    total_tokens = tokens * world  # same shape on every rank; ragged=False so the count is identical
+    value = total_tokens / (ms_step / 1e3)
+    flop_step = tokens * GEMM_FLOP_PER_TOKEN
+    seq = 1 + nv + 2 + 1 + nt
+    attn_flop = b * 4 * HEADS * 128 * seq * (seq + 1) // 2
+    lora_flop = tokens * 2 * args.lora * 69888 * 2 // 2 if args.lora else 0
+    tf_layer = (flop_step + attn_flop + lora_flop) / (ms_step / 1e3) / 1e12
+    # dominant kernel: the gate/up SwiGLU grouped GEMM (2 * T * H * 2I flop per launch)
+    roof = None
+    if kernels:
+        gu = kernels.get("gemm_swiglu")
+        if gu:
+            flop = 2.0 * tokens * H * 2 * I + (2.0 * tokens * args.lora * 2 * I if args.lora else 0)
+            ach = flop / (gu["ms"] / 1e3) / 1e12
+            roof = {"kernel": "k3_grouped_gemm<256> (SwiGLU gate/up)", "bound": "tensor", "achieved": ach,
+                    "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+                    "traffic": None, "peak_source": pk["source"] + " (burst figure)",
+                    "flop_per_launch": flop, "ms_per_launch": gu["ms"]}
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        ctok, ctimes = cpu_forward_timer(args.workload, 3, 1, args.lora)
+        best = min(ctimes)
+        cpu = {"value": ctok / best, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"1 of {b} samples ({ctok} tokens), fp32 eager oracle, best of 3 after 1 warm-up"}
+    h2d = sum(t.numel() * t.element_size() for t in (h_host, tt_host, pos_host, pm_host))
+    d2h = out_host.numel() * out_host.element_size()
+    print(json.dumps({
+        "metric": "visual-expert prefill tokens/s", "value": value, "unit": "tokens/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": config_dict(args, tokens),
+        "tokens_per_s_per_gpu": value / world,
+        "layer_tflops_per_gpu": tf_layer, "layer_frac_of_bf16_peak": tf_layer / pk["bf16_tflops"],
+        "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
+        "e2e": {"value": total_tokens / (ms_e2e / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+        "gpu_launches": launches, "clocks": clocks, "peaks": pk,
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--lora", type=int, default=0, help="LoRA rank on all ten Linears (0 = frozen weights only)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

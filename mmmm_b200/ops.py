@@ -10,7 +10,7 @@ from typing import List, Optional, Sequence
 
 import torch
 
-from . import _lib
+from . import _lib, instrument
 from ._lib import EPI_PLAIN, EPI_RESIDUAL, EPI_ROPE, EPI_SWIGLU, GemmArgs  # noqa: F401
 
 _BF16 = torch.bfloat16
@@ -57,7 +57,8 @@ def partition(token_type_ids: torch.Tensor, padding_mask: torch.Tensor, sorted_t
         _dev(t, name, torch.int32)
         if t.numel() < n:
             raise ValueError(f"{name} needs at least {n} int32 elements")
-    rc = _lib.lib().vex_partition(token_type_ids.data_ptr(), padding_mask.data_ptr(), B, L,
+    with instrument.region("partition", 2):
+      rc = _lib.lib().vex_partition(token_type_ids.data_ptr(), padding_mask.data_ptr(), B, L,
                                   sorted_to_flat.data_ptr(), flat_to_sorted.data_ptr(), sorted_to_token.data_ptr(),
                                   token_to_sorted.data_ptr(), token_to_flat.data_ptr(), cu_seqlens.data_ptr(),
                                   counts.data_ptr(), scratch.data_ptr(), _stream())
@@ -81,7 +82,8 @@ def rmsnorm_gather(x: torch.Tensor, weight: torch.Tensor, eps: float, row_src: O
         _dev(row_src, "row_src", torch.int32)
     _dev(n_rows, "n_rows", torch.int32)
     rows_cap = out.numel() // H
-    rc = _lib.lib().vex_rmsnorm_gather(x.data_ptr(), weight.data_ptr(), int(weight.dtype == torch.float32),
+    with instrument.region("rmsnorm"):
+      rc = _lib.lib().vex_rmsnorm_gather(x.data_ptr(), weight.data_ptr(), int(weight.dtype == torch.float32),
                                        float(eps), _ptr(row_src), n_rows.data_ptr(), out.data_ptr(), rows_cap, H,
                                        _stream())
     _lib.check(rc, "vex_rmsnorm_gather")
@@ -96,7 +98,8 @@ def silu_mul(gate: torch.Tensor, up: torch.Tensor, n_rows: torch.Tensor, out: to
     if gate.shape != up.shape or gate.shape != out.shape:
         raise ValueError("gate/up/out shapes differ")
     I = gate.shape[-1]
-    rc = _lib.lib().vex_silu_mul(gate.data_ptr(), up.data_ptr(), out.data_ptr(), _dev(n_rows, "n_rows",
+    with instrument.region("silu_mul"):
+      rc = _lib.lib().vex_silu_mul(gate.data_ptr(), up.data_ptr(), out.data_ptr(), _dev(n_rows, "n_rows",
                                  torch.int32).data_ptr(), gate.numel() // I, I, _stream())
     _lib.check(rc, "vex_silu_mul")
 
@@ -110,7 +113,8 @@ def residual_scatter(y: torch.Tensor, residual: torch.Tensor, row_dst: Optional[
     H = y.shape[-1]
     if residual.shape[-1] != H or out.shape != residual.shape:
         raise ValueError("shape mismatch")
-    rc = _lib.lib().vex_residual_scatter(y.data_ptr(), residual.data_ptr(), _ptr(row_dst),
+    with instrument.region("residual_scatter"):
+      rc = _lib.lib().vex_residual_scatter(y.data_ptr(), residual.data_ptr(), _ptr(row_dst),
                                          _dev(n_rows, "n_rows", torch.int32).data_ptr(), out.data_ptr(),
                                          y.numel() // H, H, _stream())
     _lib.check(rc, "vex_residual_scatter")
@@ -123,7 +127,8 @@ def copy_padded_rows(x: torch.Tensor, flat_to_sorted: torch.Tensor, out: torch.T
     _dev(out, "out", _BF16)
     _dev(flat_to_sorted, "flat_to_sorted", torch.int32)
     H = x.shape[-1]
-    rc = _lib.lib().vex_copy_padded_rows(x.data_ptr(), flat_to_sorted.data_ptr(), out.data_ptr(), x.numel() // H, H,
+    with instrument.region("copy_padded_rows"):
+      rc = _lib.lib().vex_copy_padded_rows(x.data_ptr(), flat_to_sorted.data_ptr(), out.data_ptr(), x.numel() // H, H,
                                          _stream())
     _lib.check(rc, "vex_copy_padded_rows")
 
@@ -197,7 +202,9 @@ def grouped_gemm_raw(a: torch.Tensor, w: Sequence[Optional[torch.Tensor]], out: 
     args.rows_cap, args.N, args.K, args.mode = rows_cap, (n_out or N), K, mode
     args.single_expert = int(single_expert)
     args.alpha = alpha
-    rc = _lib.lib().vex_grouped_gemm(C.byref(args), _stream())
+    name = ("gemm_plain", "gemm_rope", "gemm_swiglu", "gemm_residual")[mode] + ("_n64" if N <= 64 else "")
+    with instrument.region(name):
+      rc = _lib.lib().vex_grouped_gemm(C.byref(args), _stream())
     _lib.check(rc, "vex_grouped_gemm")
 
 
@@ -234,7 +241,8 @@ def attention(qkv: torch.Tensor, cu_seqlens: torch.Tensor, batch: int, max_len_c
         raise ValueError("qkv rows must be [3 * heads * 128] wide (head_dim 128 only)")
     if out_row_map is not None:
         _dev(out_row_map, "out_row_map", torch.int32)
-    rc = _lib.lib().vex_attention(qkv.data_ptr(), cu_seqlens.data_ptr(), batch, max_len_cap, heads,
+    with instrument.region("attention"):
+      rc = _lib.lib().vex_attention(qkv.data_ptr(), cu_seqlens.data_ptr(), batch, max_len_cap, heads,
                                   _ptr(out_row_map), out.data_ptr(), float(scale), _stream())
     _lib.check(rc, "vex_attention")
 
