@@ -146,8 +146,10 @@ int vex_grouped_gemm(const vexGemmArgs* args, vexStream stream);
 /* K4 -- causal block-diagonal (varlen) flash attention over the token-order QKV buffer.
  * Replaces attention_fn's prefill branch (:106-128): per sample, token i attends to tokens j <= i of
  * the same sample (causality by token rank, not position_ids), scale = 128^-0.5, fp32 softmax.
- *   qkv [T, 3, heads, 128] bf16 (q and k already rotated), out rows scattered through out_row_map
- *   (token_to_sorted; NULL = identity) into [rows_cap, heads*128] bf16. */
+ *   qkv [rows_cap = B*max_len_cap, 3, heads, 128] bf16, rows [0, T) live (q and k already rotated); rows
+ *   [T, T+128) are scratch and are zeroed by the call.  out rows are scattered through out_row_map
+ *   (token_to_sorted; NULL = identity) into [rows_cap, heads*128] bf16.
+ *   Environment VEX_ATTN_IMPL=mma selects the mma.sync baseline kernel instead of the tcgen05 one. */
 int vex_attention(const void* qkv, const int32_t* cu_seqlens, int B, int max_len_cap, int heads,
                   const int32_t* out_row_map, void* out, float scale, vexStream stream);
 
