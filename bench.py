@@ -149,23 +149,23 @@ def run_reference_arm(args):
 
 def config_dict(args, tokens_per_gpu):
     b, nv, nt = WORKLOADS[args.workload]
-    return {"workload": f"{args.workload}: 1 visual-expert layer (hidden {H}, {HEADS} heads, I {I}) bf16 prefill, "
-                        f"batch {b} x ({nv} vision + {nt} text tokens) per GPU",
+    return {"workload": f"{args.workload}: {args.layers} visual-expert layer(s) (hidden {H}, {HEADS} heads, I {I}) bf16 "
+                        f"prefill, batch {b} x ({nv} vision + {nt} text tokens) per GPU",
+            "layers": args.layers, "cuda_graph": bool(args.graph),
             "samples_per_gpu": b, "seq_len": 1 + nv + 2 + 1 + nt, "tokens_per_gpu": tokens_per_gpu,
             "lora_r": args.lora, "parallelism": f"dp{args.gpus} (samples sharded, no collective)",
             "l2": "per-step working set (0.81 GB weights + >0.5 GB activations) exceeds the 126 MB L2; no flush needed"}
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
-def make_gpu_layer(device, lora_r: int):
+def make_gpu_layer(device, lora_r: int, seed: int = 0):
     """Random-init layer with the reference's init (Linear ~ N(0, 0.02)), generated on the device."""
     from mmmm_b200.modeling_cogvlm import CogVLMDecoderLayer, VexConfig
     from mmmm_b200.peft_compat import attach_mock_lora
-    torch.manual_seed(0)
     with torch.device("meta"):
         layer = CogVLMDecoderLayer(VexConfig(hidden_size=H, intermediate_size=I, num_attention_heads=HEADS))
     layer = layer.to_empty(device=device).to(torch.bfloat16)
-    g = torch.Generator(device=device).manual_seed(0)
+    g = torch.Generator(device=device).manual_seed(seed)
     with torch.no_grad():
         for m in layer.modules():
             if isinstance(m, torch.nn.Linear):
@@ -175,23 +175,34 @@ def make_gpu_layer(device, lora_r: int):
         rot = layer.self_attn.rotary_emb
         rot.inv_freq = (1.0 / (rot.base ** (torch.arange(0, 128, 2, device=device) / 128))).to(torch.bfloat16)
     if lora_r:
+        torch.manual_seed(seed)
         attach_mock_lora(layer, r=lora_r, lora_alpha=8, b_std=0.02)
     return layer.eval()
+
+
+def ncu_traffic(key: str):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (not live)."""
+    f = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(f)).get(key)
+    except Exception:
+        return None
 
 
 def run_ours(args):
     import torch.distributed as dist
     from mmmm_b200 import ops  # noqa: F401  (loads libvex.so; raises if it is missing)
-    from mmmm_b200._lib import lib
-    from mmmm_b200.inputs import make_inputs
     from mmmm_b200 import instrument
+    from mmmm_b200._lib import lib
+    from mmmm_b200.graph import GraphedPrefill
+    from mmmm_b200.inputs import make_inputs
+    from mmmm_b200.sharding import max_over_ranks
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("--gpus N > 1 must be launched with torchrun (one rank per GPU)")
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("--gpus N > 1 must be launched with torchrun (one rank per GPU)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if lib().vex_device_check() != 0:
@@ -200,26 +211,61 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     b, nv, nt = WORKLOADS[args.workload]
-    layer = make_gpu_layer(dev, args.lora)
+    layers = [make_gpu_layer(dev, args.lora, seed=i) for i in range(args.layers)]
     host = make_inputs(b, nv, nt, H, seed=rank)
-    pin = lambda t: t.pin_memory()
-    h_host, tt_host, pos_host, pm_host = map(pin, (host.hidden_states, host.token_type_ids, host.position_ids,
-                                                   host.padding_mask))
-    out_host = torch.empty_like(h_host).pin_memory()
     tokens = host.num_valid_tokens
     inp = host.to(dev)
 
-    def step():
-        return layer(inp.hidden_states, token_type_ids=inp.token_type_ids, position_ids=inp.position_ids,
-                     padding_mask=inp.padding_mask)[0]
+    def forward(hs, tt, pos, pm):
+        for layer in layers:
+            hs = layer(hs, token_type_ids=tt, position_ids=pos, padding_mask=pm)[0]
+        return hs
+
+    graphed = None
+    if args.graph:
+        graphed = GraphedPrefill(layers, inp.hidden_states, inp.token_type_ids, inp.position_ids, inp.padding_mask)
+        step = graphed.replay
+    else:
+        def step():
+            return forward(inp.hidden_states, inp.token_type_ids, inp.position_ids, inp.padding_mask)
+
+    # ---- e2e: the public module call on HOST (pinned) inputs; H2D + D2H inside the timed region.  Two requests
+    # are kept in flight (copy-in stream / compute stream / copy-out stream, double-buffered) the way a serving
+    # loop would, so the copies of step i+1 / i-1 overlap the compute of step i.
+    pin = lambda t: t.pin_memory()
+    h_host, tt_host, pos_host, pm_host = map(pin, (host.hidden_states, host.token_type_ids, host.position_ids,
+                                                   host.padding_mask))
+    out_host = [torch.empty_like(h_host).pin_memory() for _ in range(2)]
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    dev_in = [tuple(torch.empty_like(t, device=dev) for t in (h_host, tt_host, pos_host, pm_host)) for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
+    ev_copied = [torch.cuda.Event() for _ in range(2)]
+    e2e_state = {"i": 0, "keep": [None, None]}
 
     def step_e2e():
-        hs = h_host.to(dev, non_blocking=True)
-        tt = tt_host.to(dev, non_blocking=True)
-        pos = pos_host.to(dev, non_blocking=True)
-        pm = pm_host.to(dev, non_blocking=True)
-        out = layer(hs, token_type_ids=tt, position_ids=pos, padding_mask=pm)[0]
-        out_host.copy_(out, non_blocking=True)
+        i = e2e_state["i"]
+        k = i & 1
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(s_in):
+            if i >= 2:
+                s_in.wait_event(ev_free[k])        # compute of step i-2 has consumed this input buffer
+            for d, src in zip(dev_in[k], (h_host, tt_host, pos_host, pm_host)):
+                d.copy_(src, non_blocking=True)
+            ev_in[k].record(s_in)
+        cur.wait_event(ev_in[k])
+        out = forward(*dev_in[k])
+        ev_free[k].record(cur)
+        ev_out[k].record(cur)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_out[k])
+            if i >= 2:
+                pass                                # out_host[k] of step i-2 was already copied (stream order)
+            out_host[k].copy_(out, non_blocking=True)
+            ev_copied[k].record(s_out)
+        out.record_stream(s_out)
+        e2e_state["i"] = i + 1
 
     def barrier():
         if world > 1:
@@ -231,77 +277,89 @@ def run_ours(args):
             for _ in range(warmup):
                 fn()
             barrier()
+            t0 = time.perf_counter()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             instrument.reset()
             e0.record()
             for _ in range(steps):
                 fn()
             e1.record()
+            launches = instrument.launches()
             barrier()
-        ms = e0.elapsed_time(e1)
-        launches = instrument.launches()
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
-        return ms / steps, launches
+            wall_ms = (time.perf_counter() - t0) * 1e3
+        ms = max(e0.elapsed_time(e1), 0.0)
+        return ms, wall_ms, launches
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_step, launches = timed(step, args.steps, args.warmup)
+    ms_total, _, launches = timed(step, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, _ = timed(step_e2e, max(3, args.steps // 2), 3)
+    ms_step = max_over_ranks(ms_total, dev) / args.steps
+    if args.graph:  # launches inside a replayed graph are not visible to the Python counter: count one eager step
+        with torch.no_grad():
+            instrument.reset()
+            forward(inp.hidden_states, inp.token_type_ids, inp.position_ids, inp.padding_mask)
+            launches = instrument.launches() * args.steps
+            torch.cuda.synchronize()
+    e2e_steps = max(4, args.steps // 2)
+    # the e2e region ends when the last D2H has landed: use the wall clock around a full synchronize
+    _, wall_e2e, _ = timed(step_e2e, e2e_steps, 4)
+    ms_e2e = max_over_ranks(wall_e2e, dev) / e2e_steps
 
-    # per-kernel breakdown of one step (CUDA events on the launching stream around every libvex call)
     kernels = None
     if rank == 0:
         with torch.no_grad():
-            kernels = instrument.profile(step, iters=max(5, args.steps // 2))
+            eager_step = lambda: forward(inp.hidden_states, inp.token_type_ids, inp.position_ids, inp.padding_mask)
+            kernels = instrument.profile(eager_step, iters=max(5, args.steps // 4))
     if world > 1:
         dist.barrier()
-
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+
     pk = peaks()
-    total_tokens = tokens * world  # same shape on every rank; ragged=False so the count is identical
+    nl = args.layers
+    total_tokens = tokens * world  # same shapes on every rank (ragged=False)
     value = total_tokens / (ms_step / 1e3)
-    flop_step = tokens * GEMM_FLOP_PER_TOKEN
     seq = 1 + nv + 2 + 1 + nt
-    attn_flop = b * 4 * HEADS * 128 * seq * (seq + 1) // 2
-    lora_flop = tokens * 2 * args.lora * 69888 * 2 // 2 if args.lora else 0
-    tf_layer = (flop_step + attn_flop + lora_flop) / (ms_step / 1e3) / 1e12
-    # dominant kernel: the gate/up SwiGLU grouped GEMM (2 * T * H * 2I flop per launch)
+    flop_gemm = tokens * GEMM_FLOP_PER_TOKEN * nl
+    flop_attn = b * 4 * HEADS * 128 * seq * (seq + 1) // 2 * nl
+    flop_lora = tokens * 2 * args.lora * 69888 * nl if args.lora else 0
+    tf_layer = (flop_gemm + flop_attn + flop_lora) / (ms_step / 1e3) / 1e12
     roof = None
-    if kernels:
-        gu = kernels.get("gemm_swiglu")
-        if gu:
-            flop = 2.0 * tokens * H * 2 * I + (2.0 * tokens * args.lora * 2 * I if args.lora else 0)
-            ach = flop / (gu["ms"] / 1e3) / 1e12
-            roof = {"kernel": "k3_grouped_gemm<256> (SwiGLU gate/up)", "bound": "tensor", "achieved": ach,
-                    "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
-                    "traffic": None, "peak_source": pk["source"] + " (burst figure)",
-                    "flop_per_launch": flop, "ms_per_launch": gu["ms"]}
+    if kernels and "gemm_swiglu" in kernels:
+        gu = kernels["gemm_swiglu"]
+        flop = 2.0 * tokens * H * 2 * I + (2.0 * tokens * args.lora * 2 * I if args.lora else 0)
+        ms_launch = gu["ms"] / max(gu["calls_per_step"], 1)
+        ach = flop / (ms_launch / 1e3) / 1e12
+        roof = {"kernel": "k3_grouped_gemm<256> (SwiGLU gate/up)", "bound": "tensor", "achieved": ach,
+                "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+                "traffic": ncu_traffic(f"gemm_swiglu_{args.workload}"), "peak_source": pk["source"] + " (burst figure)",
+                "flop_per_launch": flop, "ms_per_launch": ms_launch}
     cpu = None
     if world == 1 and not args.no_cpu:
         ctok, ctimes = cpu_forward_timer(args.workload, 3, 1, args.lora)
         best = min(ctimes)
         cpu = {"value": ctok / best, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"1 of {b} samples ({ctok} tokens), fp32 eager oracle, best of 3 after 1 warm-up"}
+               "sample": f"1 of {b} samples ({ctok} tokens), 1 layer, fp32 eager oracle, best of 3 after 1 warm-up"}
+        if nl > 1:
+            cpu["value"] /= nl
+            cpu["sample"] += f"; scaled by 1/{nl} for the {nl}-layer stack"
     h2d = sum(t.numel() * t.element_size() for t in (h_host, tt_host, pos_host, pm_host))
-    d2h = out_host.numel() * out_host.element_size()
+    d2h = out_host[0].numel() * out_host[0].element_size()
+    cfg = config_dict(args, tokens)
     print(json.dumps({
         "metric": "visual-expert prefill tokens/s", "value": value, "unit": "tokens/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": config_dict(args, tokens),
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
         "tokens_per_s_per_gpu": value / world,
         "layer_tflops_per_gpu": tf_layer, "layer_frac_of_bf16_peak": tf_layer / pk["bf16_tflops"],
         "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
         "e2e": {"value": total_tokens / (ms_e2e / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
+                "how": "layer(...) on pinned host inputs; 2 requests in flight (H2D / compute / D2H streams)"},
         "gpu_launches": launches, "clocks": clocks, "peaks": pk,
     }))
     if world > 1:
@@ -311,12 +369,14 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--lora", type=int, default=0, help="LoRA rank on all ten Linears (0 = frozen weights only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--layers", type=int, default=1, help="decoder layers per step (32 = the full stack, config 3/4)")
+    ap.add_argument("--graph", type=int, default=1, help="1: replay the forward as one CUDA graph (default), 0: eager")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -76,15 +76,16 @@ int vex_partition(const int64_t* token_type_ids, const uint8_t* padding_mask, in
                   int32_t* token_to_sorted, int32_t* token_to_flat, int32_t* cu_seqlens, int32_t* counts,
                   int32_t* scratch, vexStream stream);
 
-/* K2 -- fused RMSNorm with gather.  Replaces RMSNorm.forward (:36-41) + hidden_states[padding_mask]
- * (:307, :326): y[r] = bf16( w * ( f32(x[src[r]]) * rsqrt(mean(f32(x)^2) + eps) ) ) for r < *n_rows.
- *   x [*, H] bf16 rows addressed through row_src (NULL = identity); y [rows_cap, H] bf16
+/* K2 -- fused RMSNorm with gather (and optional scatter).  Replaces RMSNorm.forward (:36-41) +
+ * hidden_states[padding_mask] (:307, :326) and, with row_dst, _mask_set (:390-393, the caller's final norm :570-573):
+ * y[dst[r]] = bf16( w * ( f32(x[src[r]]) * rsqrt(mean(f32(x)^2) + eps) ) ) for r < *n_rows.
+ *   x [*, H] bf16 rows addressed through row_src (NULL = identity); y [*, H] bf16 rows through row_dst (NULL = identity)
  *   weight: bf16 (weight_is_fp32 == 0) or fp32; n_rows: device int32 (e.g. counts + VEX_COUNT_VALID)
  *   H in {256, 512, ..., 1536, 2048, 4096} (whole row kept in registers by one warp).
  */
 int vex_rmsnorm_gather(const void* x, const void* weight, int weight_is_fp32, float eps,
-                       const int32_t* row_src, const int32_t* n_rows, void* y, int rows_cap, int H,
-                       vexStream stream);
+                       const int32_t* row_src, const int32_t* row_dst, const int32_t* n_rows, void* y, int rows_cap,
+                       int H, vexStream stream);
 
 /* K5 -- standalone SiLU gate: out = bf16(bf16(silu(gate)) * up), rows < *n_rows.  Replaces
  * act_fn(gate_proj(x)) * up_proj(x) (:55) when the SwiGLU epilogue of vex_grouped_gemm is not used. */

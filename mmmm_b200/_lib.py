@@ -65,7 +65,7 @@ def lib() -> C.CDLL:
         L.vex_last_cuda_error.restype = C.c_int
         L.vex_device_check.restype = C.c_int
         L.vex_partition.argtypes = [p, p, i32, i32, p, p, p, p, p, p, p, p, p]
-        L.vex_rmsnorm_gather.argtypes = [p, p, i32, f32, p, p, p, i32, i32, p]
+        L.vex_rmsnorm_gather.argtypes = [p, p, i32, f32, p, p, p, p, i32, i32, p]
         L.vex_silu_mul.argtypes = [p, p, p, p, i32, i32, p]
         L.vex_residual_scatter.argtypes = [p, p, p, p, p, i32, i32, p]
         L.vex_copy_padded_rows.argtypes = [p, p, p, i32, i32, p]

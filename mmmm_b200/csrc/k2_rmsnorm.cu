@@ -13,8 +13,8 @@ constexpr int K2_WARPS = 8;
 template <int NCHUNK>  // H = NCHUNK * 256
 __global__ void __launch_bounds__(K2_WARPS * 32)
     k2_rmsnorm(const __nv_bfloat16* __restrict__ x, const void* __restrict__ weight, int weight_is_fp32, float eps,
-               const int32_t* __restrict__ row_src, const int32_t* __restrict__ n_rows_ptr,
-               __nv_bfloat16* __restrict__ y, int rows_cap) {
+               const int32_t* __restrict__ row_src, const int32_t* __restrict__ row_dst,
+               const int32_t* __restrict__ n_rows_ptr, __nv_bfloat16* __restrict__ y, int rows_cap) {
   constexpr int H = NCHUNK * 256;
   const int lane = lane_id();
   const int n_rows = min(*n_rows_ptr, rows_cap);
@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(K2_WARPS * 32)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float inv = rsqrtf(ss * (1.0f / H) + eps);
-    uint4* yp = reinterpret_cast<uint4*>(y + static_cast<int64_t>(r) * H);
+    const int dst = row_dst ? row_dst[r] : r;
+    uint4* yp = reinterpret_cast<uint4*>(y + static_cast<int64_t>(dst) * H);
 #pragma unroll
     for (int i = 0; i < NCHUNK; ++i) {
       const int col = (i * 32 + lane) * 8;
@@ -76,8 +77,8 @@ __global__ void __launch_bounds__(K2_WARPS * 32)
 }  // namespace vex
 
 extern "C" int vex_rmsnorm_gather(const void* x, const void* weight, int weight_is_fp32, float eps,
-                                  const int32_t* row_src, const int32_t* n_rows, void* y, int rows_cap, int H,
-                                  vexStream stream) {
+                                  const int32_t* row_src, const int32_t* row_dst, const int32_t* n_rows, void* y,
+                                  int rows_cap, int H, vexStream stream) {
   if (!x || !weight || !n_rows || !y || rows_cap <= 0) return VEX_E_INVALID;
   if (H % 256 != 0 || H <= 0 || H > 4096) return VEX_E_UNSUPPORTED;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -86,8 +87,8 @@ extern "C" int vex_rmsnorm_gather(const void* x, const void* weight, int weight_
   auto yp = static_cast<__nv_bfloat16*>(y);
 #define VEX_K2_CASE(NC)                                                                                        \
   case NC:                                                                                                     \
-    vex::k2_rmsnorm<NC><<<grid, vex::K2_WARPS * 32, 0, s>>>(xp, weight, weight_is_fp32, eps, row_src, n_rows, \
-                                                             yp, rows_cap);                                    \
+    vex::k2_rmsnorm<NC><<<grid, vex::K2_WARPS * 32, 0, s>>>(xp, weight, weight_is_fp32, eps, row_src, row_dst, \
+                                                             n_rows, yp, rows_cap);                                   \
     break;
   switch (H / 256) {
     VEX_K2_CASE(1) VEX_K2_CASE(2) VEX_K2_CASE(3) VEX_K2_CASE(4) VEX_K2_CASE(5) VEX_K2_CASE(6) VEX_K2_CASE(8)

@@ -186,6 +186,21 @@ class VisionExpertAttention(nn.Module):
                 _apply_prefix(prefix, "vision_expert_dense")], []
 
 
+def masked_rms_norm(norm: nn.Module, hidden_states: torch.Tensor, token_type_ids: torch.Tensor,
+                    padding_mask: torch.Tensor) -> torch.Tensor:
+    """``_mask_set(h, pm, norm(h[pm]))`` -- the caller's final norm (modeling_cogvlm.py:570-573, :390-393): rows
+    with ``padding_mask == True`` are normalised in place of a fresh copy, the others pass through."""
+    plan = GLOBAL_PLAN_CACHE.get(token_type_ids, padding_mask)
+    mod = resolve_norm(norm)
+    B, L, H = hidden_states.shape
+    x = hidden_states.contiguous().view(B * L, H)
+    out = torch.empty_like(x)
+    ops.copy_padded_rows(x, plan.flat_to_sorted, out)
+    ops.rmsnorm_gather(x, mod.weight.detach(), mod.variance_epsilon, plan.token_to_flat, plan.n_valid, out,
+                       plan.token_to_flat)
+    return out.view(B, L, H)
+
+
 def get_expert_mask(token_type_ids: torch.Tensor, padding_mask: torch.Tensor):
     """Boolean masks with the reference's meaning (:58-70), derived from the K1 plan without a host sync."""
     plan = GLOBAL_PLAN_CACHE.get(token_type_ids, padding_mask)

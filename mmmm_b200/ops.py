@@ -68,7 +68,7 @@ def partition(token_type_ids: torch.Tensor, padding_mask: torch.Tensor, sorted_t
 # ------------------------------------------------------------------------------------------ K2
 @torch.library.custom_op("vex::rmsnorm_gather", mutates_args=("out",))
 def rmsnorm_gather(x: torch.Tensor, weight: torch.Tensor, eps: float, row_src: Optional[torch.Tensor],
-                   n_rows: torch.Tensor, out: torch.Tensor) -> None:
+                   n_rows: torch.Tensor, out: torch.Tensor, row_dst: Optional[torch.Tensor] = None) -> None:
     """K2 (vex_rmsnorm_gather): RMSNorm.forward (modeling_cogvlm.py:36-41) fused with the row gather."""
     _dev(x, "x", _BF16)
     _dev(out, "out", _BF16)
@@ -80,12 +80,14 @@ def rmsnorm_gather(x: torch.Tensor, weight: torch.Tensor, eps: float, row_src: O
         raise ValueError("hidden size mismatch")
     if row_src is not None:
         _dev(row_src, "row_src", torch.int32)
+    if row_dst is not None:
+        _dev(row_dst, "row_dst", torch.int32)
     _dev(n_rows, "n_rows", torch.int32)
     rows_cap = out.numel() // H
     with instrument.region("rmsnorm"):
       rc = _lib.lib().vex_rmsnorm_gather(x.data_ptr(), weight.data_ptr(), int(weight.dtype == torch.float32),
-                                       float(eps), _ptr(row_src), n_rows.data_ptr(), out.data_ptr(), rows_cap, H,
-                                       _stream())
+                                       float(eps), _ptr(row_src), _ptr(row_dst), n_rows.data_ptr(), out.data_ptr(),
+                                       rows_cap, H, _stream())
     _lib.check(rc, "vex_rmsnorm_gather")
 
 
@@ -241,7 +243,7 @@ def attention(qkv: torch.Tensor, cu_seqlens: torch.Tensor, batch: int, max_len_c
         raise ValueError("qkv rows must be [3 * heads * 128] wide (head_dim 128 only)")
     if out_row_map is not None:
         _dev(out_row_map, "out_row_map", torch.int32)
-    with instrument.region("attention"):
+    with instrument.region("attention", 2):  # tail-row zeroing + the attention kernel
       rc = _lib.lib().vex_attention(qkv.data_ptr(), cu_seqlens.data_ptr(), batch, max_len_cap, heads,
                                   _ptr(out_row_map), out.data_ptr(), float(scale), _stream())
     _lib.check(rc, "vex_attention")

@@ -293,8 +293,11 @@ def test_k3_rope_epilogue_scatter_to_token_order():
 
 
 # ------------------------------------------------------------------------------------------ K4
-@pytest.mark.parametrize("lens", [[1], [64], [65, 3, 128], [300, 17, 1, 255], [1357], [700, 1485]])
-def test_k4_attention_vs_oracle(lens):
+@pytest.mark.parametrize("impl", ["tc", "mma"])
+@pytest.mark.parametrize("lens", [[1], [64], [65, 3, 128], [129, 128, 127], [300, 17, 1, 255], [1357], [700, 1485]])
+def test_k4_attention_vs_oracle(lens, impl, monkeypatch):
+    """Both implementations (tcgen05/TMEM fast path and the mma.sync baseline) against the oracle."""
+    monkeypatch.setenv("VEX_ATTN_IMPL", impl)
     ops = _ops()
     heads = 3
     B, Lmax = len(lens), max(lens)
@@ -308,7 +311,7 @@ def test_k4_attention_vs_oracle(lens):
     # token-order packed qkv [T, 3, heads, 128]
     tok = lambda t: t.permute(0, 2, 1, 3)[pm]            # [T, heads, 128]
     qkv = torch.stack([tok(q), tok(k), tok(v)], dim=1).reshape(T, 3 * heads * 128).contiguous()
-    qkv_buf = torch.zeros(B * Lmax, 3 * heads * 128, dtype=torch.bfloat16)
+    qkv_buf = torch.full((B * Lmax, 3 * heads * 128), float("nan"), dtype=torch.bfloat16)  # tail rows are garbage
     qkv_buf[:T] = qkv
     cu = torch.zeros(B + 1, dtype=torch.int32)
     cu[1:] = torch.tensor(lens).cumsum(0)

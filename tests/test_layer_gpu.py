@@ -205,3 +205,36 @@ def test_c1_one_sample_full_width_vs_oracle():
                              num_heads=heads)
     mx, fro = _errs(out.cpu()[0], ref[0])
     assert mx <= MAX_REL and fro <= FRO_REL, (mx, fro)
+
+
+def test_graphed_prefill_and_masked_final_norm():
+    """CUDA-graph replay of a 2-layer stack + the caller's masked final norm (:570-573) equals the eager module
+    calls bit-for-bit, and the graph re-routes when the static id buffers are refilled (K1 is inside the graph)."""
+    from mmmm_b200.graph import GraphedPrefill
+    from mmmm_b200.inputs import make_inputs
+    from mmmm_b200.modeling_cogvlm import RMSNorm, masked_rms_norm
+    H, I, heads = 512, 768, 4
+    ws = [O.random_weights(H, I, heads, seed=s, dtype=torch.bfloat16) for s in (1, 2)]
+    layers = [_make_layer(w, dict(hidden_size=H, intermediate_size=I, num_attention_heads=heads)) for w in ws]
+    norm = RMSNorm(H).to(torch.bfloat16).cuda()
+    norm.weight.data.copy_(1 + 0.1 * torch.randn(H))
+    a = make_inputs(2, 120, 50, H, ragged=True, seed=9).to("cuda")
+    b = make_inputs(2, 120, 50, H, ragged=True, seed=10).to("cuda")     # different padding / contents, same shape
+
+    def eager(x):
+        h = x.hidden_states
+        with torch.no_grad():
+            for layer in layers:
+                (h,) = layer(h, token_type_ids=x.token_type_ids, position_ids=x.position_ids, padding_mask=x.padding_mask)
+            return masked_rms_norm(norm, h, x.token_type_ids, x.padding_mask)
+
+    g = GraphedPrefill(layers, a.hidden_states, a.token_type_ids, a.position_ids, a.padding_mask, final_norm=norm)
+    for x in (a, b, a):
+        got = g(x.hidden_states, x.token_type_ids, x.position_ids, x.padding_mask).clone()
+        assert torch.equal(got, eager(x))
+    # and the stack + final norm against the oracle
+    ref = O.decoder_stack(ws, a.hidden_states.cpu(), a.token_type_ids.cpu(), a.position_ids.cpu(), a.padding_mask.cpu(),
+                          num_heads=heads, final_norm_weight=norm.weight.detach().cpu())
+    pm = a.padding_mask.cpu()
+    mx, fro = _errs(eager(a).cpu()[pm], ref[pm])
+    assert mx <= 2 * MAX_REL and fro <= 2 * FRO_REL, (mx, fro)

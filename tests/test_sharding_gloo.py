@@ -1,0 +1,57 @@
+"""world_size-2 gloo test (CPU) of the N > 1 host logic: contiguous sample sharding covers the batch exactly, the
+per-rank results concatenate to the full-batch result (samples are independent on this path -- checked with the
+oracle, the product has no CPU path), and timing is reduced with max over ranks."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mmmm_b200.sharding import shard_range
+
+
+def test_shard_range_partitions():
+    for n in (1, 7, 8, 64, 65):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+def _worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mmmm_b200.inputs import make_inputs
+        from mmmm_b200.sharding import max_over_ranks, shard_batch, sum_over_ranks
+        from oracle import oracle_layer as O
+        torch.set_num_threads(2)
+        H, I, heads = 256, 256, 2
+        w = O.random_weights(H, I, heads, seed=0)
+        inp = make_inputs(5, 12, 7, H, ragged=True, seed=3, dtype=torch.float32)   # same global batch on all ranks
+        h, tt, pos, pm = shard_batch((inp.hidden_states, inp.token_type_ids, inp.position_ids, inp.padding_mask),
+                                     rank, world)
+        (out,) = O.decoder_layer(w, h, tt, pos, pm, num_heads=heads)
+        torch.save(dict(out=out, n=int(pm.sum())), os.path.join(tmp, f"r{rank}.pt"))
+        assert max_over_ranks(10.0 + rank) == 10.0 + world - 1
+        total = sum_over_ranks(float(pm.sum()))
+        assert total == float(inp.padding_mask.sum())
+        dist.barrier()
+        if rank == 0:
+            (full,) = O.decoder_layer(w, inp.hidden_states, inp.token_type_ids, inp.position_ids, inp.padding_mask,
+                                      num_heads=heads)
+            parts = torch.cat([torch.load(os.path.join(tmp, f"r{r}.pt"))["out"] for r in range(world)])
+            m = inp.padding_mask
+            torch.testing.assert_close(parts[m], full[m], rtol=1e-5, atol=1e-6)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharded_forward(tmp_path):
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)

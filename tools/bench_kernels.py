@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Per-kernel timing on the GPU box (CUDA events, L2-sized working sets): attention implementations and the
+grouped GEMM at the BASELINE config-2 shapes.  Prints one JSON line per measurement."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mmmm_b200 import ops  # noqa: E402
+from mmmm_b200.inputs import make_ids  # noqa: E402
+from mmmm_b200.plan import build_plan  # noqa: E402
+
+
+def timeit(fn, iters=20, warmup=5):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def bench_attention(B=8, nv=1225, nt=256, heads=32):
+    tt, pos, pm = make_ids(B, nv, nt)
+    plan = build_plan(tt.cuda(), pm.cuda())
+    L = tt.shape[1]
+    cap = B * L
+    qkv = torch.randn(cap, 3 * heads * 128, device="cuda").bfloat16()
+    out = torch.empty(cap, heads * 128, device="cuda", dtype=torch.bfloat16)
+    flop = B * 4 * heads * 128 * L * (L + 1) / 2
+    res = {}
+    for impl in ("mma", "tc"):
+        os.environ["VEX_ATTN_IMPL"] = impl
+        ms = timeit(lambda: ops.attention(qkv, plan.cu_seqlens, B, L, heads, plan.token_to_sorted, out, 128 ** -0.5))
+        res[impl] = out.clone()
+        print(json.dumps({"kernel": f"attention_{impl}", "B": B, "L": L, "ms": ms, "tflops": flop / ms / 1e9}))
+    d = (res["mma"].float() - res["tc"].float()).abs().max().item()
+    print(json.dumps({"attention_mma_vs_tc_maxabs": d}))
+    os.environ.pop("VEX_ATTN_IMPL", None)
+
+
+def bench_gemm(Tv=9808, Tl=2072):
+    H, I = 4096, 11008
+    cap = Tv + Tl
+    counts = torch.tensor([Tv, Tl, cap, 0], dtype=torch.int32, device="cuda")
+    mk = lambda *s: (torch.randn(*s, device="cuda") * 0.02).bfloat16()
+    x = mk(cap, H)
+    for name, N, K, mode in (("qkv", 3 * H, H, ops.EPI_PLAIN), ("dense", H, H, ops.EPI_PLAIN),
+                             ("gateup_swiglu", I, H, ops.EPI_SWIGLU), ("down", H, I, ops.EPI_PLAIN)):
+        a = x if K == H else mk(cap, K)
+        w = [mk(N, K), mk(N, K) if mode == ops.EPI_SWIGLU else None, mk(N, K), mk(N, K) if mode == ops.EPI_SWIGLU else None]
+        out = torch.empty(cap, N, device="cuda", dtype=torch.bfloat16)
+        ms = timeit(lambda: ops.grouped_gemm_fused(a, w, out, counts, mode, None, None, [None, None], [None] * 4, 0,
+                                                   [], 0, False, 1.0))
+        flop = 2.0 * cap * N * K * (2 if mode == ops.EPI_SWIGLU else 1)
+        ref = timeit(lambda: torch.matmul(a, w[0].T))
+        print(json.dumps({"kernel": f"gemm_{name}", "M": cap, "N": N, "K": K, "ms": ms, "tflops": flop / ms / 1e9,
+                          "cublas_single_expert_ms": ref, "cublas_tflops": 2.0 * cap * N * K / ref / 1e9}))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "attention"):
+        bench_attention()
+        bench_attention(B=2, nv=2048, nt=512)
+    if which in ("all", "gemm"):
+        bench_gemm()
