@@ -27,6 +27,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -45,6 +46,7 @@ struct alignas(64) GemmTmaps {
   CUtensorMap w[2][2];   // [expert][half] weights [N, K]
   CUtensorMap t[2];      // [half] LoRA T = s * X.A^T [rows_cap, r]
   CUtensorMap lb[2][2];  // [expert][half] lora_B [N, r]
+  CUtensorMap lb64[2][2];  // same tensors with 64-row boxes (CTA-pair kernel, SwiGLU LoRA steps)
 };
 
 struct GemmDev {
@@ -136,6 +138,164 @@ __device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* p, float (&o)[
     for (int j = 0; j < 4; ++j) {
       o[8 * i + 2 * j] = bf16_lo(w[j]);
       o[8 * i + 2 * j + 1] = bf16_hi(w[j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// epilogue of one 128 x BN accumulator tile, executed by one of the four epilogue warps (32 rows each)
+//   t_acc      : TMEM address of this warp's lane quarter at the accumulator's first column
+//   release()  : called once, right after the last TMEM read of the tile (hands the accumulator back)
+// ---------------------------------------------------------------------------------------------
+template <int BN, class Release>
+__device__ __forceinline__ void epilogue_tile(const GemmDev& p, int e, int m, int n, int cnt0, int cnt1,
+                                              uint32_t t_acc, uint32_t stage_base, int lane, int ew,
+                                              Release release) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int PANEL = Cfg::PANEL;
+  constexpr int PITCH = Cfg::PANEL_BYTES;
+  constexpr int LPR = PITCH / 16;  // lanes per staged row during write-out
+  constexpr int RPI = 32 / LPR;    // rows per write-out iteration
+  const uint32_t stage_row = stage_base + static_cast<uint32_t>(lane * PITCH);
+
+  // coalesced write-out of one staged panel: out[g, col0 + ...] for the 32 rows of this warp
+  auto write_panel = [&](int g_row, int col0, bool add_residual) {
+#pragma unroll 4
+    for (int it = 0; it < 32 / RPI; ++it) {
+      const int rr = it * RPI + lane / LPR;
+      const int piece = lane % LPR;
+      const int g = __shfl_sync(0xffffffffu, g_row, rr);
+      const int col = col0 + piece * 8;
+      if (g >= 0 && col < p.N) {
+        uint4 v = ld_shared_v4(stage_base + static_cast<uint32_t>(rr * PITCH + ((piece ^ (rr & 7)) << 4)));
+        const int64_t off = static_cast<int64_t>(g) * p.ldo + col;
+        if (add_residual) {
+          const uint4 r4 = ld_stream(p.residual + off);
+          const uint32_t a[4] = {v.x, v.y, v.z, v.w}, b[4] = {r4.x, r4.y, r4.z, r4.w};
+          uint32_t* vp = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            vp[j] = pack_bf16(bf16_lo(a[j]) + bf16_lo(b[j]), bf16_hi(a[j]) + bf16_hi(b[j]));
+        }
+        *reinterpret_cast<uint4*>(p.out + off) = v;
+      }
+    }
+  };
+
+  const int r_local = m * BM + ew * 32 + lane;
+  const bool valid = r_local < (e ? cnt1 : cnt0);
+  const int s_row = (e ? cnt0 : 0) + r_local;
+  int g_row = -1;
+  int pos = 0;
+  if (valid) {
+    g_row = p.row_map ? p.row_map[s_row] : s_row;
+    if (p.mode == VEX_EPI_ROPE) {
+      const int64_t pz = p.position_ids[p.sorted_to_flat[s_row]];
+      pos = static_cast<int>(min(max(pz, int64_t(0)), int64_t(p.rope_len - 1)));
+    }
+  }
+  uint32_t raw[32];
+  float v[32];
+
+  if (p.mode == VEX_EPI_SWIGLU) {
+    if constexpr (BN == 256) {
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        uint32_t raw_u[32];
+        tmem_ld_32x32b_x32(t_acc + q * 32, raw);
+        tmem_ld_32x32b_x32(t_acc + 128 + q * 32, raw_u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float g = bf16r(__uint_as_float(raw[j]));    // gate_proj output, bf16 like the eager Linear
+          const float u = bf16r(__uint_as_float(raw_u[j]));  // up_proj output
+          v[j] = bf16r(silu_acc(g)) * u;                     // silu -> bf16, product -> bf16 (on store)
+        }
+        stage_piece32(stage_row, q * 4, lane, v);
+      }
+      release();
+      write_panel(g_row, n * 128, false);
+      __syncwarp();
+    }
+  } else {
+    constexpr int NPANEL = BN / PANEL;
+#pragma unroll 1
+    for (int pn = 0; pn < NPANEL; ++pn) {
+      const int col0 = n * BN + pn * PANEL;
+      if (p.mode == VEX_EPI_ROPE && col0 < p.rope_cols) {
+        if constexpr (PANEL == 128) {
+          // one head: pairs (j, j + 64); thread owns the whole row so both halves are local
+#pragma unroll 1
+          for (int q = 0; q < 2; ++q) {
+            uint32_t raw_hi[32];
+            tmem_ld_32x32b_x32(t_acc + pn * PANEL + q * 32, raw);
+            tmem_ld_32x32b_x32(t_acc + pn * PANEL + 64 + q * 32, raw_hi);
+            const __nv_bfloat16* cr = p.rope_cos + static_cast<int64_t>(pos) * 128 + q * 32;
+            const __nv_bfloat16* sr = p.rope_sin + static_cast<int64_t>(pos) * 128 + q * 32;
+            uint4 ct[4], st[4];  // packed bf16 table entries for columns q*32 .. q*32+31
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              ct[i] = __ldg(reinterpret_cast<const uint4*>(cr) + i);
+              st[i] = __ldg(reinterpret_cast<const uint4*>(sr) + i);
+            }
+            tmem_ld_wait();
+            // x1 = q[j], x2 = q[j + 64] as the eager bf16 Linear would have produced them
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              raw[j] = __float_as_uint(bf16r(__uint_as_float(raw[j])));
+              raw_hi[j] = __float_as_uint(bf16r(__uint_as_float(raw_hi[j])));
+            }
+            // first half: q*cos + rotate_half(q)*sin, rotate_half(q)[j] = -q[j + 64]; every product and the
+            // sum are rounded to bf16 like the eager ops (the sum is rounded by the bf16 pack)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const uint32_t cw = reinterpret_cast<const uint32_t*>(ct)[j >> 1];
+              const uint32_t sw = reinterpret_cast<const uint32_t*>(st)[j >> 1];
+              const float cj = (j & 1) ? bf16_hi(cw) : bf16_lo(cw);
+              const float sj = (j & 1) ? bf16_hi(sw) : bf16_lo(sw);
+              v[j] = bf16r(__uint_as_float(raw[j]) * cj) - bf16r(__uint_as_float(raw_hi[j]) * sj);
+            }
+            stage_piece32(stage_row, q * 4, lane, v);
+            // second half uses the table entries of column j + 64 (equal to column j for the reference's
+            // cat(freqs, freqs) table, but read them anyway)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              ct[i] = __ldg(reinterpret_cast<const uint4*>(cr + 64) + i);
+              st[i] = __ldg(reinterpret_cast<const uint4*>(sr + 64) + i);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const uint32_t cw = reinterpret_cast<const uint32_t*>(ct)[j >> 1];
+              const uint32_t sw = reinterpret_cast<const uint32_t*>(st)[j >> 1];
+              const float cj = (j & 1) ? bf16_hi(cw) : bf16_lo(cw);
+              const float sj = (j & 1) ? bf16_hi(sw) : bf16_lo(sw);
+              v[j] = bf16r(__uint_as_float(raw_hi[j]) * cj) + bf16r(__uint_as_float(raw[j]) * sj);
+            }
+            stage_piece32(stage_row, 8 + q * 4, lane, v);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int q = 0; q < PANEL / 32; ++q) {
+          tmem_ld_32x32b_x32(t_acc + pn * PANEL + q * 32, raw);
+          tmem_ld_wait();
+          if (p.mode == VEX_EPI_PLAIN) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          }
+          stage_piece32(stage_row, q * 4, lane, v);
+        }
+      }
+      if (pn == NPANEL - 1) {  // every TMEM read of this accumulator is done: hand it back
+        release();
+      } else {
+        __syncwarp();
+      }
+      write_panel(g_row, col0, p.mode == VEX_EPI_RESIDUAL);
+      __syncwarp();
     }
   }
 }
@@ -299,166 +459,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
   } else if (warp >= 4) {
     // =============================== epilogue ===============================
-    constexpr int PANEL = Cfg::PANEL;
-    constexpr int PITCH = Cfg::PANEL_BYTES;
-    constexpr int LPR = PITCH / 16;  // lanes per staged row during write-out
-    constexpr int RPI = 32 / LPR;    // rows per write-out iteration
-    const int ew = warp - 4;         // == warp % 4: the TMEM lane quarter this warp may read
+    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
     const uint32_t stage_base = smem_u32(epi_smem + ew * Cfg::EPI_WARP_BYTES);
-    const uint32_t stage_row = stage_base + static_cast<uint32_t>(lane * PITCH);
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
     int acc = 0;
     uint32_t acc_phase = 0;
-
-    // coalesced write-out of one staged panel: out[g, col0 + ...] for the 32 rows of this warp
-    auto write_panel = [&](int g_row, int col0, bool add_residual) {
-#pragma unroll 4
-      for (int it = 0; it < 32 / RPI; ++it) {
-        const int rr = it * RPI + lane / LPR;
-        const int piece = lane % LPR;
-        const int g = __shfl_sync(0xffffffffu, g_row, rr);
-        const int col = col0 + piece * 8;
-        if (g >= 0 && col < p.N) {
-          uint4 v = ld_shared_v4(stage_base + static_cast<uint32_t>(rr * PITCH + ((piece ^ (rr & 7)) << 4)));
-          const int64_t off = static_cast<int64_t>(g) * p.ldo + col;
-          if (add_residual) {
-            const uint4 r4 = ld_stream(p.residual + off);
-            const uint32_t a[4] = {v.x, v.y, v.z, v.w}, b[4] = {r4.x, r4.y, r4.z, r4.w};
-            uint32_t* vp = reinterpret_cast<uint32_t*>(&v);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              vp[j] = pack_bf16(bf16_lo(a[j]) + bf16_lo(b[j]), bf16_hi(a[j]) + bf16_hi(b[j]));
-          }
-          *reinterpret_cast<uint4*>(p.out + off) = v;
-        }
-      }
-    };
-
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord c = decode_tile(tile, mt0, mt1, n_tiles);
-      const int r_local = c.m * BM + ew * 32 + lane;
-      const bool valid = r_local < (c.e ? cnt1 : cnt0);
-      const int s_row = (c.e ? cnt0 : 0) + r_local;
-      int g_row = -1;
-      int pos = 0;
-      if (valid) {
-        g_row = p.row_map ? p.row_map[s_row] : s_row;
-        if (p.mode == VEX_EPI_ROPE) {
-          const int64_t pz = p.position_ids[p.sorted_to_flat[s_row]];
-          pos = static_cast<int>(min(max(pz, int64_t(0)), int64_t(p.rope_len - 1)));
-        }
-      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_acc = t_lane + static_cast<uint32_t>(acc * BN);
-      uint32_t raw[32];
-      float v[32];
-
-      if (p.mode == VEX_EPI_SWIGLU) {
-        if constexpr (BN == 256) {
-#pragma unroll 1
-          for (int q = 0; q < 4; ++q) {
-            uint32_t raw_u[32];
-            tmem_ld_32x32b_x32(t_acc + q * 32, raw);
-            tmem_ld_32x32b_x32(t_acc + 128 + q * 32, raw_u);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float g = bf16r(__uint_as_float(raw[j]));    // gate_proj output, bf16 like the eager Linear
-              const float u = bf16r(__uint_as_float(raw_u[j]));  // up_proj output
-              v[j] = bf16r(silu_acc(g)) * u;                     // silu -> bf16, product -> bf16 (on store)
-            }
-            stage_piece32(stage_row, q * 4, lane, v);
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-          write_panel(g_row, c.n * 128, false);
-          __syncwarp();
-        }
-      } else {
-        constexpr int NPANEL = BN / PANEL;
-#pragma unroll 1
-        for (int pn = 0; pn < NPANEL; ++pn) {
-          const int col0 = c.n * BN + pn * PANEL;
-          if (p.mode == VEX_EPI_ROPE && col0 < p.rope_cols) {
-            if constexpr (PANEL == 128) {
-              // one head: pairs (j, j + 64); thread owns the whole row so both halves are local
-#pragma unroll 1
-              for (int q = 0; q < 2; ++q) {
-                uint32_t raw_hi[32];
-                tmem_ld_32x32b_x32(t_acc + pn * PANEL + q * 32, raw);
-                tmem_ld_32x32b_x32(t_acc + pn * PANEL + 64 + q * 32, raw_hi);
-                const __nv_bfloat16* cr = p.rope_cos + static_cast<int64_t>(pos) * 128 + q * 32;
-                const __nv_bfloat16* sr = p.rope_sin + static_cast<int64_t>(pos) * 128 + q * 32;
-                uint4 ct[4], st[4];  // packed bf16 table entries for columns q*32 .. q*32+31
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  ct[i] = __ldg(reinterpret_cast<const uint4*>(cr) + i);
-                  st[i] = __ldg(reinterpret_cast<const uint4*>(sr) + i);
-                }
-                tmem_ld_wait();
-                // x1 = q[j], x2 = q[j + 64] as the eager bf16 Linear would have produced them
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  raw[j] = __float_as_uint(bf16r(__uint_as_float(raw[j])));
-                  raw_hi[j] = __float_as_uint(bf16r(__uint_as_float(raw_hi[j])));
-                }
-                // first half: q*cos + rotate_half(q)*sin, rotate_half(q)[j] = -q[j + 64]; every product and the
-                // sum are rounded to bf16 like the eager ops (the sum is rounded by the bf16 pack)
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const uint32_t cw = reinterpret_cast<const uint32_t*>(ct)[j >> 1];
-                  const uint32_t sw = reinterpret_cast<const uint32_t*>(st)[j >> 1];
-                  const float cj = (j & 1) ? bf16_hi(cw) : bf16_lo(cw);
-                  const float sj = (j & 1) ? bf16_hi(sw) : bf16_lo(sw);
-                  v[j] = bf16r(__uint_as_float(raw[j]) * cj) - bf16r(__uint_as_float(raw_hi[j]) * sj);
-                }
-                stage_piece32(stage_row, q * 4, lane, v);
-                // second half uses the table entries of column j + 64 (equal to column j for the reference's
-                // cat(freqs, freqs) table, but read them anyway)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  ct[i] = __ldg(reinterpret_cast<const uint4*>(cr + 64) + i);
-                  st[i] = __ldg(reinterpret_cast<const uint4*>(sr + 64) + i);
-                }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const uint32_t cw = reinterpret_cast<const uint32_t*>(ct)[j >> 1];
-                  const uint32_t sw = reinterpret_cast<const uint32_t*>(st)[j >> 1];
-                  const float cj = (j & 1) ? bf16_hi(cw) : bf16_lo(cw);
-                  const float sj = (j & 1) ? bf16_hi(sw) : bf16_lo(sw);
-                  v[j] = bf16r(__uint_as_float(raw_hi[j]) * cj) + bf16r(__uint_as_float(raw[j]) * sj);
-                }
-                stage_piece32(stage_row, 8 + q * 4, lane, v);
-              }
-            }
-          } else {
-#pragma unroll 1
-            for (int q = 0; q < PANEL / 32; ++q) {
-              tmem_ld_32x32b_x32(t_acc + pn * PANEL + q * 32, raw);
-              tmem_ld_wait();
-              if (p.mode == VEX_EPI_PLAIN) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-              }
-              stage_piece32(stage_row, q * 4, lane, v);
-            }
-          }
-          if (pn == NPANEL - 1) {  // every TMEM read of this accumulator is done: hand it back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-          } else {
-            __syncwarp();
-          }
-          write_panel(g_row, col0, p.mode == VEX_EPI_RESIDUAL);
-          __syncwarp();
-        }
-      }
+      epilogue_tile<BN>(p, c.e, c.m, c.n, cnt0, cnt1, t_lane + static_cast<uint32_t>(acc * BN), stage_base, lane, ew,
+                        [&]() {
+                          tc_fence_before();
+                          __syncwarp();
+                          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                        });
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -469,6 +484,242 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 super-tile.
+// Each CTA loads its own 128 A rows and HALF of the B tile (128 weight rows); tcgen05.mma.cta_group::2
+// (M = 256), issued by the leader CTA only, reads both halves of B from the two CTAs' shared memory and writes
+// rows [0,128) of D to the leader's TMEM and rows [128,256) to the peer's.  Per SM this halves the B bytes
+// moved L2 -> SM and read from shared memory by the tensor core (the 1-CTA kernel runs shared memory at
+// ~85 % of its bandwidth), which frees two more pipeline stages (6 x 32 KB) and lowers power.
+//   full[stage]      : leader CTA only; both CTAs' TMA loads post their bytes on it (shared::cluster address)
+//   empty[stage]     : one per CTA; released by the leader's tcgen05.commit multicast to both CTAs
+//   tmem_full[acc]   : one per CTA; tcgen05.commit multicast
+//   tmem_empty[acc]  : leader CTA only, 8 arrivals (4 epilogue warps x 2 CTAs; the peer arrives remotely)
+// ---------------------------------------------------------------------------------------------
+struct PairCfg {
+  static constexpr int BN = 256;
+  static constexpr int STAGES = 6;
+  static constexpr int A_BYTES = BM * BK * 2;          // 16 KB
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;    // 16 KB: this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_WARP_BYTES = GemmCfg<256>::EPI_WARP_BYTES;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int NUM_BARS = 2 * STAGES + 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * EPI_WARP_BYTES + NUM_BARS * 8 + 16 + 1024;
+};
+
+struct PairTile {
+  int e, m2, n;  // expert, index of the 256-row super-tile inside the expert segment, n-tile
+};
+
+__device__ __forceinline__ PairTile decode_pair_tile(int tile, int mp0, int mp1, int n_tiles) {
+  PairTile c;
+  int mp_e = mp0;
+  c.e = 0;
+  const int t0 = mp0 * n_tiles;
+  if (tile >= t0) {
+    c.e = 1;
+    tile -= t0;
+    mp_e = mp1;
+  }
+  constexpr int GROUP = GROUP_M / 2;  // 8 super-tiles = 16 m-tiles per raster group
+  const int per_group = GROUP * n_tiles;
+  const int g = tile / per_group;
+  const int r = tile - g * per_group;
+  const int m_lo = g * GROUP;
+  const int gm = min(GROUP, mp_e - m_lo);
+  c.n = r / gm;
+  c.m2 = m_lo + (r - c.n * gm);
+  return c;
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    k3_grouped_gemm_pair(const __grid_constant__ GemmTmaps tm, const GemmDev p) {
+  using Cfg = PairCfg;
+  constexpr int BN = Cfg::BN;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + 4 * Cfg::EPI_WARP_BYTES);
+  uint64_t* full_bar = bars;                   // used in the leader CTA
+  uint64_t* empty_bar = bars + STAGES;         // per CTA
+  uint64_t* tmem_full = bars + 2 * STAGES;     // per CTA
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // used in the leader CTA
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + Cfg::NUM_BARS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_pair(tmem_base_smem, Cfg::TMEM_COLS);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm.a);
+    tma_prefetch_desc(&tm.w[0][0]);
+  }
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  const int cnt0 = min(max(p.counts[0], 0), p.rows_cap);
+  const int cnt1 = p.single_expert ? 0 : min(max(p.counts[1], 0), p.rows_cap - cnt0);
+  const int mp0 = (cnt0 + 2 * BM - 1) / (2 * BM);
+  const int mp1 = (cnt1 + 2 * BM - 1) / (2 * BM);
+  const bool swiglu = p.mode == VEX_EPI_SWIGLU;
+  const int n_span = swiglu ? BN / 2 : BN;
+  const int n_tiles = (p.N + n_span - 1) / n_span;
+  const int total_tiles = (mp0 + mp1) * n_tiles;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    // =============================== TMA producer (both CTAs) ===============================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const PairTile c = decode_pair_tile(tile, mp0, mp1, n_tiles);
+      const int row0 = (c.e ? cnt0 : 0) + (2 * c.m2 + static_cast<int>(rank)) * BM;
+      // this CTA's half of the 256 accumulator columns: leader = [0,128), peer = [128,256).
+      // SwiGLU: leader half = gate_proj rows, peer half = up_proj rows of the same 128 output columns.
+      const int nrow = swiglu ? c.n * n_span : c.n * BN + static_cast<int>(rank) * (BN / 2);
+      const CUtensorMap* wmap = &tm.w[c.e][swiglu ? rank : 0];
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
+        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+        tma_load_2d_pair(sa, &tm.a, full_leader, kb * BK, row0);
+        tma_load_2d_pair(sa + Cfg::A_BYTES, wmap, full_leader, kb * BK, nrow);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if ((p.lora_mask >> c.e) & 1) {
+        const int halves = swiglu ? 2 : 1;
+        for (int h = 0; h < halves; ++h) {
+          for (int ls = 0; ls < p.lora_steps; ++ls) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (swiglu) {
+              // N = 128 MMA into accumulator half h: each CTA supplies 64 rows of lora_B (half-box)
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES / 2));
+              tma_load_2d_pair(sa, &tm.t[h], full_leader, ls * BK, row0);
+              tma_load_2d_pair(sa + Cfg::A_BYTES, &tm.lb64[c.e][h], full_leader, ls * BK,
+                               c.n * n_span + static_cast<int>(rank) * 64);
+            } else {
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+              tma_load_2d_pair(sa, &tm.t[0], full_leader, ls * BK, row0);
+              tma_load_2d_pair(sa + Cfg::A_BYTES, &tm.lb[c.e][0], full_leader, ls * BK, nrow);
+            }
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // =============================== MMA issuer (leader CTA) ===============================
+    constexpr uint32_t idesc_full = umma_idesc_bf16(2 * BM, BN);
+    constexpr uint32_t idesc_half = umma_idesc_bf16(2 * BM, BN / 2);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const PairTile c = decode_pair_tile(tile, mp0, mp1, n_tiles);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+      uint32_t accumulate = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint64_t da = umma_desc_kmajor_sw128(sa);
+        const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          umma_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc_full, accumulate);
+          accumulate = 1;
+        }
+        umma_commit_pair(&empty_bar[stage], 3);  // frees the slot in both CTAs
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if ((p.lora_mask >> c.e) & 1) {
+        const int halves = swiglu ? 2 : 1;
+        for (int h = 0; h < halves; ++h) {
+          for (int ls = 0; ls < p.lora_steps; ++ls) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint64_t da = umma_desc_kmajor_sw128(sa);
+            const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::A_BYTES);
+            const uint32_t d_half = d_tmem + static_cast<uint32_t>(swiglu ? h * (BN / 2) : 0);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_ss_pair(d_half, da + 2 * k, db + 2 * k, swiglu ? idesc_half : idesc_full, 1u);
+            umma_commit_pair(&empty_bar[stage], 3);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+      umma_commit_pair(&tmem_full[acc], 3);  // accumulators of both CTAs complete -> both epilogues
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // =============================== epilogue (both CTAs, own 128 rows) ===============================
+    const int ew = warp - 4;
+    const uint32_t stage_base = smem_u32(epi_smem + ew * Cfg::EPI_WARP_BYTES);
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const PairTile c = decode_pair_tile(tile, mp0, mp1, n_tiles);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      epilogue_tile<BN>(p, c.e, 2 * c.m2 + static_cast<int>(rank), c.n, cnt0, cnt1,
+                        t_lane + static_cast<uint32_t>(acc * BN), stage_base, lane, ew, [&]() {
+                          tc_fence_before();
+                          __syncwarp();
+                          if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+                        });
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer's shared memory / TMEM stay alive until the leader's last MMA has been consumed
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -534,6 +785,36 @@ static int launch_gemm(const GemmTmaps& tm, const GemmDev& dev, cudaStream_t s) 
   return VEX_OK;
 }
 
+static int launch_gemm_pair(const GemmTmaps& tm, const GemmDev& dev, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    VEX_CUDA_TRY(cudaFuncSetAttribute(k3_grouped_gemm_pair, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      PairCfg::SMEM_BYTES));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(num_sms() & ~1);  // whole CTA pairs
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = PairCfg::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VEX_CUDA_TRY(cudaLaunchKernelEx(&cfg, k3_grouped_gemm_pair, tm, dev));
+  return VEX_OK;
+}
+
+// VEX_GEMM_PAIR=0 selects the single-CTA kernel for every shape (A/B switch; default: CTA pairs)
+static bool use_pair_kernel() {
+  const char* e = std::getenv("VEX_GEMM_PAIR");  // read per call so tests can flip it
+  return !(e && e[0] == '0');
+}
+
 }  // namespace vex
 
 extern "C" int vex_grouped_gemm(const vexGemmArgs* a, vexStream stream) {
@@ -580,6 +861,9 @@ extern "C" int vex_grouped_gemm(const vexGemmArgs* a, vexStream stream) {
         dev.lora_mask |= 1 << e;
         if ((rc = make_tmap_2d(&tm.lb[e][h], a->lora_b[e][h], a->N, a->lora_r, a->lora_r, half_rows)) != VEX_OK)
           return rc;
+        if (swiglu &&
+            (rc = make_tmap_2d(&tm.lb64[e][h], a->lora_b[e][h], a->N, a->lora_r, a->lora_r, 64)) != VEX_OK)
+          return rc;
       }
       if (any) {
         if (!a->lora_t[h]) return VEX_E_INVALID;
@@ -606,5 +890,6 @@ extern "C" int vex_grouped_gemm(const vexGemmArgs* a, vexStream stream) {
   dev.mode = a->mode;
   dev.single_expert = a->single_expert;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return small_n ? launch_gemm<64>(tm, dev, s) : launch_gemm<256>(tm, dev, s);
+  if (small_n) return launch_gemm<64>(tm, dev, s);
+  return use_pair_kernel() ? launch_gemm_pair(tm, dev, s) : launch_gemm<256>(tm, dev, s);
 }

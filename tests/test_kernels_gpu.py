@@ -128,6 +128,13 @@ def test_k6_residual_scatter_and_copy_padded():
 
 
 # ------------------------------------------------------------------------------------------ K3
+@pytest.fixture(params=["pair", "single"], autouse=False)
+def gemm_kernel(request, monkeypatch):
+    """Both tile kernels: the CTA-pair (cta_group::2) default and the single-CTA variant."""
+    monkeypatch.setenv("VEX_GEMM_PAIR", "1" if request.param == "pair" else "0")
+    return request.param
+
+
 def _gemm_problem(Tv, Tl, N, K, seed=0, cap_extra=5):
     g = torch.Generator().manual_seed(seed)
     cap = Tv + Tl + cap_extra
@@ -152,7 +159,7 @@ GEMM_SHAPES = [  # Tv, Tl, N, K
 
 
 @pytest.mark.parametrize("Tv,Tl,N,K", GEMM_SHAPES)
-def test_k3_plain_grouped(Tv, Tl, N, K):
+def test_k3_plain_grouped(Tv, Tl, N, K, gemm_kernel):
     ops = _ops()
     a, wv, wl, counts, cap = _gemm_problem(Tv, Tl, N, K, seed=N + K)
     out = torch.full((cap, N), 3.0, dtype=torch.bfloat16).cuda()
@@ -177,7 +184,7 @@ def test_k3_small_n_lora_a_shape():
     assert (out[333:] == 0).all()
 
 
-def test_k3_scatter_and_residual():
+def test_k3_scatter_and_residual(gemm_kernel):
     ops = _ops()
     Tv, Tl, N, K = 260, 140, 512, 320
     a, wv, wl, counts, cap = _gemm_problem(Tv, Tl, N, K, seed=9, cap_extra=40)
@@ -202,7 +209,7 @@ def test_k3_scatter_and_residual():
 
 
 @pytest.mark.parametrize("r", [64, 16])
-def test_k3_lora_k_extension(r):
+def test_k3_lora_k_extension(r, gemm_kernel):
     ops = _ops()
     Tv, Tl, N, K = 200, 150, 768, 256
     a, wv, wl, counts, cap = _gemm_problem(Tv, Tl, N, K, seed=21)
@@ -228,7 +235,7 @@ def test_k3_lora_k_extension(r):
 
 
 @pytest.mark.parametrize("lora", [False, True])
-def test_k3_swiglu(lora):
+def test_k3_swiglu(lora, gemm_kernel):
     ops = _ops()
     Tv, Tl, I, K, r = 300, 180, 640, 256, 64
     g = torch.Generator().manual_seed(33)
@@ -261,7 +268,7 @@ def test_k3_swiglu(lora):
     assert (out[T:] == 0).all()
 
 
-def test_k3_rope_epilogue_scatter_to_token_order():
+def test_k3_rope_epilogue_scatter_to_token_order(gemm_kernel):
     from mmmm_b200.inputs import make_ids
     ops = _ops()
     heads, Hd = 2, 256
