@@ -154,6 +154,13 @@ int vex_grouped_gemm(const vexGemmArgs* args, vexStream stream);
 int vex_attention(const void* qkv, const int32_t* cu_seqlens, int B, int max_len_cap, int heads,
                   const int32_t* out_row_map, void* out, float scale, vexStream stream);
 
+/* K4d -- decode-step attention (q_len == 1 against the KV cache).  Replaces attention_fn's generation branch
+ * (:129-141): q [B, heads*128] rows of stride ldq elements (already rotated), k / v [B, heads, L, 128] (the
+ * reference cache layout, current token included), mask uint8 [B, L] (attention mask over past + current),
+ * out [B, heads*128].  Query scaled in bf16, bf16 scores, fp32 softmax cast to bf16, like the eager reference. */
+int vex_attention_decode(const void* q, int64_t ldq, const void* k, const void* v, const uint8_t* mask, void* out,
+                         int B, int heads, int L, float scale, vexStream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,7 +9,8 @@ __all__ = ["CogVLMDecoderLayer", "VexConfig", "swap_decoder_layers", "build_plan
 
 def __getattr__(name):
     if name in ("CogVLMDecoderLayer", "VexConfig", "swap_decoder_layers", "RMSNorm", "VisionExpertAttention",
-                "VisionExpertMLP", "MLP", "RotaryEmbedding", "get_expert_mask"):
+                "VisionExpertMLP", "MLP", "RotaryEmbedding", "get_expert_mask", "VisualExpertDecoder",
+                "masked_rms_norm"):
         from . import modeling_cogvlm as m
         return getattr(m, name)
     if name == "build_plan":

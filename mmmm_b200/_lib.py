@@ -19,7 +19,7 @@ COUNT_VISION, COUNT_LANGUAGE, COUNT_VALID, COUNT_MAXLEN, NUM_COUNTS = 0, 1, 2, 3
 SYMBOLS = [
     "vex_abi_version", "vex_error_string", "vex_last_cuda_error", "vex_device_check", "vex_partition",
     "vex_rmsnorm_gather", "vex_silu_mul", "vex_residual_scatter", "vex_copy_padded_rows", "vex_grouped_gemm",
-    "vex_attention",
+    "vex_attention", "vex_attention_decode",
 ]
 
 
@@ -71,6 +71,7 @@ def lib() -> C.CDLL:
         L.vex_copy_padded_rows.argtypes = [p, p, p, i32, i32, p]
         L.vex_grouped_gemm.argtypes = [C.POINTER(GemmArgs), p]
         L.vex_attention.argtypes = [p, p, i32, i32, i32, p, p, f32, p]
+        L.vex_attention_decode.argtypes = [p, i64, p, p, p, p, i32, i32, i32, f32, p]
         for name in SYMBOLS:
             fn = getattr(L, name)
             if name not in ("vex_error_string",):

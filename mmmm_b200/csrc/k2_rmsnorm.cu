@@ -4,6 +4,8 @@
 // rounding to bf16; fused with the hidden_states[padding_mask] gather (:307, :326).
 // One warp per row, the whole row stays in registers (H/256 x 16-byte loads in flight per lane),
 // no shared memory, no block barrier.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace vex {
@@ -11,65 +13,76 @@ namespace vex {
 constexpr int K2_WARPS = 8;
 
 template <int NCHUNK>  // H = NCHUNK * 256
-__global__ void __launch_bounds__(K2_WARPS * 32)
+__global__ void __launch_bounds__(K2_WARPS * 32, 3)
     k2_rmsnorm(const __nv_bfloat16* __restrict__ x, const void* __restrict__ weight, int weight_is_fp32, float eps,
                const int32_t* __restrict__ row_src, const int32_t* __restrict__ row_dst,
                const int32_t* __restrict__ n_rows_ptr, __nv_bfloat16* __restrict__ y, int rows_cap) {
   constexpr int H = NCHUNK * 256;
+  // WPR warps share one row so that a lane holds at most 8 x 16 bytes of it (32 registers): 24 warps per SM
+  // stay resident with every load of their row slice in flight (the 1-warp-per-row version needed 230
+  // registers and ran 8 warps per SM at 68 % of the HBM roofline)
+  constexpr int WPR = NCHUNK > 8 ? 2 : 1;   // warps per row
+  constexpr int CPL = NCHUNK / WPR;         // 16-byte chunks per lane
+  constexpr int ROWS = K2_WARPS / WPR;      // rows per CTA iteration
+  static_assert(NCHUNK % WPR == 0, "row slices must be whole chunks");
+  // weight vector staged once per CTA in shared memory (fp32): short-latency LDS in the per-row epilogue
+  __shared__ __align__(16) float w_s[H];
+  __shared__ float part[K2_WARPS];
+  for (int i = threadIdx.x; i < H; i += K2_WARPS * 32)
+    w_s[i] = weight_is_fp32 ? static_cast<const float*>(weight)[i]
+                            : __bfloat162float(static_cast<const __nv_bfloat16*>(weight)[i]);
+  __syncthreads();
   const int lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const int slot = warp / WPR, half = warp % WPR;
   const int n_rows = min(*n_rows_ptr, rows_cap);
-  const int warps_total = gridDim.x * K2_WARPS;
-  for (int r = blockIdx.x * K2_WARPS + (threadIdx.x >> 5); r < n_rows; r += warps_total) {
-    const int src = row_src ? row_src[r] : r;
-    const uint4* xp = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(src) * H);
-    uint4 v[NCHUNK];
-#pragma unroll
-    for (int i = 0; i < NCHUNK; ++i) v[i] = ld_stream(xp + i * 32 + lane);
+  // CTA-uniform trip count (the pair barrier below is a CTA barrier when WPR == 2)
+  for (int r0 = blockIdx.x * ROWS; r0 < n_rows; r0 += gridDim.x * ROWS) {
+    const int r = r0 + slot;
+    const bool live = r < n_rows;
+    uint4 v[CPL];
     float ss = 0.f;
+    if (live) {
+      const int src = row_src ? row_src[r] : r;
+      const uint4* xp = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(src) * H) + half * CPL * 32;
 #pragma unroll
-    for (int i = 0; i < NCHUNK; ++i) {
-      const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      for (int i = 0; i < CPL; ++i) v[i] = ld_stream(xp + i * 32 + lane);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float a = bf16_lo(u[j]), b = bf16_hi(u[j]);
-        ss = fmaf(a, a, ss);
-        ss = fmaf(b, b, ss);
+      for (int i = 0; i < CPL; ++i) {
+        const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = bf16_lo(u[j]), b = bf16_hi(u[j]);
+          ss = fmaf(a, a, ss);
+          ss = fmaf(b, b, ss);
+        }
       }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float inv = rsqrtf(ss * (1.0f / H) + eps);
-    const int dst = row_dst ? row_dst[r] : r;
-    uint4* yp = reinterpret_cast<uint4*>(y + static_cast<int64_t>(dst) * H);
+    if constexpr (WPR == 2) {
+      if (lane == 0) part[warp] = ss;
+      __syncthreads();
+      ss = part[slot * 2] + part[slot * 2 + 1];
+      __syncthreads();  // part[] is rewritten in the next iteration
+    }
+    if (live) {
+      const float inv = rsqrtf(ss * (1.0f / H) + eps);
+      const int dst = row_dst ? row_dst[r] : r;
+      uint4* yp = reinterpret_cast<uint4*>(y + static_cast<int64_t>(dst) * H) + half * CPL * 32;
 #pragma unroll
-    for (int i = 0; i < NCHUNK; ++i) {
-      const int col = (i * 32 + lane) * 8;
-      float w[8];
-      if (weight_is_fp32) {
-        const float4* wp = reinterpret_cast<const float4*>(static_cast<const float*>(weight) + col);
-        const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
-        w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w;
-        w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
-      } else {
-        const uint4 wb = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(weight) + col));
-        const uint32_t u[4] = {wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          w[2 * j] = bf16_lo(u[j]);
-          w[2 * j + 1] = bf16_hi(u[j]);
-        }
-      }
-      const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-      uint4 o;
-      uint32_t* op = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int i = 0; i < CPL; ++i) {
+        const int col = ((half * CPL + i) * 32 + lane) * 8;
+        const float4 w0 = *reinterpret_cast<const float4*>(&w_s[col]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&w_s[col + 4]);
+        uint4 o;
         // reference order: (x * rsqrt(var + eps)) in fp32, then weight * that, then one cast
-        const float a = w[2 * j] * (bf16_lo(u[j]) * inv);
-        const float b = w[2 * j + 1] * (bf16_hi(u[j]) * inv);
-        op[j] = pack_bf16(a, b);
+        o.x = pack_bf16(w0.x * (bf16_lo(v[i].x) * inv), w0.y * (bf16_hi(v[i].x) * inv));
+        o.y = pack_bf16(w0.z * (bf16_lo(v[i].y) * inv), w0.w * (bf16_hi(v[i].y) * inv));
+        o.z = pack_bf16(w1.x * (bf16_lo(v[i].z) * inv), w1.y * (bf16_hi(v[i].z) * inv));
+        o.w = pack_bf16(w1.z * (bf16_lo(v[i].w) * inv), w1.w * (bf16_hi(v[i].w) * inv));
+        st_stream(yp + i * 32 + lane, o);
       }
-      st_stream(yp + i * 32 + lane, o);
     }
   }
 }
@@ -82,7 +95,8 @@ extern "C" int vex_rmsnorm_gather(const void* x, const void* weight, int weight_
   if (!x || !weight || !n_rows || !y || rows_cap <= 0) return VEX_E_INVALID;
   if (H % 256 != 0 || H <= 0 || H > 4096) return VEX_E_UNSUPPORTED;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int grid = vex::ceil_div(rows_cap, vex::K2_WARPS);
+  // persistent-ish grid: every CTA stages the weight vector once, then strides over rows
+  const int grid = std::min(vex::ceil_div(rows_cap, vex::K2_WARPS / 2), 148 * 3);
   auto xp = static_cast<const __nv_bfloat16*>(x);
   auto yp = static_cast<__nv_bfloat16*>(y);
 #define VEX_K2_CASE(NC)                                                                                        \

@@ -342,6 +342,87 @@ def visual_expert_layer_forward(layer: "CogVLMDecoderLayer", hidden_states: torc
     return out, present
 
 
+_decode_consts: dict = {}
+
+
+def _decode_constants(batch: int, device):
+    """Device constants of a decode step: counts = [B, 0, B, 1] (all rows go through ONE weight set) and the
+    identity row map.  Built once per (batch, device): no per-step host->device copy."""
+    key = (batch, device)
+    if key not in _decode_consts:
+        _decode_consts[key] = (torch.tensor([batch, 0, batch, 1], dtype=torch.int32, device=device),
+                               torch.arange(batch, dtype=torch.int32, device=device))
+    return _decode_consts[key]
+
+
+def _lora_t_single(x: torch.Tensor, spec: LinearSpec, counts: torch.Tensor):
+    if spec.lora_A is None:
+        return None, 0, None
+    if spec.r % 8 or spec.r > 64:
+        raise NotImplementedError(f"LoRA rank {spec.r}: the fused K-extension handles multiples of 8 up to 64")
+    t = torch.empty(x.shape[0], spec.r, dtype=torch.bfloat16, device=x.device)
+    ops.grouped_gemm(x, _bf16(spec.lora_A), None, t, counts, None, float(spec.scaling))
+    return t, spec.r, _bf16(spec.lora_B)
+
+
+def visual_expert_layer_decode(layer: "CogVLMDecoderLayer", hidden_states: torch.Tensor, position_ids: torch.Tensor,
+                               padding_mask: torch.Tensor, past_key_value, use_cache: bool = True):
+    """One generation step (q_len == 1 with a KV cache): the reference's L == 1 rules -- every token goes to the
+    LANGUAGE expert regardless of padding (get_expert_mask :67), plain RMSNorm on every row (:308-309, :327-328),
+    cache concat on dim 2 (:258-260) and the generation branch of attention_fn (:129-141)."""
+    attn, mlp = layer.self_attn, layer.mlp
+    B, L, H = hidden_states.shape
+    heads = attn.num_heads
+    I = mlp.language_mlp.intermediate_size
+    dev = hidden_states.device
+    past_k, past_v = past_key_value
+    if past_k.shape[0] != B or past_k.shape[1] != heads or past_k.shape[3] != HEAD_DIM:
+        raise ValueError(f"past_key_value must be [B, {heads}, L_past, {HEAD_DIM}]")
+    Lkv = past_k.shape[2] + 1
+    if padding_mask.shape != (B, Lkv):
+        raise ValueError(f"padding_mask must cover past + current positions: expected {(B, Lkv)}")
+    counts, ident = _decode_constants(B, dev)
+    n_rows = counts[2:3]
+    new = lambda *shape: torch.empty(*shape, dtype=torch.bfloat16, device=dev)
+    hf = hidden_states.view(B, H)
+    ln1, ln2 = resolve_norm(layer.input_layernorm), resolve_norm(layer.post_attention_layernorm)
+    qkv_s = resolve_linear(attn.language_expert_query_key_value)
+    dense_s = resolve_linear(attn.language_expert_dense)
+    gate_s, up_s = resolve_linear(mlp.language_mlp.gate_proj), resolve_linear(mlp.language_mlp.up_proj)
+    down_s = resolve_linear(mlp.language_mlp.down_proj)
+
+    def gemm(a, w, out, mode, spec_pair, residual=None, rope=(), rope_cols=0):
+        t, r, lb = [None, None], 0, [None] * 4
+        for h, sp in enumerate(spec_pair):
+            th, rh, bh = _lora_t_single(a, sp, counts)
+            if th is not None:
+                t[h], r, lb[h] = th, rh, bh
+        if len(spec_pair) == 2 and (t[0] is None) != (t[1] is None):
+            raise NotImplementedError("gate_proj and up_proj adapters must come in pairs")
+        ops.grouped_gemm_fused(a, w, out, counts, mode, None, residual, t, lb, r, list(rope), rope_cols, True, 1.0)
+
+    xn = new(B, H)
+    ops.rmsnorm_gather(hf, ln1.weight.detach(), ln1.variance_epsilon, None, n_rows, xn)
+    max_pos = max(Lkv, attn.max_position_embeddings)
+    cos, sin = attn.rotary_emb.tables(max_pos, dev, torch.bfloat16)
+    qkv = new(B, 3 * H)
+    gemm(xn, [_bf16(qkv_s.weight)], qkv, ops.EPI_ROPE, [qkv_s],
+         rope=(cos, sin, position_ids.reshape(-1), ident), rope_cols=2 * H)
+    k_new = qkv[:, H:2 * H].reshape(B, heads, 1, HEAD_DIM)
+    v_new = qkv[:, 2 * H:].reshape(B, heads, 1, HEAD_DIM)
+    k = torch.cat([past_k, k_new], dim=2)   # :259-260 (the tuple-cache API reallocates every step)
+    v = torch.cat([past_v, v_new], dim=2)
+    ctx = new(B, H)
+    ops.attention_decode(qkv[:, :H], k, v, padding_mask, ctx, HEAD_DIM ** -0.5)
+    h1 = new(B, H)
+    gemm(ctx, [_bf16(dense_s.weight)], h1, ops.EPI_RESIDUAL, [dense_s], residual=hf)
+    ops.rmsnorm_gather(h1, ln2.weight.detach(), ln2.variance_epsilon, None, n_rows, xn)
+    act = new(B, I)
+    gemm(xn, [_bf16(gate_s.weight), _bf16(up_s.weight)], act, ops.EPI_SWIGLU, [gate_s, up_s])
+    gemm(act, [_bf16(down_s.weight)], h1, ops.EPI_RESIDUAL, [down_s])  # in place: h1 += down(act)
+    return h1.view(B, 1, H), ((k, v) if use_cache else None)
+
+
 class CogVLMDecoderLayer(nn.Module):
     """Drop-in for the reference ``CogVLMDecoderLayer`` (:286-340)."""
 
@@ -369,9 +450,10 @@ class CogVLMDecoderLayer(nn.Module):
             padding_mask = attention_mask  # BASELINE wording; the reference converts one level up (:539)
         if token_type_ids is None or position_ids is None or padding_mask is None:
             raise TypeError("token_type_ids, position_ids and padding_mask (or attention_mask) are required")
-        if past_key_value is not None:
-            raise NotImplementedError("decode with past_key_value (q_len == 1 branch, :129-141) is not implemented "
-                                      "by the B200 path yet (SURVEY 8(f)-2); refusing to fall back silently")
+        decode = past_key_value is not None
+        if decode and hidden_states.dim() == 3 and hidden_states.shape[1] != 1:
+            raise NotImplementedError("past_key_value with q_len > 1 (chunked prefill) is not implemented; the "
+                                      "reference's generation branch asserts q_len == 1 as well (:131)")
         if not hidden_states.is_cuda:
             raise ValueError("hidden_states must be a CUDA tensor: the visual-expert layer has no CPU path")
         if hidden_states.dtype != torch.bfloat16:
@@ -380,6 +462,8 @@ class CogVLMDecoderLayer(nn.Module):
             raise ValueError(f"hidden_states must be [B, L, {self.hidden_size}]")
         if hidden_states.shape[:2] != token_type_ids.shape or position_ids.shape != token_type_ids.shape:
             raise ValueError("token_type_ids / position_ids must be [B, L] like hidden_states")
+        if not decode and hidden_states.shape[1] == 1:
+            raise NotImplementedError("q_len == 1 without a KV cache is not part of the prefill path")
         if torch.is_grad_enabled() and (hidden_states.requires_grad or any(
                 p.requires_grad for p in self.parameters())):
             raise NotImplementedError("the fused layer is forward-only in this round (training variant: "
@@ -389,9 +473,14 @@ class CogVLMDecoderLayer(nn.Module):
         hidden_states = hidden_states.contiguous()
         if position_ids.dtype != torch.int64:
             position_ids = position_ids.long()
-        plan = GLOBAL_PLAN_CACHE.get(token_type_ids, padding_mask)
-        out, present = visual_expert_layer_forward(self, hidden_states, plan, position_ids.contiguous(),
-                                                   use_cache=bool(use_cache), fuse_epilogue=self.fuse_epilogue)
+        if decode:
+            out, present = visual_expert_layer_decode(self, hidden_states, position_ids.contiguous(),
+                                                      padding_mask.bool().contiguous(), past_key_value,
+                                                      use_cache=bool(use_cache))
+        else:
+            plan = GLOBAL_PLAN_CACHE.get(token_type_ids, padding_mask)
+            out, present = visual_expert_layer_forward(self, hidden_states, plan, position_ids.contiguous(),
+                                                       use_cache=bool(use_cache), fuse_epilogue=self.fuse_epilogue)
         outputs = (out,)
         if output_attentions:
             outputs += (None,)
@@ -416,3 +505,56 @@ def swap_decoder_layers(model: nn.Module) -> nn.Module:
         new.self_attn.rotary_emb.inv_freq = old.self_attn.rotary_emb.inv_freq
         layers[i] = new
     return model
+
+
+class VisualExpertDecoder(nn.Module):
+    """The decoder part of the reference ``CogVLMModel``: ``layers`` + final ``norm`` driven like
+    ``CogVLMModel.llm_forward`` (modeling_cogvlm.py:477-586) from ``inputs_embeds`` (embedding lookup and the
+    vision encoder stay with the caller -- they are outside the hot path).  State-dict keys ``layers.N.*`` and
+    ``norm.weight`` equal those of ``CogVLMModel``, so its checkpoint loads with ``strict=False``.
+
+    The routing plan (K1) is computed once and shared by all layers; with ``graph=True`` the whole prefill is
+    captured into one CUDA graph per input shape (``GraphedPrefill``)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.layers = nn.ModuleList([CogVLMDecoderLayer(config) for _ in range(config.num_hidden_layers)])
+        self.norm = RMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+        self._graphs = {}
+
+    def llm_forward(self, inputs_embeds: torch.Tensor, token_type_ids: torch.Tensor,
+                    attention_mask: Optional[torch.Tensor] = None, position_ids: Optional[torch.Tensor] = None,
+                    past_key_values=None, use_cache: bool = False, graph: bool = False):
+        """Returns ``(last_hidden_state, next_cache)`` -- the non-dict return of the reference (:579-580)."""
+        B, L, _ = inputs_embeds.shape
+        dev = inputs_embeds.device
+        past_len = 0 if past_key_values is None else past_key_values[0][0].shape[2]
+        if position_ids is None:  # :523-528
+            position_ids = torch.arange(past_len, L + past_len, dtype=torch.long, device=dev).unsqueeze(0).expand(B, L)
+        position_ids = position_ids.reshape(-1, L).long().contiguous()
+        if attention_mask is None:  # :535-538
+            attention_mask = torch.ones(B, L + past_len, dtype=torch.bool, device=dev)
+        padding_mask = attention_mask.bool()  # :539
+        if graph and past_key_values is None and not use_cache:
+            from .graph import GraphedPrefill
+            key = (B, L, inputs_embeds.dtype, dev)
+            if key not in self._graphs:
+                self._graphs[key] = GraphedPrefill(self.layers, inputs_embeds, token_type_ids, position_ids,
+                                                   padding_mask, final_norm=self.norm)
+            return self._graphs[key](inputs_embeds, token_type_ids, position_ids, padding_mask), None
+        h = inputs_embeds
+        cache = () if use_cache else None
+        for i, layer in enumerate(self.layers):  # :547-569
+            out = layer(h, token_type_ids=token_type_ids, position_ids=position_ids, padding_mask=padding_mask,
+                        past_key_value=None if past_key_values is None else past_key_values[i], use_cache=use_cache)
+            h = out[0]
+            if use_cache:
+                cache += (out[1],)
+        if L > 1:  # :570-573
+            h = masked_rms_norm(self.norm, h, token_type_ids, padding_mask)
+        else:
+            h = self.norm(h)
+        return h, cache
+
+    forward = llm_forward

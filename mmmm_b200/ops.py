@@ -249,6 +249,23 @@ def attention(qkv: torch.Tensor, cu_seqlens: torch.Tensor, batch: int, max_len_c
     _lib.check(rc, "vex_attention")
 
 
-for _op in (partition, rmsnorm_gather, silu_mul, residual_scatter, copy_padded_rows, grouped_gemm, grouped_gemm_fused,
+@torch.library.custom_op("vex::attention_decode", mutates_args=("out",))
+def attention_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask: torch.Tensor, out: torch.Tensor,
+                     scale: float) -> None:
+    """K4d (vex_attention_decode): generation branch of attention_fn (modeling_cogvlm.py:129-141).
+    q [B, heads*128] (a row-strided view is fine), k / v [B, heads, L, 128], mask bool [B, L], out [B, heads*128]."""
+    _dev(k, "k", _BF16), _dev(v, "v", _BF16), _dev(out, "out", _BF16), _dev(mask, "mask", torch.bool)
+    if not q.is_cuda or q.dtype != _BF16 or q.stride(-1) != 1:
+        raise ValueError("q must be a CUDA bf16 tensor with unit inner stride")
+    B, heads, L, d = k.shape
+    if d != 128 or v.shape != k.shape or q.shape != (B, heads * 128) or mask.shape != (B, L):
+        raise ValueError("shape mismatch (head_dim 128 only)")
+    with instrument.region("attention_decode"):
+      rc = _lib.lib().vex_attention_decode(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), mask.data_ptr(),
+                                           out.data_ptr(), B, heads, L, float(scale), _stream())
+    _lib.check(rc, "vex_attention_decode")
+
+
+for _op in (attention_decode, partition, rmsnorm_gather, silu_mul, residual_scatter, copy_padded_rows, grouped_gemm, grouped_gemm_fused,
             attention):
     _op.register_fake(lambda *a, **k: None)

@@ -168,6 +168,24 @@ def attention(q, k, v, padding_mask):
     return out
 
 
+def attention_decode(q, k, v, padding_mask):
+    """Generation branch of ``attention_fn`` (modeling_cogvlm.py:129-141): q_len == 1 against the cached keys.
+    q [B, heads, 1, d]; k, v [B, heads, Lkv, d]; padding_mask [B, Lkv].  The query is scaled IN its dtype
+    (``query_layer *= d ** -0.5``), masked keys/values are zeroed, scores are masked to -inf, softmax runs in fp32
+    and is cast back to the score dtype before the weighted sum."""
+    assert q.shape[2] == 1
+    qs = q[:, :, 0] * (q.shape[-1] ** -0.5)                                   # [B, H, d]       :132
+    kk = k.permute(0, 2, 1, 3).clone()                                         # [B, Lkv, H, d]
+    vv = v.permute(0, 2, 1, 3).clone()
+    kk[~padding_mask] = 0                                                      # :134-135
+    vv[~padding_mask] = 0
+    scores = torch.einsum("nhd,nlhd->nlh", qs, kk)                             # :136
+    scores[~padding_mask] = -torch.inf                                         # :137
+    scores = scores.softmax(dim=1, dtype=torch.float32).to(dtype=scores.dtype)  # :138
+    out = torch.einsum("nlhd,nlh->nhd", vv, scores)[:, None]                   # [B, 1, H, d]   :141
+    return out.permute(0, 2, 1, 3)                                             # [B, H, 1, d]   :142
+
+
 # --------------------------------------------------------------------------------------------- a3/a6/a7/a8/a9
 def decoder_layer(
     weights: Dict[str, torch.Tensor],
@@ -181,8 +199,10 @@ def decoder_layer(
     lora: Optional[Dict[str, LoRA]] = None,
     use_cache: bool = False,
     cos_sin: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+    past_key_value: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
 ):
-    """``CogVLMDecoderLayer.forward`` (modeling_cogvlm.py:295-340) for q_len > 1 and no past KV.
+    """``CogVLMDecoderLayer.forward`` (modeling_cogvlm.py:295-340): prefill (q_len > 1, no past KV) and the
+    decode step (q_len == 1 with ``past_key_value``; ``padding_mask`` then covers past + current positions).
 
     ``weights`` uses the reference state-dict keys; ``lora`` maps a Linear's
     module path (e.g. ``"self_attn.vision_expert_query_key_value"``) to its adapter.  Rows with
@@ -192,7 +212,7 @@ def decoder_layer(
     """
     lora = lora or {}
     B, L, Hd = hidden_states.shape
-    assert L > 1, "decode (q_len == 1) is out of the oracle's scope"
+    assert (L > 1) == (past_key_value is None), "supported: prefill without cache, or q_len == 1 with cache"
     d = Hd // num_heads
     vmask, lmask = expert_masks(token_type_ids, padding_mask)
     masks = (vmask, lmask)
@@ -202,7 +222,10 @@ def decoder_layer(
 
     # --- attention block (:305-321) ---
     residual = hidden_states
-    h = masked_rms_norm(hidden_states, padding_mask, weights["input_layernorm.weight"], rms_norm_eps)
+    if L > 1:
+        h = masked_rms_norm(hidden_states, padding_mask, weights["input_layernorm.weight"], rms_norm_eps)
+    else:                                                                     # :308-309
+        h = rms_norm(hidden_states, weights["input_layernorm.weight"], rms_norm_eps)
     mixed = torch.zeros(B, L, 3 * Hd, dtype=h.dtype, device=h.device)        # :243
     for expert, m in zip(EXPERTS, masks):                                     # :244-245
         mixed[m] = lin(h[m], f"self_attn.{expert}_expert_query_key_value")
@@ -216,8 +239,14 @@ def decoder_layer(
         cos, sin = cos_sin
     cos, sin = cos.to(v.dtype), sin.to(v.dtype)                               # :177-180
     q, k = apply_rotary(q, k, cos, sin, position_ids)                         # :256
+    if past_key_value is not None:                                            # :258-260
+        k = torch.cat([past_key_value[0], k], dim=2)
+        v = torch.cat([past_key_value[1], v], dim=2)
     present = (k, v) if use_cache else None                                   # :262
-    ctx = attention(q, k, v, padding_mask)                                    # :264
+    if L > 1:
+        ctx = attention(q, k, v, padding_mask)                                # :264, prefill branch
+    else:
+        ctx = attention_decode(q, k, v, padding_mask)                         # :264, generation branch
     ctx = ctx.transpose(1, 2).contiguous().reshape(B, L, Hd)                  # :275
     attn_out = torch.zeros(B, L, Hd, dtype=h.dtype, device=h.device)          # :277 (empty in the reference)
     for expert, m in zip(EXPERTS, masks):                                     # :278-279
@@ -226,7 +255,10 @@ def decoder_layer(
 
     # --- MLP block (:324-330) ---
     residual = h
-    hn = masked_rms_norm(h, padding_mask, weights["post_attention_layernorm.weight"], rms_norm_eps)
+    if L > 1:
+        hn = masked_rms_norm(h, padding_mask, weights["post_attention_layernorm.weight"], rms_norm_eps)
+    else:                                                                     # :327-328
+        hn = rms_norm(h, weights["post_attention_layernorm.weight"], rms_norm_eps)
     mlp_out = torch.zeros_like(hn)                                            # :95
     for expert, m in zip(EXPERTS, masks):                                     # :96-97, MLP.forward :54-56
         x = hn[m]

@@ -4,10 +4,11 @@ The reference file ``/root/reference/mmmm/models/cogvlm/modeling_cogvlm.py`` can
 directly in this image: it pulls ``luolib`` (-> monai), ``mmmm.utils`` (-> cytoolz),
 ``mmmm.data.utils`` (-> monai, nibabel) and, inside ``attention_fn`` (modeling_cogvlm.py:113),
 ``xformers``.  None of these are installed and there is no network.  This loader installs tiny
-``sys.modules`` stubs for exactly the names the file imports, executes the
-reference source *from where it lies* (nothing is copied into this repo) and substitutes
-``attention_fn`` -- whose arithmetic lives in the absent xformers 0.0.27 -- with an equivalent
-block-diagonal-causal softmax attention written against xformers' documented semantics.
+``sys.modules`` stubs for exactly the names the file imports and executes the
+reference source *from where it lies* (nothing is copied into this repo, nothing is patched).  The two
+xformers 0.0.27 entry points ``attention_fn`` calls (``memory_efficient_attention`` and
+``BlockDiagonalCausalMask.from_tensor_lists_qkv``) are stand-ins written against xformers' documented
+semantics; the reference's own ``attention_fn`` -- including its generation branch -- runs unmodified.
 
 Only ``tests/`` and ``oracle/make_golden.py`` may import this module.  It only works where
 ``/root/reference`` exists (the build container); the GPU box uses the committed fixtures under
@@ -38,36 +39,43 @@ def _stub(name: str, **attrs):
     return m
 
 
-def block_diag_causal_attention(q, k, v, padding_mask, dropout_p: float = 0.0):
-    """Stand-in for ``attention_fn`` (modeling_cogvlm.py:106-142), prefill branch.
+class BlockDiagonalCausalMask:
+    """Stand-in for ``xformers.ops.fmha.attn_bias.BlockDiagonalCausalMask`` (xformers 0.0.27, absent here):
+    remembers the per-sample lengths; ``from_tensor_lists_qkv`` concatenates the per-sample [1, n_i, H, D]
+    tensors along dim 1, as documented."""
 
-    xformers ``memory_efficient_attention(q, k, v, BlockDiagonalCausalMask)`` semantics: per sample,
-    the tokens with ``padding_mask == True`` are compacted (order preserved); token i attends to
-    compacted tokens j <= i of the same sample; scale = head_dim ** -0.5; softmax in fp32; output in
-    the input dtype.  Rows with ``padding_mask == False`` are zero (modeling_cogvlm.py:119,126).
-    Inputs/outputs are [B, heads, L, head_dim] like the reference function.
-    """
-    assert dropout_p == 0.0
-    B, H, L, D = q.shape
-    if padding_mask.shape[1] != L:
-        raise NotImplementedError("decode branch (q_len == 1 with cache) is not part of the oracle")
-    out = torch.zeros_like(q)
-    scale = D ** -0.5
-    for b in range(B):
-        idx = padding_mask[b].nonzero(as_tuple=True)[0]
-        n = idx.numel()
+    def __init__(self, seqlens):
+        self.seqlens = list(seqlens)
+
+    @classmethod
+    def from_tensor_lists_qkv(cls, q_list, k_list, v_list):
+        bias = cls([q.shape[1] for q in q_list])
+        return bias, torch.cat(q_list, dim=1), torch.cat(k_list, dim=1), torch.cat(v_list, dim=1)
+
+
+def memory_efficient_attention(q, k, v, attn_bias=None, p: float = 0.0):
+    """Stand-in for ``xformers.ops.memory_efficient_attention`` under a ``BlockDiagonalCausalMask``:
+    q, k, v are [1, T, H, D] (all samples packed); inside block i token a attends to tokens b <= a of the same
+    block; scale = D ** -0.5; softmax in fp32; probabilities rounded to the value dtype before P @ V (what the
+    flash kernels do); output in the input dtype."""
+    assert p == 0.0 and isinstance(attn_bias, BlockDiagonalCausalMask)
+    out = torch.empty_like(q)
+    scale = q.shape[-1] ** -0.5
+    start = 0
+    for n in attn_bias.seqlens:
         if n == 0:
             continue
-        qb = q[b, :, idx].float()
-        kb = k[b, :, idx].float()
-        vb = v[b, :, idx]
+        sl = slice(start, start + n)
+        qb = q[0, sl].permute(1, 0, 2).float()   # [H, n, D]
+        kb = k[0, sl].permute(1, 0, 2).float()
+        vb = v[0, sl].permute(1, 0, 2)
         s = torch.matmul(qb, kb.transpose(-1, -2)) * scale
         causal = torch.ones(n, n, dtype=torch.bool, device=q.device).tril()
         s = s.masked_fill(~causal, float("-inf"))
-        p = torch.softmax(s, dim=-1)
-        # FA-style kernels round P to the value dtype before the PV product
-        ob = torch.matmul(p.to(vb.dtype).float(), vb.float())
-        out[b, :, idx] = ob.to(q.dtype)
+        pr = torch.softmax(s, dim=-1)
+        ob = torch.matmul(pr.to(vb.dtype).float(), vb.float())
+        out[0, sl] = ob.permute(1, 0, 2).to(q.dtype)
+        start += n
     return out
 
 
@@ -104,6 +112,11 @@ def load_reference():
     _stub("mmmm.data.defs", CE_IGNORE_INDEX=-100)
     _stub("mmmm.data.utils", LANGUAGE_TOKEN_TYPE=0, VISION_TOKEN_TYPE=1)  # mmmm/data/utils.py:192-193
     _stub("mmmm.models.cogvlm.visual", EVA2CLIPModel=nn.Identity)
+    # xformers is absent: attention_fn (modeling_cogvlm.py:106-142) runs UNMODIFIED against these two stand-ins
+    _stub("xformers")
+    _stub("xformers.ops", memory_efficient_attention=memory_efficient_attention)
+    _stub("xformers.ops.fmha")
+    _stub("xformers.ops.fmha.attn_bias", BlockDiagonalCausalMask=BlockDiagonalCausalMask)
 
     def _load(name, path):
         spec = importlib.util.spec_from_file_location(name, path)
@@ -114,7 +127,6 @@ def load_reference():
 
     _load("mmmm.models.cogvlm.configuration_cogvlm", ref + "/models/cogvlm/configuration_cogvlm.py")
     M = _load("mmmm.models.cogvlm.modeling_cogvlm", ref + "/models/cogvlm/modeling_cogvlm.py")
-    M.attention_fn = block_diag_causal_attention  # xformers is absent (see module docstring)
     _LOADED = M
     return M
 

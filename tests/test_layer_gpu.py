@@ -238,3 +238,68 @@ def test_graphed_prefill_and_masked_final_norm():
     pm = a.padding_mask.cpu()
     mx, fro = _errs(eager(a).cpu()[pm], ref[pm])
     assert mx <= 2 * MAX_REL and fro <= 2 * FRO_REL, (mx, fro)
+
+
+@pytest.mark.parametrize("lora", [None, 32])
+def test_decode_steps_vs_oracle(lora):
+    """Prefill with use_cache, then three generation steps (q_len == 1, growing KV cache and attention mask)
+    against the oracle's restatement of the generation branch (bit-exact to the reference, tests/test_oracle.py)."""
+    from mmmm_b200.inputs import make_inputs
+    H, I, heads = 512, 768, 4
+    w = O.random_weights(H, I, heads, seed=11, dtype=torch.bfloat16)
+    ad = O.random_lora(H, I, r=lora, seed=12, dtype=torch.bfloat16, b_std=0.1) if lora else None
+    layer = _make_layer(w, dict(hidden_size=H, intermediate_size=I, num_attention_heads=heads), lora=ad)
+    inp = make_inputs(3, 150, 40, H, ragged=True, seed=13)
+    tt, pos, pm = inp.token_type_ids, inp.position_ids, inp.padding_mask
+    out, kv = _run(layer, inp.hidden_states, tt, pos, pm, use_cache=True)
+    ref_out, ref_kv = O.decoder_layer(w, inp.hidden_states, tt, pos, pm, num_heads=heads, lora=ad, use_cache=True)
+    g = torch.Generator().manual_seed(14)
+    mask = pm.clone()
+    next_pos = pos.max(dim=1, keepdim=True).values + 1
+    for step in range(3):
+        x = torch.randn(3, 1, H, generator=g).bfloat16()
+        mask = torch.cat([mask, torch.ones(3, 1, dtype=torch.bool)], dim=1)
+        tt1 = torch.zeros(3, 1, dtype=torch.long)
+        p1 = next_pos + step
+        with torch.no_grad():
+            out, kv = layer(x.cuda(), token_type_ids=tt1.cuda(), position_ids=p1.cuda(), padding_mask=mask.cuda(),
+                            past_key_value=kv, use_cache=True)
+        ref_out, ref_kv = O.decoder_layer(w, x, tt1, p1, mask, num_heads=heads, lora=ad, use_cache=True,
+                                          past_key_value=ref_kv)
+        assert out.shape == (3, 1, H) and kv[0].shape == ref_kv[0].shape
+        mx, fro = _errs(out.cpu(), ref_out)
+        assert mx <= MAX_REL and fro <= FRO_REL, (step, mx, fro)
+        mh = mask[:, None, :].expand(kv[0].shape[:3])
+        for got, want in zip(kv, ref_kv):
+            mx, fro = _errs(got.cpu()[mh], want[mh])
+            assert mx <= MAX_REL and fro <= FRO_REL, (step, mx, fro)
+
+
+def test_decoder_stack_wrapper_vs_oracle():
+    """VisualExpertDecoder.llm_forward (layers + masked final norm, :547-573), eager and CUDA-graph replay."""
+    from mmmm_b200.inputs import make_inputs
+    from mmmm_b200.modeling_cogvlm import VexConfig, VisualExpertDecoder
+    H, I, heads, nl = 512, 768, 4, 3
+    ws = [O.random_weights(H, I, heads, seed=20 + i, dtype=torch.bfloat16) for i in range(nl)]
+    model = VisualExpertDecoder(VexConfig(hidden_size=H, intermediate_size=I, num_attention_heads=heads,
+                                          num_hidden_layers=nl))
+    sd = {f"layers.{i}.{k}": v for i, w in enumerate(ws) for k, v in w.items()}
+    norm_w = (1 + 0.1 * torch.randn(H, generator=torch.Generator().manual_seed(5))).bfloat16()
+    sd["norm.weight"] = norm_w
+    model.load_state_dict(sd, strict=True)
+    model = model.to(torch.bfloat16).cuda().eval()
+    inp = make_inputs(2, 100, 30, H, ragged=True, seed=21)
+    ref = O.decoder_stack(ws, inp.hidden_states, inp.token_type_ids, inp.position_ids, inp.padding_mask,
+                          num_heads=heads, final_norm_weight=norm_w)
+    d = inp.to("cuda")
+    with torch.no_grad():
+        out, cache = model.llm_forward(d.hidden_states, d.token_type_ids, d.padding_mask.long(), d.position_ids)
+        out_g, _ = model.llm_forward(d.hidden_states, d.token_type_ids, d.padding_mask.long(), d.position_ids,
+                                     graph=True)
+        _, cache = model.llm_forward(d.hidden_states, d.token_type_ids, d.padding_mask.long(), d.position_ids,
+                                     use_cache=True)
+    assert cache is not None and len(cache) == nl and cache[0][0].shape == (2, heads, inp.padding_mask.shape[1], 128)
+    assert torch.equal(out, out_g)
+    pm = inp.padding_mask
+    mx, fro = _errs(out.cpu()[pm], ref[pm])
+    assert mx <= 2 * MAX_REL and fro <= 2 * FRO_REL, (mx, fro)

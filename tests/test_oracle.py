@@ -123,3 +123,32 @@ def test_lora_restatement_is_additive():
     y0 = O.linear(x, w[p + ".weight"])
     y1 = O.linear(x, w[p + ".weight"], lora[p])
     torch.testing.assert_close(y1 - y0, x @ lora[p].A.T @ lora[p].B.T, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.skipif(not RL.reference_available(), reason="/root/reference not present on this machine")
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_oracle_decode_steps_bit_exact_vs_live_reference(dtype):
+    """Prefill with use_cache, then two q_len == 1 steps through the generation branch (:129-141, :258-262)."""
+    from mmmm_b200.inputs import make_ids
+    hidden, heads, inter = 256, 2, 320
+    layer, cfg = RL.make_reference_layer(hidden, inter, heads, dtype=dtype, seed=6)
+    tt, pos, pm = make_ids(3, 11, 9, ragged=True, seed=6)
+    g = torch.Generator().manual_seed(10)
+    h = torch.randn(3, tt.shape[1], hidden, generator=g).to(dtype)
+    w = dict(layer.state_dict())
+    with torch.no_grad():
+        _, ref_kv = layer(h, token_type_ids=tt, position_ids=pos, padding_mask=pm, use_cache=True)
+    _, kv = O.decoder_layer(w, h, tt, pos, pm, num_heads=heads, rms_norm_eps=cfg.rms_norm_eps, use_cache=True)
+    mask = pm.clone()
+    next_pos = pos.max(dim=1, keepdim=True).values + 1
+    for step in range(2):
+        x = torch.randn(3, 1, hidden, generator=g).to(dtype)
+        mask = torch.cat([mask, torch.ones(3, 1, dtype=torch.bool)], dim=1)
+        tt1 = torch.zeros(3, 1, dtype=torch.long)
+        with torch.no_grad():
+            ref_out, ref_kv = layer(x, token_type_ids=tt1, position_ids=next_pos + step, padding_mask=mask,
+                                    past_key_value=ref_kv, use_cache=True)
+        out, kv = O.decoder_layer(w, x, tt1, next_pos + step, mask, num_heads=heads,
+                                  rms_norm_eps=cfg.rms_norm_eps, use_cache=True, past_key_value=kv)
+        assert torch.equal(out, ref_out)
+        assert torch.equal(kv[0], ref_kv[0]) and torch.equal(kv[1], ref_kv[1])
