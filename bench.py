@@ -105,6 +105,12 @@ def cpu_forward_timer(workload: str, steps: int, warmup: int, lora_r: int = 0):
     """fp32 eager forward of ONE sample of the workload through the oracle (reference restatement)."""
     from oracle import oracle_layer as O
     from mmmm_b200.inputs import make_inputs
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would pin the CPU
+    # arm to one core)
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
     _, nv, nt = WORKLOADS[workload]
     w = O.random_weights(H, I, HEADS, seed=0, dtype=torch.float32)
     lora = O.random_lora(H, I, r=lora_r, dtype=torch.float32) if lora_r else None
