@@ -377,6 +377,83 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """BASELINE config 5: LoRA (r = --lora, default 64) forward + backward of an N-layer visual-expert decoder with
+    the LoRA-gradient all-reduce (NCCL) -- one step = fwd + self-checkpointed bwd + all-reduce over one batch.
+    Backward arithmetic is the interim PyTorch-op implementation (mmmm_b200/training.py)."""
+    import torch.distributed as dist
+    from mmmm_b200 import instrument
+    from mmmm_b200.inputs import make_inputs
+    from mmmm_b200.sharding import max_over_ranks
+    from mmmm_b200.training import LoraGradReducer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    r = args.lora or 64
+    b, nv, nt = WORKLOADS[args.workload]
+    layers = [make_gpu_layer(dev, r, seed=i).train() for i in range(args.layers)]
+    params = [p for l in layers for p in l.parameters() if p.requires_grad]
+    reducer = LoraGradReducer(params)
+    inp = make_inputs(b, nv, nt, H, seed=rank).to(dev)
+    tokens = int(inp.padding_mask.sum())
+    proj = torch.randn_like(inp.hidden_states)
+    ar_ms = []
+
+    def step():
+        h = inp.hidden_states.detach().requires_grad_(True)
+        x = h
+        for layer in layers:
+            x = layer(x, token_type_ids=inp.token_type_ids, position_ids=inp.position_ids,
+                      padding_mask=inp.padding_mask)[0]
+        loss = (x.float() * proj.float()).mean()
+        for p in params:
+            p.grad = None
+        loss.backward()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        reducer.reduce()
+        e1.record()
+        ar_ms.append((e0, e1))
+        return loss
+
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ar_ms.clear()
+    instrument.reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    launches = instrument.launches()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms_step = max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+    allreduce_ms = sum(a.elapsed_time(b_) for a, b_ in ar_ms) / max(len(ar_ms), 1)
+    if rank == 0:
+        total = tokens * world
+        print(json.dumps({
+            "metric": "visual-expert LoRA train tokens/s", "value": total / (ms_step / 1e3), "unit": "tokens/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": dict(config_dict(args, tokens), lora_r=r, mode="train: fwd + recompute + bwd + LoRA-grad allreduce"),
+            "allreduce_ms": allreduce_ms, "allreduce_bytes": reducer.nbytes, "trainable_params": reducer.flat.numel(),
+            "gpu_launches": launches,
+            "note": "backward arithmetic = interim PyTorch device ops (cuBLAS / SDPA); forward = native kernels",
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -387,12 +464,15 @@ def main():
     ap.add_argument("--lora", type=int, default=0, help="LoRA rank on all ten Linears (0 = frozen weights only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--layers", type=int, default=1, help="decoder layers per step (32 = the full stack, config 3/4)")
+    ap.add_argument("--train", action="store_true", help="config 5: LoRA fwd+bwd training step + grad all-reduce")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the forward as one CUDA graph (default), 0: eager")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.train:
+        run_train(args)
     else:
         run_ours(args)
 

@@ -258,8 +258,9 @@ def _lora_t(x_sorted: torch.Tensor, specs: Tuple[LinearSpec, LinearSpec], counts
 
 def visual_expert_layer_forward(layer: "CogVLMDecoderLayer", hidden_states: torch.Tensor, plan: RoutingPlan,
                                 position_ids: torch.Tensor, *, use_cache: bool = False,
-                                fuse_epilogue: Optional[bool] = None):
-    """The whole layer on the device; returns (out [B, L, H], present_kv or None)."""
+                                fuse_epilogue: Optional[bool] = None, keep: Optional[dict] = None):
+    """The whole layer on the device; returns (out [B, L, H], present_kv or None).  ``keep`` (training recompute):
+    a dict that receives the intermediates the backward needs (gate/up are then materialised separately)."""
     fuse = _fuse_default() if fuse_epilogue is None else fuse_epilogue
     attn, mlp = layer.self_attn, layer.mlp
     B, L, H = hidden_states.shape
@@ -285,13 +286,19 @@ def visual_expert_layer_forward(layer: "CogVLMDecoderLayer", hidden_states: torc
     pos_flat = position_ids.reshape(-1)
     qkv = new(cap, 3 * H)  # token order: row t = [q(heads*128) | k | v], q and k rotated
     t, r, lb = _lora_t(xn, qkv_s, counts)
-    ops.grouped_gemm_fused(xn, W(qkv_s), qkv, counts, ops.EPI_ROPE, plan.sorted_to_token, None, [t, None],
+    if keep is not None:
+        keep.update(xn1=xn, t_qkv=t, specs=dict(qkv=qkv_s, dense=dense_s, gate=gate_s, up=up_s, down=down_s),
+                    ln1=ln1, ln2=ln2, cos=cos, sin=sin)
+        xn = new(cap, H)  # the second norm gets its own buffer (xn1 is needed by the backward)
+    ops.grouped_gemm_fused(keep["xn1"] if keep is not None else xn, W(qkv_s), qkv, counts, ops.EPI_ROPE, plan.sorted_to_token, None, [t, None],
                            [lb[0], None, lb[1], None], r, [cos, sin, pos_flat, s2f], 2 * H, False, 1.0)
     ctx = new(cap, H)      # expert-sorted order again: the A operand of the dense GEMM
     ops.attention(qkv, plan.cu_seqlens, B, L, heads, plan.token_to_sorted, ctx, HEAD_DIM ** -0.5)
     h1 = new(B, L, H)
     ops.copy_padded_rows(hf, plan.flat_to_sorted, h1.view(cap, H))
     t, r, lb = _lora_t(ctx, dense_s, counts)
+    if keep is not None:
+        keep.update(qkv=qkv, ctx=ctx, t_dense=t)
     if fuse:
         ops.grouped_gemm_fused(ctx, W(dense_s), h1.view(cap, H), counts, ops.EPI_RESIDUAL, s2f, hf, [t, None],
                                [lb[0], None, lb[1], None], r, [], 0, False, 1.0)
@@ -308,7 +315,9 @@ def visual_expert_layer_forward(layer: "CogVLMDecoderLayer", hidden_states: torc
     tu, ru, lbu = _lora_t(xn, up_s, counts)
     if (tg is None) != (tu is None) or rg != ru:
         raise NotImplementedError("gate_proj and up_proj adapters must come in pairs of equal rank")
-    if fuse:
+    if keep is not None:
+        keep.update(xn2=xn, t_gate=tg, t_up=tu)
+    if fuse and keep is None:
         w4 = [_bf16(gate_s[0].weight), _bf16(up_s[0].weight), _bf16(gate_s[1].weight), _bf16(up_s[1].weight)]
         ops.grouped_gemm_fused(xn, w4, act, counts, ops.EPI_SWIGLU, None, None, [tg, tu],
                                [lbg[0], lbu[0], lbg[1], lbu[1]], rg, [], 0, False, 1.0)
@@ -319,7 +328,11 @@ def visual_expert_layer_forward(layer: "CogVLMDecoderLayer", hidden_states: torc
         ops.grouped_gemm_fused(xn, W(up_s), u, counts, ops.EPI_PLAIN, None, None, [tu, None],
                                [lbu[0], None, lbu[1], None], ru, [], 0, False, 1.0)
         ops.silu_mul(g, u, plan.n_valid, act)
+        if keep is not None:
+            keep.update(gate=g, up=u)
     t, r, lb = _lora_t(act, down_s, counts)
+    if keep is not None:
+        keep.update(act=act, t_down=t, h1=h1.clone())  # h1 is overwritten in place by the down projection below
     if fuse:  # in place: h1[row] += down(act)[row]; padded rows of h1 already hold the input
         ops.grouped_gemm_fused(act, W(down_s), h1.view(cap, H), counts, ops.EPI_RESIDUAL, s2f, None, [t, None],
                                [lb[0], None, lb[1], None], r, [], 0, False, 1.0)
@@ -464,10 +477,10 @@ class CogVLMDecoderLayer(nn.Module):
             raise ValueError("token_type_ids / position_ids must be [B, L] like hidden_states")
         if not decode and hidden_states.shape[1] == 1:
             raise NotImplementedError("q_len == 1 without a KV cache is not part of the prefill path")
-        if torch.is_grad_enabled() and (hidden_states.requires_grad or any(
-                p.requires_grad for p in self.parameters())):
-            raise NotImplementedError("the fused layer is forward-only in this round (training variant: "
-                                      "BASELINE config 5); run under torch.no_grad()")
+        train = torch.is_grad_enabled() and (hidden_states.requires_grad or any(
+            p.requires_grad for p in self.parameters()))
+        if train and (decode or use_cache):
+            raise NotImplementedError("autograd through the decode / use_cache paths is not implemented")
         if output_attentions:
             warnings.warn("output_attentions is not implemented.")  # same as the reference (:281-282)
         hidden_states = hidden_states.contiguous()
@@ -477,6 +490,10 @@ class CogVLMDecoderLayer(nn.Module):
             out, present = visual_expert_layer_decode(self, hidden_states, position_ids.contiguous(),
                                                       padding_mask.bool().contiguous(), past_key_value,
                                                       use_cache=bool(use_cache))
+        elif train:  # LoRA training step (BASELINE config 5): fused forward, self-checkpointing backward
+            from .training import layer_forward_train
+            plan = GLOBAL_PLAN_CACHE.get(token_type_ids, padding_mask)
+            out, present = layer_forward_train(self, hidden_states, plan, position_ids.contiguous()), None
         else:
             plan = GLOBAL_PLAN_CACHE.get(token_type_ids, padding_mask)
             out, present = visual_expert_layer_forward(self, hidden_states, plan, position_ids.contiguous(),

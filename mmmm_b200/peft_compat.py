@@ -142,6 +142,7 @@ class MockModulesToSave(nn.Module):
         self.active_adapters = [adapter_name]
         self.disable_adapters = False
         self.original_module.requires_grad_(False)
+        self.modules_to_save.requires_grad_(True)
 
     def forward(self, *a, **k):
         return resolve_norm(self)(*a, **k)
@@ -152,6 +153,9 @@ def attach_mock_lora(layer: nn.Module, r: int = 64, lora_alpha: float = 8, b_std
     """Wraps a decoder layer's children the way ``get_peft_model`` would with the targets of
     mmmm/utils.py:19-43: all ten Linears (vision-only when ``lora_lang`` is False,
     modeling_cogvlm.py:79-85, :211-220) and both RMSNorms as modules_to_save."""
+    for p in layer.parameters():  # get_peft_model freezes every base parameter (mark_only_lora_as_trainable)
+        p.requires_grad_(False)
+
     def wrap(parent, name):
         setattr(parent, name, MockLoraLinear(getattr(parent, name), r=r, lora_alpha=lora_alpha, b_std=b_std))
 

@@ -165,8 +165,8 @@ def test_error_behaviour_on_gpu():
             layer(h.cpu(), ids.cpu(), ids.cpu(), pm.cpu())
         out = layer(h, ids, ids, attention_mask=pm)   # BASELINE's name for the 4th argument
         assert out[0].shape == h.shape
-    with pytest.raises(NotImplementedError):           # grad-requiring call: forward-only this round
-        layer(h, ids, ids, pm)
+    with pytest.raises(NotImplementedError):           # base weights are frozen under PEFT: full fine-tuning is
+        layer(h, ids, ids, pm)                         # not what the fused training path implements
 
 
 @pytest.mark.parametrize("ragged", [False, True])
@@ -303,3 +303,64 @@ def test_decoder_stack_wrapper_vs_oracle():
     pm = inp.padding_mask
     mx, fro = _errs(out.cpu()[pm], ref[pm])
     assert mx <= 2 * MAX_REL and fro <= 2 * FRO_REL, (mx, fro)
+
+
+@pytest.mark.parametrize("lora_lang", [True, False])
+def test_training_step_gradients_vs_oracle_autograd(lora_lang):
+    """BASELINE config 5 shape of work on a small layer: LoRA forward + backward through the fused layer
+    (self-checkpointing autograd.Function) against torch.autograd over the oracle in fp32 on the same
+    bf16-representable values: gradients of the input, every lora_A / lora_B and both RMSNorm weights."""
+    from mmmm_b200.inputs import make_inputs
+    H, I, heads, r = 512, 768, 4, 32
+    w = O.random_weights(H, I, heads, seed=31, dtype=torch.bfloat16)
+    ad = O.random_lora(H, I, r=r, seed=32, dtype=torch.bfloat16, b_std=0.05)
+    if not lora_lang:
+        ad = {k: v for k, v in ad.items() if "vision" in k}
+    from mmmm_b200.modeling_cogvlm import CogVLMDecoderLayer, VexConfig
+    from mmmm_b200.peft_compat import attach_mock_lora
+    layer = CogVLMDecoderLayer(VexConfig(hidden_size=H, intermediate_size=I, num_attention_heads=heads,
+                                         lora_lang=lora_lang))
+    layer.load_state_dict(w)
+    layer = layer.to(torch.bfloat16).cuda()
+    attach_mock_lora(layer, r=r, lora_lang=lora_lang)
+    for path, a in ad.items():
+        m = layer.get_submodule(path)
+        m.lora_A["default"].weight.data.copy_(a.A)
+        m.lora_B["default"].weight.data.copy_(a.B)
+        m.scaling["default"] = a.scaling
+    layer.train()
+    inp = make_inputs(2, 90, 30, H, ragged=True, seed=33)
+    pm = inp.padding_mask
+    gsel = torch.Generator().manual_seed(34)
+    proj = torch.randn(inp.hidden_states.shape, generator=gsel).bfloat16() * pm[..., None]   # d_out (0 on padding)
+
+    x = inp.hidden_states.cuda().requires_grad_(True)
+    (out,) = layer(x, token_type_ids=inp.token_type_ids.cuda(), position_ids=inp.position_ids.cuda(),
+                   padding_mask=pm.cuda())
+    (out.float() * proj.cuda().float()).sum().backward()
+
+    # oracle autograd in fp32
+    wf = {k: v.float() for k, v in w.items()}
+    adf = {k: O.LoRA(v.A.float().requires_grad_(True), v.B.float().requires_grad_(True), v.scaling) for k, v in ad.items()}
+    for k in ("input_layernorm.weight", "post_attention_layernorm.weight"):
+        wf[k].requires_grad_(True)
+    xr = inp.hidden_states.float().requires_grad_(True)
+    (ref,) = O.decoder_layer(wf, xr, inp.token_type_ids, inp.position_ids, pm, num_heads=heads, lora=adf)
+    (ref * proj.float()).sum().backward()
+
+    def close(got, want, name, tol=4e-2):
+        e = float((got.float().cpu() - want).norm() / want.norm().clamp_min(1e-12))
+        assert e <= tol, (name, e)
+
+    mx, fro = _errs(out.detach().cpu()[pm], ref.detach()[pm])
+    assert mx <= MAX_REL and fro <= FRO_REL, (mx, fro)
+    close(x.grad[pm.cuda()], xr.grad[pm], "d_hidden")
+    for path, a in adf.items():
+        m = layer.get_submodule(path)
+        close(m.lora_A["default"].weight.grad, a.A.grad, path + ".lora_A")
+        close(m.lora_B["default"].weight.grad, a.B.grad, path + ".lora_B")
+    close(layer.input_layernorm.modules_to_save["default"].weight.grad, wf["input_layernorm.weight"].grad, "ln1")
+    close(layer.post_attention_layernorm.modules_to_save["default"].weight.grad,
+          wf["post_attention_layernorm.weight"].grad, "ln2")
+    if not lora_lang:   # language adapters do not exist: nothing else received a gradient
+        assert all(p.grad is None for n, p in layer.named_parameters() if not p.requires_grad)

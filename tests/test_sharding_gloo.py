@@ -41,6 +41,17 @@ def _worker(rank, world, port, tmp):
         assert max_over_ranks(10.0 + rank) == 10.0 + world - 1
         total = sum_over_ranks(float(pm.sum()))
         assert total == float(inp.padding_mask.sum())
+        # LoRA-gradient all-reduce through the flat buffer (the training variant's only collective)
+        from mmmm_b200.training import LoraGradReducer
+        ps = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5)),
+              torch.nn.Parameter(torch.zeros(2), requires_grad=False)]
+        ps[0].grad = torch.full((3, 4), float(rank + 1))
+        ps[1].grad = torch.arange(5.0) * (rank + 1)
+        red = LoraGradReducer(ps, chunk_bytes=16)
+        assert red.flat.numel() == 17
+        red.reduce()
+        mean = sum(range(1, world + 1)) / world
+        assert torch.equal(ps[0].grad, torch.full((3, 4), mean)) and torch.equal(ps[1].grad, torch.arange(5.0) * mean)
         dist.barrier()
         if rank == 0:
             (full,) = O.decoder_layer(w, inp.hidden_states, inp.token_type_ids, inp.position_ids, inp.padding_mask,
