@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VEX_ABI_VERSION 1
+#define VEX_ABI_VERSION 2
 
 #define VEX_OK 0
 #define VEX_E_INVALID (-1)     /* bad argument (null pointer, size, alignment) */
@@ -140,6 +140,11 @@ typedef struct vexGemmArgs {
   int32_t mode;
   int32_t single_expert;    /* 1: counts[0] rows all use w[0][*] (plain dense GEMM) */
   float alpha;              /* VEX_EPI_PLAIN: out = bf16(alpha * acc) (LoRA scaling folded into T) */
+  int32_t w_transposed;     /* 0: w is [N, K] (forward, out = A . W^T).  1: w is [K, N] row-major and out = A . W --
+                               the backward form dX = dY . W that reads the nn.Linear weight [out, in] as stored
+                               (K = out features, N = in features; what autograd does for :244-245 etc.).  lora_b[e][0]
+                               is then lora_A [r, N] and lora_t = scaling * dY . lora_B.  PLAIN / RESIDUAL only;
+                               K % 64 == 0 */
 } vexGemmArgs;
 
 int vex_grouped_gemm(const vexGemmArgs* args, vexStream stream);
@@ -160,6 +165,34 @@ int vex_attention(const void* qkv, const int32_t* cu_seqlens, int B, int max_len
  * out [B, heads*128].  Query scaled in bf16, bf16 scores, fp32 softmax cast to bf16, like the eager reference. */
 int vex_attention_decode(const void* q, int64_t ldq, const void* k, const void* v, const uint8_t* mask, void* out,
                          int B, int heads, int L, float scale, vexStream stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Training-step variant (BASELINE config 5): backward of the layer for LoRA fine-tuning.  The reference has no
+ * backward code of its own -- torch.autograd differentiates modeling_cogvlm.py:30-340 inside
+ * MMMMForCausalLM.training_step (mmmm/models/mmmm.py:299-306) under non-reentrant checkpointing (:287-291);
+ * these entry points are the adjoints of the forward kernels above.  The input-gradient GEMMs are
+ * vex_grouped_gemm with w_transposed = 1.
+ * --------------------------------------------------------------------------------------------------- */
+
+/* out[r] = x[row_src[r]] for r < *n_rows (bf16 rows of H elements, H % 8 == 0): gathers d_out [B*L, H] into
+ * expert-sorted order -- the adjoint of the out[mask] = ... scatters (:96-97, :278-279). */
+int vex_gather_rows(const void* x, const int32_t* row_src, const int32_t* n_rows, void* out, int rows_cap, int H,
+                    vexStream stream);
+
+/* Adjoint of K5 / the SwiGLU epilogue (MLP.forward :55): given d(act), gate = gate_proj(x), up = up_proj(x)
+ * (bf16, [rows_cap, I]) writes dgate and dup with the eager-bf16 rounding points
+ * (s = bf16(silu(gate)); dup = bf16(dact * s); dgate = bf16(bf16(dact * up) * silu'(gate))). */
+int vex_silu_mul_backward(const void* dact, const void* gate, const void* up, void* dgate, void* dup,
+                          const int32_t* n_rows, int rows_cap, int I, vexStream stream);
+
+/* Adjoint of K2 (RMSNorm.forward :36-41), fp32 internals:
+ *   dx[dx_map[r]] = bf16( inv*(dy[r]*w) - x*inv^3*sum(dy[r]*w*x)/H  +  add[add_map[r]] ),  x = x[x_map[r]]
+ *   dweight[H] (fp32, caller-zeroed or accumulating) += sum_r dy[r] * x * inv
+ * `add` (may be NULL) is the gradient arriving through the residual branch (:321, :330), fused here.
+ * Maps may be NULL (identity).  H in {256, 512, 1024, 2048, 4096}. */
+int vex_rmsnorm_backward(const void* dy, const void* x, const int32_t* x_map, const void* weight, int weight_is_fp32,
+                         float eps, const void* add, const int32_t* add_map, void* dx, const int32_t* dx_map,
+                         float* dweight, const int32_t* n_rows, int rows_cap, int H, vexStream stream);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,7 @@ COUNT_VISION, COUNT_LANGUAGE, COUNT_VALID, COUNT_MAXLEN, NUM_COUNTS = 0, 1, 2, 3
 SYMBOLS = [
     "vex_abi_version", "vex_error_string", "vex_last_cuda_error", "vex_device_check", "vex_partition",
     "vex_rmsnorm_gather", "vex_silu_mul", "vex_residual_scatter", "vex_copy_padded_rows", "vex_grouped_gemm",
-    "vex_attention", "vex_attention_decode",
+    "vex_attention", "vex_attention_decode", "vex_gather_rows", "vex_silu_mul_backward", "vex_rmsnorm_backward",
 ]
 
 
@@ -35,7 +35,7 @@ class GemmArgs(C.Structure):
         ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("position_ids", C.c_void_p),
         ("sorted_to_flat", C.c_void_p), ("rope_len", C.c_int32), ("rope_cols", C.c_int32),
         ("rows_cap", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("mode", C.c_int32),
-        ("single_expert", C.c_int32), ("alpha", C.c_float),
+        ("single_expert", C.c_int32), ("alpha", C.c_float), ("w_transposed", C.c_int32),
     ]
 
 
@@ -72,6 +72,9 @@ def lib() -> C.CDLL:
         L.vex_grouped_gemm.argtypes = [C.POINTER(GemmArgs), p]
         L.vex_attention.argtypes = [p, p, i32, i32, i32, p, p, f32, p]
         L.vex_attention_decode.argtypes = [p, i64, p, p, p, p, i32, i32, i32, f32, p]
+        L.vex_gather_rows.argtypes = [p, p, p, p, i32, i32, p]
+        L.vex_silu_mul_backward.argtypes = [p, p, p, p, p, p, i32, i32, p]
+        L.vex_rmsnorm_backward.argtypes = [p, p, p, p, i32, f32, p, p, p, p, p, p, i32, i32, p]
         for name in SYMBOLS:
             fn = getattr(L, name)
             if name not in ("vex_error_string",):

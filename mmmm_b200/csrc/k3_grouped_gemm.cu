@@ -64,6 +64,7 @@ struct GemmDev {
   int rows_cap, N, K, mode, single_expert;
   int lora_steps;  // 64-wide k-blocks along r (0 = no LoRA)
   int lora_mask;   // bit e: expert e has an adapter
+  int trans_b;     // 1: weights are [K, N] row-major (MN-major B operand): out = A . W  (backward dgrad)
 };
 
 template <int BN>
@@ -80,6 +81,17 @@ struct GemmCfg {
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * EPI_WARP_BYTES + NUM_BARS * 8 + 16 + 1024;
 };
+
+// B-operand descriptor of one pipeline stage.  MN-major tiles are stored as 64-column chunks of 8 KB
+// (64 k-rows x 128 B): LBO = 8192 (next chunk of 64 n), SBO = 1024 (next group of 8 k-rows).
+constexpr int MN_CHUNK_BYTES = 64 * BK * 2;
+template <bool TB>
+__device__ __forceinline__ uint64_t b_desc(uint32_t smem_addr) {
+  if constexpr (TB) return umma_desc_mnmajor_sw128(smem_addr, MN_CHUNK_BYTES, 1024);
+  else return umma_desc_kmajor_sw128(smem_addr);
+}
+template <bool TB>
+constexpr uint64_t B_KSTEP = TB ? (16 * 128) >> 4 : 2;  // descriptor start-address increment per K = 16 step
 
 struct TileCoord {
   int e, m, n;
@@ -300,7 +312,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, int e, int m, in
   }
 }
 
-template <int BN>
+// TB = true: the B operand is MN-major -- the weight tensor is [K, N] row-major (N contiguous), loaded as
+// BN/64 boxes of {64 n, 64 k} (8 KB each, 128B-swizzled k-rows); this is the dgrad form dX = dY . W, which
+// reads the nn.Linear weight [out, in] exactly as stored (K = out, N = in) -- no transposed copy.
+template <int BN, bool TB>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     k3_grouped_gemm(const __grid_constant__ GemmTmaps tm, const GemmDev p) {
   using Cfg = GemmCfg<BN>;
@@ -368,8 +383,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         uint8_t* sb = sa + Cfg::A_BYTES;
         mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
         tma_load_2d(sa, &tm.a, &full_bar[stage], kb * BK, row0);
-        tma_load_2d(sb, w0, &full_bar[stage], kb * BK, nrow0);
-        tma_load_2d(sb + Cfg::HALF_B, w1, &full_bar[stage], kb * BK, nrow1);
+        if constexpr (TB) {
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c)
+            tma_load_2d(sb + c * MN_CHUNK_BYTES, w0, &full_bar[stage], nrow0 + 64 * c, kb * BK);
+        } else {
+          tma_load_2d(sb, w0, &full_bar[stage], kb * BK, nrow0);
+          tma_load_2d(sb + Cfg::HALF_B, w1, &full_bar[stage], kb * BK, nrow1);
+        }
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -389,8 +410,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             } else {
               mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
               tma_load_2d(sa, &tm.t[0], &full_bar[stage], ls * BK, row0);
-              tma_load_2d(sb, &tm.lb[c.e][0], &full_bar[stage], ls * BK, nrow0);
-              tma_load_2d(sb + Cfg::HALF_B, &tm.lb[c.e][0], &full_bar[stage], ls * BK, nrow1);
+              if constexpr (TB) {
+#pragma unroll
+                for (int cc = 0; cc < BN / 64; ++cc)
+                  tma_load_2d(sb + cc * MN_CHUNK_BYTES, &tm.lb[c.e][0], &full_bar[stage], nrow0 + 64 * cc, ls * BK);
+              } else {
+                tma_load_2d(sb, &tm.lb[c.e][0], &full_bar[stage], ls * BK, nrow0);
+                tma_load_2d(sb + Cfg::HALF_B, &tm.lb[c.e][0], &full_bar[stage], ls * BK, nrow1);
+              }
             }
             if (++stage == STAGES) {
               stage = 0;
@@ -402,8 +429,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
   } else if (warp == 1 && lane == 0) {
     // =============================== MMA issuer ===============================
-    constexpr uint32_t idesc_full = umma_idesc_bf16(BM, BN);
-    constexpr uint32_t idesc_half = umma_idesc_bf16(BM, BN / 2);
+    constexpr uint32_t idesc_full = umma_idesc_bf16(BM, BN, 0, TB ? 1 : 0);
+    constexpr uint32_t idesc_half = umma_idesc_bf16(BM, BN / 2, 0, TB ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -419,11 +446,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
         const uint64_t da = umma_desc_kmajor_sw128(sa);
-        const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::A_BYTES);
+        const uint64_t db = b_desc<TB>(sa + Cfg::A_BYTES);
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
-          // +32 bytes per K=16 step inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-          umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc_full, accumulate);
+          // K-major: +32 bytes per K=16 step inside the 128-byte swizzle row (+2 in the addr >> 4 field);
+          // MN-major: 16 k-rows of 128 B = +2048 bytes (+128)
+          umma_ss(d_tmem, da + 2 * k, db + B_KSTEP<TB> * k, idesc_full, accumulate);
           accumulate = 1;
         }
         umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
@@ -440,11 +468,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
             const uint64_t da = umma_desc_kmajor_sw128(sa);
-            const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::A_BYTES);
+            const uint64_t db = b_desc<TB>(sa + Cfg::A_BYTES);
             const uint32_t d_half = d_tmem + static_cast<uint32_t>(swiglu ? h * (BN / 2) : 0);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_ss(d_half, da + 2 * k, db + 2 * k, swiglu ? idesc_half : idesc_full, 1u);
+              umma_ss(d_half, da + 2 * k, db + B_KSTEP<TB> * k, swiglu ? idesc_half : idesc_full, 1u);
             umma_commit(&empty_bar[stage]);
             if (++stage == STAGES) {
               stage = 0;
@@ -536,6 +564,7 @@ __device__ __forceinline__ PairTile decode_pair_tile(int tile, int mp0, int mp1,
   return c;
 }
 
+template <bool TB>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     k3_grouped_gemm_pair(const __grid_constant__ GemmTmaps tm, const GemmDev p) {
   using Cfg = PairCfg;
@@ -605,7 +634,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
         if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
         tma_load_2d_pair(sa, &tm.a, full_leader, kb * BK, row0);
-        tma_load_2d_pair(sa + Cfg::A_BYTES, wmap, full_leader, kb * BK, nrow);
+        if constexpr (TB) {  // this CTA's 128 columns of B = two {64 n, 64 k} boxes
+          tma_load_2d_pair(sa + Cfg::A_BYTES, wmap, full_leader, nrow, kb * BK);
+          tma_load_2d_pair(sa + Cfg::A_BYTES + MN_CHUNK_BYTES, wmap, full_leader, nrow + 64, kb * BK);
+        } else {
+          tma_load_2d_pair(sa + Cfg::A_BYTES, wmap, full_leader, kb * BK, nrow);
+        }
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -627,7 +661,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             } else {
               if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
               tma_load_2d_pair(sa, &tm.t[0], full_leader, ls * BK, row0);
-              tma_load_2d_pair(sa + Cfg::A_BYTES, &tm.lb[c.e][0], full_leader, ls * BK, nrow);
+              if constexpr (TB) {
+                tma_load_2d_pair(sa + Cfg::A_BYTES, &tm.lb[c.e][0], full_leader, nrow, ls * BK);
+                tma_load_2d_pair(sa + Cfg::A_BYTES + MN_CHUNK_BYTES, &tm.lb[c.e][0], full_leader, nrow + 64, ls * BK);
+              } else {
+                tma_load_2d_pair(sa + Cfg::A_BYTES, &tm.lb[c.e][0], full_leader, ls * BK, nrow);
+              }
             }
             if (++stage == STAGES) {
               stage = 0;
@@ -639,8 +678,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
   } else if (warp == 1 && lane == 0 && rank == 0) {
     // =============================== MMA issuer (leader CTA) ===============================
-    constexpr uint32_t idesc_full = umma_idesc_bf16(2 * BM, BN);
-    constexpr uint32_t idesc_half = umma_idesc_bf16(2 * BM, BN / 2);
+    constexpr uint32_t idesc_full = umma_idesc_bf16(2 * BM, BN, 0, TB ? 1 : 0);
+    constexpr uint32_t idesc_half = umma_idesc_bf16(2 * BM, BN / 2, 0, TB ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -656,10 +695,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
         const uint64_t da = umma_desc_kmajor_sw128(sa);
-        const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::A_BYTES);
+        const uint64_t db = b_desc<TB>(sa + Cfg::A_BYTES);
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
-          umma_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc_full, accumulate);
+          umma_ss_pair(d_tmem, da + 2 * k, db + B_KSTEP<TB> * k, idesc_full, accumulate);
           accumulate = 1;
         }
         umma_commit_pair(&empty_bar[stage], 3);  // frees the slot in both CTAs
@@ -676,11 +715,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
             const uint64_t da = umma_desc_kmajor_sw128(sa);
-            const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::A_BYTES);
+            const uint64_t db = b_desc<TB>(sa + Cfg::A_BYTES);
             const uint32_t d_half = d_tmem + static_cast<uint32_t>(swiglu ? h * (BN / 2) : 0);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_ss_pair(d_half, da + 2 * k, db + 2 * k, swiglu ? idesc_half : idesc_full, 1u);
+              umma_ss_pair(d_half, da + 2 * k, db + B_KSTEP<TB> * k, swiglu ? idesc_half : idesc_full, 1u);
             umma_commit_pair(&empty_bar[stage], 3);
             if (++stage == STAGES) {
               stage = 0;
@@ -772,23 +811,24 @@ int num_sms() {
   return n;
 }
 
-template <int BN>
+template <int BN, bool TB>
 static int launch_gemm(const GemmTmaps& tm, const GemmDev& dev, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    VEX_CUDA_TRY(cudaFuncSetAttribute(k3_grouped_gemm<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VEX_CUDA_TRY(cudaFuncSetAttribute(k3_grouped_gemm<BN, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       GemmCfg<BN>::SMEM_BYTES));
     configured = true;
   }
-  k3_grouped_gemm<BN><<<num_sms(), GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, s>>>(tm, dev);
+  k3_grouped_gemm<BN, TB><<<num_sms(), GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, s>>>(tm, dev);
   VEX_LAUNCH_CHECK();
   return VEX_OK;
 }
 
+template <bool TB>
 static int launch_gemm_pair(const GemmTmaps& tm, const GemmDev& dev, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    VEX_CUDA_TRY(cudaFuncSetAttribute(k3_grouped_gemm_pair, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VEX_CUDA_TRY(cudaFuncSetAttribute(k3_grouped_gemm_pair<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       PairCfg::SMEM_BYTES));
     configured = true;
   }
@@ -805,7 +845,7 @@ static int launch_gemm_pair(const GemmTmaps& tm, const GemmDev& dev, cudaStream_
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  VEX_CUDA_TRY(cudaLaunchKernelEx(&cfg, k3_grouped_gemm_pair, tm, dev));
+  VEX_CUDA_TRY(cudaLaunchKernelEx(&cfg, k3_grouped_gemm_pair<TB>, tm, dev));
   return VEX_OK;
 }
 
@@ -833,6 +873,9 @@ extern "C" int vex_grouped_gemm(const vexGemmArgs* a, vexStream stream) {
       return VEX_E_INVALID;
     if (a->rope_cols % 128 != 0) return VEX_E_UNSUPPORTED;  // heads of 128
   }
+  const bool tb = a->w_transposed != 0;
+  if (tb && (swiglu || a->mode == VEX_EPI_ROPE)) return VEX_E_UNSUPPORTED;
+  if (tb && (a->K % 64 != 0 || (a->lora_r > 0 && a->lora_r % 8 != 0))) return VEX_E_UNSUPPORTED;
   const bool small_n = a->N <= 64 && a->mode == VEX_EPI_PLAIN;
   const int BN = small_n ? 64 : 256;
   const int half_rows = swiglu ? 128 : BN / 2;
@@ -844,7 +887,9 @@ extern "C" int vex_grouped_gemm(const vexGemmArgs* a, vexStream stream) {
   const int n_exp = a->single_expert ? 1 : 2;
   for (int e = 0; e < n_exp; ++e)
     for (int h = 0; h < (swiglu ? 2 : 1); ++h)
-      if ((rc = make_tmap_2d(&tm.w[e][h], a->w[e][h], a->N, a->K, a->ldw, half_rows)) != VEX_OK) return rc;
+      if ((rc = tb ? make_tmap_2d(&tm.w[e][h], a->w[e][h], a->K, a->N, a->ldw, 64)  // [K, N]: boxes of {64 n, 64 k}
+                   : make_tmap_2d(&tm.w[e][h], a->w[e][h], a->N, a->K, a->ldw, half_rows)) != VEX_OK)
+        return rc;
 
   GemmDev dev;
   std::memset(&dev, 0, sizeof(dev));
@@ -859,7 +904,9 @@ extern "C" int vex_grouped_gemm(const vexGemmArgs* a, vexStream stream) {
         if (swiglu && !a->lora_b[e][1 - h]) return VEX_E_UNSUPPORTED;  // gate and up adapters come in pairs
         any = true;
         dev.lora_mask |= 1 << e;
-        if ((rc = make_tmap_2d(&tm.lb[e][h], a->lora_b[e][h], a->N, a->lora_r, a->lora_r, half_rows)) != VEX_OK)
+        // transposed form: the K-extension reads lora_A [r, N] (dX += (s dT) . A)
+        if ((rc = tb ? make_tmap_2d(&tm.lb[e][h], a->lora_b[e][h], a->lora_r, a->N, a->N, 64)
+                     : make_tmap_2d(&tm.lb[e][h], a->lora_b[e][h], a->N, a->lora_r, a->lora_r, half_rows)) != VEX_OK)
           return rc;
         if (swiglu &&
             (rc = make_tmap_2d(&tm.lb64[e][h], a->lora_b[e][h], a->N, a->lora_r, a->lora_r, 64)) != VEX_OK)
@@ -889,7 +936,12 @@ extern "C" int vex_grouped_gemm(const vexGemmArgs* a, vexStream stream) {
   dev.K = a->K;
   dev.mode = a->mode;
   dev.single_expert = a->single_expert;
+  dev.trans_b = tb;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (small_n) return launch_gemm<64>(tm, dev, s);
-  return use_pair_kernel() ? launch_gemm_pair(tm, dev, s) : launch_gemm<256>(tm, dev, s);
+  if (tb) {
+    if (small_n) return launch_gemm<64, true>(tm, dev, s);
+    return use_pair_kernel() ? launch_gemm_pair<true>(tm, dev, s) : launch_gemm<256, true>(tm, dev, s);
+  }
+  if (small_n) return launch_gemm<64, false>(tm, dev, s);
+  return use_pair_kernel() ? launch_gemm_pair<false>(tm, dev, s) : launch_gemm<256, false>(tm, dev, s);
 }

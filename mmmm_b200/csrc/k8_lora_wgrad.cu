@@ -1,0 +1,199 @@
+// K8 -- LoRA weight gradients of the routed Linears on tcgen05: per expert e (row segment of the sorted order)
+//
+//     OUT_e[f, j] += sum_{t in segment e}  X[t, f] * Y[t, j]          f < F (128-wide tiles), j < r (<= 64)
+//
+// which is both adapter gradients of  y = x W^T + s (x A^T) B^T  (PEFT lora.Linear on top of
+// modeling_cogvlm.py:244-245, :278-279, :96-97; wiring scripts/cli.py:82-88):
+//     dB[out, r] = dy^T . T          X = dy  [rows, out],  Y = T  = s x A^T [rows, r]   (kept by the forward)
+//     dA[r, in]  = dT^T . x          X = x   [rows, in ],  Y = dT = s dy B  [rows, r]   (from the dgrad GEMM),
+//                                    stored transposed (transpose_out = 1)
+// The reduction runs over TOKENS, so both operands are MN-major (the contiguous dimension is f resp. j, not the
+// reduction index): X tiles arrive as two {64 f, 64 t} TMA boxes (A operand, M = 128), Y as one {64 j, 64 t} box
+// (B operand, N = 64); D[128, 64] fp32 lives in 64 TMEM columns.  HBM-bound (X is read once: 2 F bytes per
+// token); the grid is (F / 128) x token-chunks of 1024 so every SM streams, partial sums are combined with fp32
+// atomics into the caller-zeroed gradient buffers.  Rows past the segment end belong to the other expert or are
+// uninitialised, so the last k-block of a chunk zeroes them in shared memory before the MMA reads it.
+#include <cuda.h>
+
+#include <cstring>
+
+#include "common.cuh"
+
+namespace vex {
+
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+
+constexpr int WG_CHUNK = 1024;  // tokens per CTA
+constexpr int WG_BK = 64;       // tokens per k-block
+constexpr int WG_STAGES = 4;
+constexpr int WG_A_BYTES = 128 * WG_BK * 2;  // 16 KB: two 8 KB chunks of 64 features
+constexpr int WG_B_BYTES = 64 * WG_BK * 2;   // 8 KB
+constexpr int WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES;
+constexpr int WG_THREADS = 192;
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 256 + 1024;
+
+struct WgTmaps {
+  CUtensorMap x, y;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+    k8_lora_wgrad(const __grid_constant__ WgTmaps tm, const int32_t* __restrict__ counts, float* __restrict__ out0,
+                  float* __restrict__ out1, int64_t ldo, int transpose_out, int F, int r, int rows_cap) {
+  // ---- which (expert, token chunk) is this CTA's? ----
+  const int cnt0 = min(max(counts[0], 0), rows_cap);
+  const int cnt1 = min(max(counts[1], 0), rows_cap - cnt0);
+  const int nc0 = (cnt0 + WG_CHUNK - 1) / WG_CHUNK, nc1 = (cnt1 + WG_CHUNK - 1) / WG_CHUNK;
+  int c = blockIdx.y, e = 0, lo, hi;
+  if (c < nc0) {
+    lo = c * WG_CHUNK;
+    hi = min(cnt0, lo + WG_CHUNK);
+  } else {
+    c -= nc0;
+    if (c >= nc1) return;
+    e = 1;
+    lo = cnt0 + c * WG_CHUNK;
+    hi = min(cnt0 + cnt1, lo + WG_CHUNK);
+  }
+  float* out = e ? out1 : out0;
+  if (out == nullptr) return;  // this expert has no adapter
+  const int n_kb = (hi - lo + WG_BK - 1) / WG_BK;
+  const int f0 = blockIdx.x * 128;
+
+  extern __shared__ uint8_t wg_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wg_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + WG_STAGES;
+  uint64_t* acc_full = bars + 2 * WG_STAGES;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 2 * WG_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < WG_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_base_smem, 64);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm.x);
+    tma_prefetch_desc(&tm.y);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // =============================== TMA producer ===============================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < n_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * WG_STAGE_BYTES;
+        const int t0 = lo + kb * WG_BK;
+        mbar_arrive_expect_tx(&full_bar[stage], WG_STAGE_BYTES);
+        tma_load_2d(sa, &tm.x, &full_bar[stage], f0, t0);
+        tma_load_2d(sa + 8192, &tm.x, &full_bar[stage], f0 + 64, t0);
+        tma_load_2d(sa + WG_A_BYTES, &tm.y, &full_bar[stage], 0, t0);
+        if (++stage == WG_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (whole warp: boundary fix-up) ===============================
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);  // A and B MN-major
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < n_kb; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      uint8_t* sa = smem + stage * WG_STAGE_BYTES;
+      const int valid = hi - (lo + kb * WG_BK);  // token rows of this k-block inside the segment
+      if (valid < WG_BK) {
+        // token row t of a box is the 128-byte line t of each 8 KB chunk (the swizzle permutes inside the line)
+        for (int i = lane; i < (WG_BK - valid) * 8 * 3; i += 32) {
+          const int chunk = i / ((WG_BK - valid) * 8), rem = i % ((WG_BK - valid) * 8);
+          const int row = valid + rem / 8, piece = rem % 8;
+          *reinterpret_cast<uint4*>(sa + chunk * 8192 + row * 128 + piece * 16) = make_uint4(0, 0, 0, 0);
+        }
+        fence_proxy_async_smem();
+      }
+      __syncwarp();
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a = smem_u32(sa), b = a + WG_A_BYTES;
+#pragma unroll
+        for (int k = 0; k < WG_BK / 16; ++k)
+          umma_ss(tmem, umma_desc_mnmajor_sw128(a + k * 2048, 8192, 1024),
+                  umma_desc_mnmajor_sw128(b + k * 2048, 8192, 1024), idesc, (kb > 0) || (k > 0));
+        umma_commit(&empty_bar[stage]);
+        if (kb == n_kb - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+      if (++stage == WG_STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else {
+    // =============================== epilogue: TMEM -> fp32 atomics ===============================
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int f = f0 + q * 32 + lane;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem + (static_cast<uint32_t>(q * 32) << 16) + half * 32, v);
+      tmem_ld_wait();
+      if (f < F) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = half * 32 + j;
+          if (col < r) {
+            float* dst = transpose_out ? out + static_cast<int64_t>(col) * ldo + f : out + static_cast<int64_t>(f) * ldo + col;
+            atomicAdd(dst, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 64);
+  }
+}
+
+}  // namespace vex
+
+extern "C" int vex_lora_wgrad(const void* x, int64_t ldx, const void* y, int64_t ldy, int r, float* out_vision,
+                              float* out_language, int64_t ldo, int transpose_out, const int32_t* counts, int rows_cap,
+                              int F, vexStream stream) {
+  using namespace vex;
+  if (!x || !y || !counts || (!out_vision && !out_language) || rows_cap <= 0 || F <= 0) return VEX_E_INVALID;
+  if (r <= 0 || r > 64 || r % 8 != 0 || F % 8 != 0 || ldx % 8 != 0 || ldy % 8 != 0) return VEX_E_UNSUPPORTED;
+  static bool configured = false;
+  if (!configured) {
+    VEX_CUDA_TRY(cudaFuncSetAttribute(k8_lora_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+    configured = true;
+  }
+  WgTmaps tm;
+  std::memset(&tm, 0, sizeof(tm));
+  int rc;
+  if ((rc = make_tmap_2d(&tm.x, x, rows_cap, F, ldx, WG_BK)) != VEX_OK) return rc;
+  if ((rc = make_tmap_2d(&tm.y, y, rows_cap, r, ldy, WG_BK)) != VEX_OK) return rc;
+  // every expert segment adds at most one partial chunk
+  dim3 grid(ceil_div(F, 128), ceil_div(rows_cap, WG_CHUNK) + 1);
+  k8_lora_wgrad<<<grid, WG_THREADS, WG_SMEM, static_cast<cudaStream_t>(stream)>>>(
+      tm, counts, out_vision, out_language, ldo, transpose_out, F, r, rows_cap);
+  VEX_LAUNCH_CHECK();
+  return VEX_OK;
+}

@@ -141,10 +141,12 @@ def grouped_gemm_raw(a: torch.Tensor, w: Sequence[Optional[torch.Tensor]], out: 
                      lora_t: Sequence[Optional[torch.Tensor]] = (None, None),
                      lora_b: Sequence[Optional[torch.Tensor]] = (None, None, None, None), lora_r: int = 0,
                      rope: Optional[tuple] = None, rope_cols: int = 0, single_expert: bool = False,
-                     alpha: float = 1.0, n_out: Optional[int] = None) -> None:
+                     alpha: float = 1.0, n_out: Optional[int] = None, w_transposed: bool = False) -> None:
     """K3 (vex_grouped_gemm).  ``w`` = [vision_w0, vision_w1, language_w0, language_w1] ([N, K] each; the *_w1
     entries are up_proj for SWIGLU, else None).  ``lora_b`` likewise; ``lora_t`` = [T_half0, T_half1].
-    ``rope`` = (cos [S,128], sin [S,128], position_ids int64 [B*L], sorted_to_flat int32)."""
+    ``rope`` = (cos [S,128], sin [S,128], position_ids int64 [B*L], sorted_to_flat int32).
+    ``w_transposed``: the weights are [K, N] (out = a . w, the dgrad form dX = dY . W over the nn.Linear weight as
+    stored) and ``lora_b`` holds lora_A [r, N]."""
     _dev(a, "a", _BF16)
     _dev(out, "out", _BF16)
     _dev(counts, "counts", torch.int32)
@@ -158,15 +160,17 @@ def grouped_gemm_raw(a: torch.Tensor, w: Sequence[Optional[torch.Tensor]], out: 
         if wt is None:
             continue
         _dev(wt, f"w[{i}]", _BF16)
-        if wt.dim() != 2 or wt.shape[1] != K:
-            raise ValueError(f"w[{i}] must be [N, {K}], got {tuple(wt.shape)}")
-        N = wt.shape[0] if N is None else N
-        if wt.shape[0] != N:
+        kd, nd = (0, 1) if w_transposed else (1, 0)
+        if wt.dim() != 2 or wt.shape[kd] != K:
+            raise ValueError(f"w[{i}] must be {'[K, N]' if w_transposed else '[N, K]'} with K = {K}, got {tuple(wt.shape)}")
+        N = wt.shape[nd] if N is None else N
+        if wt.shape[nd] != N:
             raise ValueError("all weights of one grouped GEMM must share N")
         args.w[i // 2][i % 2] = wt.data_ptr()
     if N is None:
         raise ValueError("no weights given")
-    args.ldw = K
+    args.ldw = N if w_transposed else K
+    args.w_transposed = int(w_transposed)
     if lora_r:
         for h, t in enumerate(lora_t):
             if t is not None:
@@ -178,8 +182,8 @@ def grouped_gemm_raw(a: torch.Tensor, w: Sequence[Optional[torch.Tensor]], out: 
             if bt is None:
                 continue
             _dev(bt, f"lora_b[{i}]", _BF16)
-            if tuple(bt.shape) != (N, lora_r):
-                raise ValueError(f"lora_b[{i}] must be [{N}, {lora_r}]")
+            if tuple(bt.shape) != ((lora_r, N) if w_transposed else (N, lora_r)):
+                raise ValueError(f"lora_b[{i}] must be [{N}, {lora_r}] ([{lora_r}, {N}] = lora_A when transposed)")
             args.lora_b[i // 2][i % 2] = bt.data_ptr()
         args.lora_r = lora_r
     args.out, args.ldo = out.data_ptr(), out.shape[-1]
@@ -204,7 +208,8 @@ def grouped_gemm_raw(a: torch.Tensor, w: Sequence[Optional[torch.Tensor]], out: 
     args.rows_cap, args.N, args.K, args.mode = rows_cap, (n_out or N), K, mode
     args.single_expert = int(single_expert)
     args.alpha = alpha
-    name = ("gemm_plain", "gemm_rope", "gemm_swiglu", "gemm_residual")[mode] + ("_n64" if N <= 64 else "")
+    name = ("gemm_plain", "gemm_rope", "gemm_swiglu", "gemm_residual")[mode] + ("_n64" if N <= 64 else "") + \
+        ("_dgrad" if w_transposed else "")
     with instrument.region(name):
       rc = _lib.lib().vex_grouped_gemm(C.byref(args), _stream())
     _lib.check(rc, "vex_grouped_gemm")
@@ -228,6 +233,22 @@ def grouped_gemm_fused(a: torch.Tensor, w: List[Optional[torch.Tensor]], out: to
     grouped_gemm_raw(a, w, out, counts, mode, row_map=row_map, residual=residual, lora_t=lora_t, lora_b=lora_b,
                      lora_r=lora_r, rope=tuple(rope) if len(rope) else None, rope_cols=rope_cols,
                      single_expert=single_expert, alpha=alpha)
+
+
+@torch.library.custom_op("vex::grouped_gemm_dgrad", mutates_args=("out",))
+def grouped_gemm_dgrad(dy: torch.Tensor, w: List[Optional[torch.Tensor]], out: torch.Tensor, counts: torch.Tensor,
+                       accumulate: bool, row_map: Optional[torch.Tensor], lora_dt: Optional[torch.Tensor],
+                       lora_a: List[Optional[torch.Tensor]], lora_r: int, single_expert: bool, alpha: float) -> None:
+    """Backward of the routed Linear w.r.t. its input (what autograd computes for modeling_cogvlm.py:244-245,
+    :278-279, :96-97): out[map(r)] (+)= dy[r] . W_e (+ dT[r] . A_e), with ``w`` = [vision W, language W] as STORED
+    ([out_features, in_features]; read as an MN-major B operand, no transposed copy), ``lora_dt`` = scaling * dy .
+    lora_B and ``lora_a`` = [vision lora_A, language lora_A] ([r, in_features]).  ``accumulate`` adds onto ``out``
+    in place (second term of d(xn) = dgate . Wg + dup . Wu)."""
+    wv, wl = (list(w) + [None])[:2]
+    av, al = (list(lora_a) + [None, None])[:2]
+    grouped_gemm_raw(dy, [wv, None, wl, None], out, counts, EPI_RESIDUAL if accumulate else EPI_PLAIN, row_map=row_map,
+                     lora_t=[lora_dt, None], lora_b=[av, None, al, None], lora_r=lora_r, single_expert=single_expert,
+                     alpha=alpha, w_transposed=True)
 
 
 # ------------------------------------------------------------------------------------------ K4
@@ -266,6 +287,63 @@ def attention_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask: to
     _lib.check(rc, "vex_attention_decode")
 
 
-for _op in (attention_decode, partition, rmsnorm_gather, silu_mul, residual_scatter, copy_padded_rows, grouped_gemm, grouped_gemm_fused,
+# ------------------------------------------------------------------------------------------ K7 (backward, row-wise)
+@torch.library.custom_op("vex::gather_rows", mutates_args=("out",))
+def gather_rows(x: torch.Tensor, row_src: Optional[torch.Tensor], n_rows: torch.Tensor, out: torch.Tensor) -> None:
+    """out[r] = x[row_src[r]], r < *n_rows (vex_gather_rows): d_out [B*L, H] -> expert-sorted rows."""
+    _dev(x, "x", _BF16), _dev(out, "out", _BF16), _dev(n_rows, "n_rows", torch.int32)
+    H = x.shape[-1]
+    if out.shape[-1] != H:
+        raise ValueError("row width mismatch")
+    with instrument.region("gather_rows"):
+      rc = _lib.lib().vex_gather_rows(x.data_ptr(), _ptr(None if row_src is None else _dev(row_src, "row_src", torch.int32)),
+                                      n_rows.data_ptr(), out.data_ptr(), out.numel() // H, H, _stream())
+    _lib.check(rc, "vex_gather_rows")
+
+
+@torch.library.custom_op("vex::silu_mul_backward", mutates_args=("dgate", "dup"))
+def silu_mul_backward(dact: torch.Tensor, gate: torch.Tensor, up: torch.Tensor, n_rows: torch.Tensor,
+                      dgate: torch.Tensor, dup: torch.Tensor) -> None:
+    """Adjoint of act_fn(gate) * up (modeling_cogvlm.py:55) -- vex_silu_mul_backward."""
+    for n, t in (("dact", dact), ("gate", gate), ("up", up), ("dgate", dgate), ("dup", dup)):
+        _dev(t, n, _BF16)
+        if t.shape != dact.shape:
+            raise ValueError("dact/gate/up/dgate/dup shapes differ")
+    I = dact.shape[-1]
+    with instrument.region("silu_mul_backward"):
+      rc = _lib.lib().vex_silu_mul_backward(dact.data_ptr(), gate.data_ptr(), up.data_ptr(), dgate.data_ptr(),
+                                            dup.data_ptr(), _dev(n_rows, "n_rows", torch.int32).data_ptr(),
+                                            dact.numel() // I, I, _stream())
+    _lib.check(rc, "vex_silu_mul_backward")
+
+
+@torch.library.custom_op("vex::rmsnorm_backward", mutates_args=("dx", "dweight"))
+def rmsnorm_backward(dy: torch.Tensor, x: torch.Tensor, x_map: Optional[torch.Tensor], weight: torch.Tensor, eps: float,
+                     add: Optional[torch.Tensor], add_map: Optional[torch.Tensor], dx: torch.Tensor,
+                     dx_map: Optional[torch.Tensor], dweight: Optional[torch.Tensor], n_rows: torch.Tensor) -> None:
+    """Adjoint of RMSNorm.forward (modeling_cogvlm.py:36-41) fused with the residual-branch gradient add and the
+    gather / scatter through the row maps -- vex_rmsnorm_backward.  ``dweight`` (fp32 [H]) is accumulated into."""
+    _dev(dy, "dy", _BF16), _dev(x, "x", _BF16), _dev(dx, "dx", _BF16), _dev(weight, "weight")
+    if weight.dtype not in (_BF16, torch.float32):
+        raise TypeError("RMSNorm weight must be bf16 or fp32")
+    H = dy.shape[-1]
+    if x.shape[-1] != H or dx.shape[-1] != H or weight.numel() != H:
+        raise ValueError("hidden size mismatch")
+    if add is not None:
+        _dev(add, "add", _BF16)
+    if dweight is not None:
+        _dev(dweight, "dweight", torch.float32)
+        if dweight.numel() != H:
+            raise ValueError("dweight must be fp32 [H]")
+    maps = [None if m is None else _dev(m, "row map", torch.int32) for m in (x_map, add_map, dx_map)]
+    with instrument.region("rmsnorm_backward"):
+      rc = _lib.lib().vex_rmsnorm_backward(dy.data_ptr(), x.data_ptr(), _ptr(maps[0]), weight.data_ptr(),
+                                           int(weight.dtype == torch.float32), float(eps), _ptr(add), _ptr(maps[1]),
+                                           dx.data_ptr(), _ptr(maps[2]), _ptr(dweight),
+                                           _dev(n_rows, "n_rows", torch.int32).data_ptr(), dy.numel() // H, H, _stream())
+    _lib.check(rc, "vex_rmsnorm_backward")
+
+
+for _op in (gather_rows, silu_mul_backward, rmsnorm_backward, grouped_gemm_dgrad, attention_decode, partition, rmsnorm_gather, silu_mul, residual_scatter, copy_padded_rows, grouped_gemm, grouped_gemm_fused,
             attention):
     _op.register_fake(lambda *a, **k: None)

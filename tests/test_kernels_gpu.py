@@ -127,6 +127,70 @@ def test_k6_residual_scatter_and_copy_padded():
     assert torch.equal(out.cpu(), want)
 
 
+# ------------------------------------------------------------------------------------------ K7 (backward, row-wise)
+def test_k7_gather_rows():
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(97, 4096, generator=g).bfloat16()
+    src = torch.randperm(97, generator=g)[:80].int()
+    out = torch.full((80, 4096), 5.0, dtype=torch.bfloat16).cuda()
+    ops.gather_rows(x.cuda(), src.cuda(), torch.tensor([61], dtype=torch.int32).cuda(), out)
+    assert torch.equal(out[:61].cpu(), x[src[:61].long()])
+    assert (out[61:] == 5.0).all()
+
+
+def test_k7_silu_mul_backward_vs_autograd():
+    """Adjoint of the eager bf16 act_fn(gate) * up (modeling_cogvlm.py:55) against torch.autograd on CPU."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(12)
+    n, I = 97, 11008
+    gate = (torch.randn(130, I, generator=g) * 2).bfloat16()
+    up = torch.randn(130, I, generator=g).bfloat16()
+    dact = torch.randn(130, I, generator=g).bfloat16()
+    ga, ua = gate[:n].clone().requires_grad_(True), up[:n].clone().requires_grad_(True)
+    (torch.nn.functional.silu(ga) * ua).backward(dact[:n])
+    dg = torch.zeros_like(gate).cuda()
+    du = torch.zeros_like(gate).cuda()
+    ops.silu_mul_backward(dact.cuda(), gate.cuda(), up.cuda(), torch.tensor([n], dtype=torch.int32).cuda(), dg, du)
+    torch.testing.assert_close(du[:n].cpu().float(), ua.grad.float(), rtol=1.6e-2, atol=1e-5)
+    torch.testing.assert_close(dg[:n].cpu().float(), ga.grad.float(), rtol=1.6e-2, atol=2e-3)
+    assert (dg[n:] == 0).all() and (du[n:] == 0).all()
+
+
+@pytest.mark.parametrize("H", [256, 1024, 2048, 4096])
+@pytest.mark.parametrize("wdtype", [torch.bfloat16, torch.float32])
+def test_k7_rmsnorm_backward_vs_autograd(H, wdtype):
+    """Adjoint of RMSNorm.forward (:36-41) incl. gather of x, the fused residual-gradient add, the scatter of dx and
+    the fp32 weight gradient, against torch.autograd over the oracle's rms_norm."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(H)
+    n_src, n_rows, cap = 300, 200, 211
+    x = (torch.randn(n_src, H, generator=g) * 3).bfloat16()
+    w = (1 + 0.2 * torch.randn(H, generator=g)).to(wdtype)
+    dy = torch.randn(cap, H, generator=g).bfloat16()
+    add = torch.randn(cap, H, generator=g).bfloat16()
+    xmap = torch.randperm(n_src, generator=g)[:cap].int()
+    dmap = torch.randperm(n_src, generator=g)[:cap].int()
+    xa = x[xmap[:n_rows].long()].clone().requires_grad_(True)
+    wa = w.clone().requires_grad_(True)
+    O.rms_norm(xa, wa, 1e-6).backward(dy[:n_rows])
+    dx = torch.full((n_src, H), 7.0, dtype=torch.bfloat16).cuda()
+    dw = torch.zeros(H, dtype=torch.float32).cuda()
+    ops.rmsnorm_backward(dy.cuda(), x.cuda(), xmap.cuda(), w.cuda(), 1e-6, add.cuda(), None, dx, dmap.cuda(), dw,
+                         torch.tensor([n_rows], dtype=torch.int32).cuda())
+    want = torch.full((n_src, H), 7.0)
+    want[dmap[:n_rows].long()] = xa.grad.float() + add[:n_rows].float()
+    torch.testing.assert_close(dx.cpu().float(), want, rtol=1.6e-2, atol=2e-2)
+    torch.testing.assert_close(dw.cpu(), wa.grad.float(), rtol=2e-2, atol=0.15)
+    # accumulating into dweight, no add, identity maps
+    dx2 = torch.zeros(cap, H, dtype=torch.bfloat16).cuda()
+    ops.rmsnorm_backward(dy.cuda(), x[xmap.long()].contiguous().cuda(), None, w.cuda(), 1e-6, None, None, dx2, None, dw,
+                         torch.tensor([n_rows], dtype=torch.int32).cuda())
+    torch.testing.assert_close(dx2[:n_rows].cpu().float(), xa.grad.float(), rtol=1.6e-2, atol=2e-2)
+    torch.testing.assert_close(dw.cpu(), 2 * wa.grad.float(), rtol=2e-2, atol=0.3)
+    assert (dx2[n_rows:] == 0).all()
+
+
 # ------------------------------------------------------------------------------------------ K3
 @pytest.fixture(params=["pair", "single"], autouse=False)
 def gemm_kernel(request, monkeypatch):
@@ -297,6 +361,78 @@ def test_k3_rope_epilogue_scatter_to_token_order(gemm_kernel):
     want = torch.cat([qr.permute(0, 2, 1, 3).reshape(T, Hd), kr.permute(0, 2, 1, 3).reshape(T, Hd), v], dim=-1)
     got = out.cpu()[s2t]
     torch.testing.assert_close(got.float(), want.float(), rtol=2e-2, atol=2e-2)
+
+
+# ------------------------------------------------------------------------------------------ K3 backward (dgrad)
+def _ref_dgrad(dy, wv, wl, Tv, Tl):
+    """dX = dY . W with W as stored [out, in] (autograd of F.linear w.r.t. its input), per expert segment."""
+    out = torch.zeros(dy.shape[0], wv.shape[1], dtype=torch.float32, device=dy.device)
+    out[:Tv] = dy[:Tv].float() @ wv.float()
+    out[Tv:Tv + Tl] = dy[Tv:Tv + Tl].float() @ wl.float()
+    return out
+
+
+DGRAD_SHAPES = [  # Tv, Tl, N (= in features), K (= out features)
+    (300, 100, 512, 256), (1, 1, 256, 128), (0, 77, 256, 192), (77, 0, 768, 256), (129, 255, 320, 448),
+    (1000, 517, 1024, 1024), (700, 300, 2752, 512),
+]
+
+
+@pytest.mark.parametrize("Tv,Tl,N,K", DGRAD_SHAPES)
+def test_k3_dgrad_transposed_weights(Tv, Tl, N, K, gemm_kernel):
+    """MN-major B operand: the nn.Linear weight [out = K, in = N] is read as stored."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(N * 7 + K)
+    cap = Tv + Tl + 5
+    dy = torch.randn(cap, K, generator=g).bfloat16().cuda()
+    wv = (torch.randn(K, N, generator=g) * 0.05).bfloat16().cuda()
+    wl = (torch.randn(K, N, generator=g) * 0.05).bfloat16().cuda()
+    counts = torch.tensor([Tv, Tl, Tv + Tl, 0], dtype=torch.int32).cuda()
+    T = Tv + Tl
+    out = torch.full((cap, N), 3.0, dtype=torch.bfloat16).cuda()
+    ops.grouped_gemm_dgrad(dy, [wv, wl], out, counts, False, None, None, [None, None], 0, False, 1.0)
+    want = _ref_dgrad(dy, wv, wl, Tv, Tl)
+    torch.testing.assert_close(out[:T].float(), want[:T], rtol=1e-2, atol=1e-2)
+    assert (out[T:] == 3.0).all()
+    # accumulate in place + scatter through a row map
+    gmap = torch.randperm(cap, generator=g).int().cuda()
+    base = torch.randn(cap, N, generator=g).bfloat16().cuda()
+    out2 = base.clone()
+    ops.grouped_gemm_dgrad(dy, [wv, wl], out2, counts, True, gmap, None, [None, None], 0, False, 1.0)
+    want2 = base.clone().float()
+    want2[gmap[:T].long()] += want[:T].bfloat16().float()
+    torch.testing.assert_close(out2.float(), want2, rtol=1e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("r", [64, 16])
+def test_k3_dgrad_lora(r, gemm_kernel):
+    """dX = dY . W + (s dY . B) . A: the small-N transposed GEMM (dT) and the transposed K-extension."""
+    ops = _ops()
+    Tv, Tl, N, K, s = 200, 150, 768, 512, 0.5
+    g = torch.Generator().manual_seed(77 + r)
+    cap = Tv + Tl + 3
+    T = Tv + Tl
+    dy = torch.randn(cap, K, generator=g).bfloat16().cuda()
+    mk = lambda *sh, sc=0.1: (torch.randn(*sh, generator=g) * sc).bfloat16().cuda()
+    wv, wl = mk(K, N, sc=0.05), mk(K, N, sc=0.05)
+    Av, Al = mk(r, N), mk(r, N)          # lora_A [r, in]
+    Bv, Bl = mk(K, r), mk(K, r)          # lora_B [out, r]
+    counts = torch.tensor([Tv, Tl, T, 0], dtype=torch.int32).cuda()
+    dt = torch.zeros(cap, r, dtype=torch.bfloat16).cuda()
+    ops.grouped_gemm_dgrad(dy, [Bv, Bl], dt, counts, False, None, None, [None, None], 0, False, s)
+    dt_ref = (_ref_dgrad(dy, Bv, Bl, Tv, Tl) * s).bfloat16()
+    torch.testing.assert_close(dt[:T].float(), dt_ref[:T].float(), rtol=1e-2, atol=1e-2)
+    assert (dt[T:] == 0).all()
+    out = torch.zeros(cap, N, dtype=torch.bfloat16).cuda()
+    ops.grouped_gemm_dgrad(dy, [wv, wl], out, counts, False, None, dt, [Av, Al], r, False, 1.0)
+    want = _ref_dgrad(dy, wv, wl, Tv, Tl) + _ref_dgrad(dt_ref, Av, Al, Tv, Tl)
+    torch.testing.assert_close(out[:T].float(), want[:T], rtol=1e-2, atol=2e-2)
+    # vision-only adapter
+    out.zero_()
+    ops.grouped_gemm_dgrad(dy, [wv, wl], out, counts, False, None, dt, [Av, None], r, False, 1.0)
+    want = _ref_dgrad(dy, wv, wl, Tv, Tl)
+    want[:Tv] += dt_ref[:Tv].float() @ Av.float()
+    torch.testing.assert_close(out[:T].float(), want[:T], rtol=1e-2, atol=2e-2)
 
 
 # ------------------------------------------------------------------------------------------ K4
