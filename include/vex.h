@@ -194,6 +194,17 @@ int vex_rmsnorm_backward(const void* dy, const void* x, const int32_t* x_map, co
                          float eps, const void* add, const int32_t* add_map, void* dx, const int32_t* dx_map,
                          float* dweight, const int32_t* n_rows, int rows_cap, int H, vexStream stream);
 
+/* K8 -- LoRA weight gradients on tcgen05 (both operands MN-major, reduction over tokens), per expert segment e:
+ *     out_e[f, j] += sum_{t in segment e} x[t, f] * y[t, j]        f < F, j < r
+ * fp32 atomics into caller-zeroed (or accumulating) buffers; out_e == NULL skips expert e.
+ *   dB[out, r] = dy^T . T   : x = dy [rows, out], y = T = scaling * a . lora_A^T (forward intermediate), transpose_out = 0, ldo = r
+ *   dA[r, in]  = dT^T . a   : x = a [rows, in],  y = dT = scaling * dy . lora_B,                        transpose_out = 1, ldo = in
+ * (autograd of PEFT lora.Linear over the routed Linears, scripts/cli.py:82-88; x / y rows in sorted order,
+ * row strides ldx / ldy elements; r % 8 == 0, r <= 64.) */
+int vex_lora_wgrad(const void* x, int64_t ldx, const void* y, int64_t ldy, int r, float* out_vision,
+                   float* out_language, int64_t ldo, int transpose_out, const int32_t* counts, int rows_cap, int F,
+                   vexStream stream);
+
 #ifdef __cplusplus
 }
 #endif

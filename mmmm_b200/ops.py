@@ -344,6 +344,30 @@ def rmsnorm_backward(dy: torch.Tensor, x: torch.Tensor, x_map: Optional[torch.Te
     _lib.check(rc, "vex_rmsnorm_backward")
 
 
-for _op in (gather_rows, silu_mul_backward, rmsnorm_backward, grouped_gemm_dgrad, attention_decode, partition, rmsnorm_gather, silu_mul, residual_scatter, copy_padded_rows, grouped_gemm, grouped_gemm_fused,
+# ------------------------------------------------------------------------------------------ K8
+@torch.library.custom_op("vex::lora_wgrad", mutates_args=("out_vision", "out_language"))
+def lora_wgrad(x: torch.Tensor, y: torch.Tensor, out_vision: Optional[torch.Tensor], out_language: Optional[torch.Tensor],
+               transpose_out: bool, counts: torch.Tensor) -> None:
+    """K8 (vex_lora_wgrad): out_e (+)= x_e^T . y_e over the rows of expert e (fp32 accumulate).  dB = dy^T . T with
+    out [F, r]; dA = dT^T . a with ``transpose_out`` and out [r, F]."""
+    _dev(x, "x", _BF16), _dev(y, "y", _BF16), _dev(counts, "counts", torch.int32)
+    F, r = x.shape[-1], y.shape[-1]
+    if x.numel() // F != y.numel() // r:
+        raise ValueError("x and y must have the same number of rows")
+    shape = (r, F) if transpose_out else (F, r)
+    for n, o in (("out_vision", out_vision), ("out_language", out_language)):
+        if o is not None:
+            _dev(o, n, torch.float32)
+            if tuple(o.shape) != shape:
+                raise ValueError(f"{n} must be fp32 {shape}")
+    if out_vision is None and out_language is None:
+        raise ValueError("no output given")
+    with instrument.region("lora_wgrad"):
+      rc = _lib.lib().vex_lora_wgrad(x.data_ptr(), F, y.data_ptr(), r, r, _ptr(out_vision), _ptr(out_language),
+                                     shape[1], int(transpose_out), counts.data_ptr(), x.numel() // F, F, _stream())
+    _lib.check(rc, "vex_lora_wgrad")
+
+
+for _op in (lora_wgrad, gather_rows, silu_mul_backward, rmsnorm_backward, grouped_gemm_dgrad, attention_decode, partition, rmsnorm_gather, silu_mul, residual_scatter, copy_padded_rows, grouped_gemm, grouped_gemm_fused,
             attention):
     _op.register_fake(lambda *a, **k: None)

@@ -435,6 +435,36 @@ def test_k3_dgrad_lora(r, gemm_kernel):
     torch.testing.assert_close(out[:T].float(), want[:T], rtol=1e-2, atol=2e-2)
 
 
+# ------------------------------------------------------------------------------------------ K8 (LoRA wgrad)
+@pytest.mark.parametrize("Tv,Tl,F,r", [(300, 100, 256, 64), (1, 1, 128, 64), (0, 77, 384, 16), (77, 0, 128, 64),
+                                       (2500, 1100, 1024, 64), (1024, 64, 640, 32), (5000, 3000, 11008, 64)])
+def test_k8_lora_wgrad(Tv, Tl, F, r):
+    """out_e = x_e^T . y_e over each expert's rows (tcgen05, both operands MN-major), fp32; rows of the other
+    expert / past the live count (NaN here) must not leak in."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(F + r + Tv)
+    T = Tv + Tl
+    cap = T + 70
+    x = torch.randn(cap, F, generator=g).bfloat16()
+    y = torch.randn(cap, r, generator=g).bfloat16()
+    x[T:] = float("nan")
+    y[T:] = float("nan")
+    counts = torch.tensor([Tv, Tl, T, 0], dtype=torch.int32).cuda()
+    xc, yc = x.cuda(), y.cuda()
+    want_v = xc[:Tv].float().T @ yc[:Tv].float()
+    want_l = xc[Tv:T].float().T @ yc[Tv:T].float()
+    tol = dict(rtol=2e-3, atol=2e-3 * max(T, 1) ** 0.5)
+    ov = torch.zeros(F, r, dtype=torch.float32).cuda()
+    ol = torch.zeros(F, r, dtype=torch.float32).cuda()
+    ops.lora_wgrad(xc, yc, ov, ol, False, counts)
+    torch.testing.assert_close(ov, want_v, **tol)
+    torch.testing.assert_close(ol, want_l, **tol)
+    # transposed store (dA layout), accumulating, language adapter absent
+    ot = torch.ones(r, F, dtype=torch.float32).cuda()
+    ops.lora_wgrad(xc, yc, ot, None, True, counts)
+    torch.testing.assert_close(ot, want_v.T + 1, **tol)
+
+
 # ------------------------------------------------------------------------------------------ K4
 @pytest.mark.parametrize("impl", ["tc", "mma"])
 @pytest.mark.parametrize("lens", [[1], [64], [65, 3, 128], [129, 128, 127], [300, 17, 1, 255], [1357], [700, 1485]])
