@@ -159,6 +159,12 @@ int vex_grouped_gemm(const vexGemmArgs* args, vexStream stream);
 int vex_attention(const void* qkv, const int32_t* cu_seqlens, int B, int max_len_cap, int heads,
                   const int32_t* out_row_map, void* out, float scale, vexStream stream);
 
+/* K4 (training): same as vex_attention, additionally writing the log-sum-exp of the scaled scores in the log2
+ * domain, lse[h * rows_cap + t] (fp32 [heads, rows_cap], rows_cap = B * max_len_cap; NULL = do not write), which
+ * vex_attention_backward reads.  tcgen05 implementation only. */
+int vex_attention_lse(const void* qkv, const int32_t* cu_seqlens, int B, int max_len_cap, int heads,
+                      const int32_t* out_row_map, void* out, float scale, float* lse, vexStream stream);
+
 /* K4d -- decode-step attention (q_len == 1 against the KV cache).  Replaces attention_fn's generation branch
  * (:129-141): q [B, heads*128] rows of stride ldq elements (already rotated), k / v [B, heads, L, 128] (the
  * reference cache layout, current token included), mask uint8 [B, L] (attention mask over past + current),
@@ -204,6 +210,22 @@ int vex_rmsnorm_backward(const void* dy, const void* x, const int32_t* x_map, co
 int vex_lora_wgrad(const void* x, int64_t ldx, const void* y, int64_t ldy, int r, float* out_vision,
                    float* out_language, int64_t ldo, int transpose_out, const int32_t* counts, int rows_cap, int F,
                    vexStream stream);
+
+/* K9 -- backward of K4 fused with the adjoint of the rotary embedding (attention_fn :106-128, rotary :188-193
+ * under autograd) and the scatter to expert-sorted rows.
+ *   qkv        [rows_cap, 3*heads*128] bf16, token order, q / k rotated (the forward's buffer, tail rows zeroed)
+ *   out_sorted [rows_cap, heads*128]   bf16, forward output in sorted order (row token_to_sorted[t] belongs to token t)
+ *   d_out_tok  [rows_cap, heads*128]   bf16, gradient of the forward output in TOKEN order; rows [T, T+128) are
+ *                                      zeroed by the call
+ *   lse        [heads, rows_cap] fp32 from vex_attention_lse; delta_ws [heads, rows_cap] fp32 workspace
+ *   position_ids int64 [B*L] indexed through token_to_flat; rope tables [rope_len, 128] bf16 (the forward's)
+ *   dqkv       [rows_cap, 3*heads*128] bf16 OUT: gradient w.r.t. the PRE-rotary q | k | v, row token_to_sorted[t]
+ *              (token_to_sorted / token_to_flat NULL = identity) -- the A operand of the QKV dgrad GEMM. */
+int vex_attention_backward(const void* qkv, const void* out_sorted, void* d_out_tok, const float* lse,
+                           float* delta_ws, const int32_t* cu_seqlens, const int32_t* token_to_sorted,
+                           const int32_t* token_to_flat, const int64_t* position_ids, const void* rope_cos,
+                           const void* rope_sin, int rope_len, int B, int max_len_cap, int heads, void* dqkv,
+                           float scale, vexStream stream);
 
 #ifdef __cplusplus
 }

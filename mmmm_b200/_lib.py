@@ -20,7 +20,7 @@ SYMBOLS = [
     "vex_abi_version", "vex_error_string", "vex_last_cuda_error", "vex_device_check", "vex_partition",
     "vex_rmsnorm_gather", "vex_silu_mul", "vex_residual_scatter", "vex_copy_padded_rows", "vex_grouped_gemm",
     "vex_attention", "vex_attention_decode", "vex_gather_rows", "vex_silu_mul_backward", "vex_rmsnorm_backward",
-    "vex_lora_wgrad",
+    "vex_lora_wgrad", "vex_attention_lse", "vex_attention_backward",
 ]
 
 
@@ -76,6 +76,8 @@ def lib() -> C.CDLL:
         L.vex_gather_rows.argtypes = [p, p, p, p, i32, i32, p]
         L.vex_silu_mul_backward.argtypes = [p, p, p, p, p, p, i32, i32, p]
         L.vex_rmsnorm_backward.argtypes = [p, p, p, p, i32, f32, p, p, p, p, p, p, i32, i32, p]
+        L.vex_attention_lse.argtypes = [p, p, i32, i32, i32, p, p, f32, p, p]
+        L.vex_attention_backward.argtypes = [p, p, p, p, p, p, p, p, p, p, p, i32, i32, i32, i32, p, f32, p]
         L.vex_lora_wgrad.argtypes = [p, i64, p, i64, i32, p, p, i64, i32, p, i32, i32, p]
         for name in SYMBOLS:
             fn = getattr(L, name)

@@ -53,7 +53,8 @@ __global__ void zero_tail_rows(__nv_bfloat16* buf, const int32_t* __restrict__ c
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k4_attention_tc(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* __restrict__ cu_seqlens, int heads,
-                    const int32_t* __restrict__ out_row_map, __nv_bfloat16* __restrict__ out, float scale_log2) {
+                    const int32_t* __restrict__ out_row_map, __nv_bfloat16* __restrict__ out, float scale_log2,
+                    float* __restrict__ lse, int rows_cap) {
   const int b = blockIdx.z, h = blockIdx.y;
   const int seq0 = cu_seqlens[b], len = cu_seqlens[b + 1] - seq0;
   const int qb = gridDim.x - 1 - blockIdx.x;  // heaviest query blocks first
@@ -261,6 +262,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     __syncwarp();
     const int tok = seq0 + q0 + r;
     const int my_dst = (q0 + r < len) ? (out_row_map ? out_row_map[tok] : tok) : -1;
+    // training: log2-domain log-sum-exp of the scaled scores, [heads, rows_cap] (read back by the backward kernels)
+    if (lse != nullptr && q0 + r < len)
+      lse[static_cast<int64_t>(h) * rows_cap + tok] = fmaf(m_run, scale_log2, log2f(l_run));
 #pragma unroll 4
     for (int it = 0; it < 16; ++it) {  // 2 rows of 256 B per iteration, 16 lanes each
       const int rr = it * 2 + (lane >> 4), piece = lane & 15;
@@ -284,7 +288,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 }
 
 int launch_attention_tc(const void* qkv, const int32_t* cu_seqlens, int B, int max_len_cap, int heads,
-                        const int32_t* out_row_map, void* out, float scale, int rows_cap, cudaStream_t s) {
+                        const int32_t* out_row_map, void* out, float scale, int rows_cap, float* lse, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
     VEX_CUDA_TRY(cudaFuncSetAttribute(k4_attention_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
@@ -301,7 +305,7 @@ int launch_attention_tc(const void* qkv, const int32_t* cu_seqlens, int B, int m
   dim3 grid(ceil_div(max_len_cap, TC_BQ), heads, B);
   k4_attention_tc<<<grid, TC_THREADS, TC_SMEM, s>>>(tm, cu_seqlens, heads, out_row_map,
                                                     static_cast<__nv_bfloat16*>(out),
-                                                    scale * 1.4426950408889634f);
+                                                    scale * 1.4426950408889634f, lse, rows_cap);
   VEX_LAUNCH_CHECK();
   return VEX_OK;
 }

@@ -1,0 +1,605 @@
+// K9 -- backward of the causal block-diagonal (varlen) attention on tcgen05 / TMEM, fused with the adjoint of the
+// rotary embedding and the scatter back to expert-sorted rows.
+//
+// Adjoint of attention_fn's prefill branch (modeling_cogvlm.py:106-128) and of apply_rotary_pos_emb_index_bhs
+// (:188-193) -- what torch.autograd runs for those lines in the reference's LoRA training step
+// (mmmm/models/mmmm.py:299-306).  With P = softmax(scale * Q K^T + causal), O = P V, delta = rowsum(dO * O):
+//     dV = P^T dO        dP = dO V^T        dS = P * (dP - delta)        dQ = scale * dS K        dK = scale * dS^T Q
+// P is recomputed from the log-sum-exp the forward kernel stores (log2 domain).  Two kernels, no atomics:
+//   k9_attn_bwd_dkdv : CTA = 128 keys of one (sample, head); loops over 64-query steps at or below the diagonal.
+//       S^T = K Q^T and dP^T = V dO^T (M = 128 keys, N = 64 queries, K-major operands) land in double-buffered
+//       TMEM; one softmax thread per KEY row turns them into P^T and dS^T (bf16, shared memory, K-major);
+//       dV += P^T dO and dK += dS^T Q accumulate in TMEM with dO / Q read as MN-major B operands from the very
+//       tiles TMA delivered.  512 TMEM columns: S^T x2, dP^T x2 (64 each), dV, dK (128 each).
+//   k9_attn_bwd_dq   : CTA = 128 queries; loops over 64-key steps; S = Q K^T, dP = dO V^T (N = 64), one softmax
+//       thread per QUERY row (its lse / delta are scalars), dQ += dS K with K as an MN-major B operand.
+// Epilogues: dQ and dK are multiplied by `scale`, pushed through the transpose of the rotary rotation with the
+// same bf16 tables the forward used, and all three gradients are written to the row token_to_sorted[t] of
+// dqkv [rows_cap, 3 * heads * 128] -- the A operand of the QKV dgrad GEMM.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace vex {
+
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+
+// rows [T, T + 128) of a token-order buffer can be touched by the last tile: keep them finite (0 * NaN = NaN)
+__global__ void k9_zero_tail_rows(__nv_bfloat16* buf, const int32_t* __restrict__ cu_seqlens, int B, int rows_cap,
+                                  int row_elems) {
+  const int T = cu_seqlens[B];
+  const int n_rows = min(rows_cap - T, 128);
+  const int64_t n_vec = static_cast<int64_t>(max(n_rows, 0)) * (row_elems / 8);
+  uint4* p = reinterpret_cast<uint4*>(buf + static_cast<int64_t>(T) * row_elems);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n_vec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    p[i] = make_uint4(0, 0, 0, 0);
+}
+
+constexpr int AB_THREADS = 256;
+constexpr int AB_T128 = 128 * 128 * 2;  // 32 KB tile of 128 rows x 128 d: two 16 KB atoms (64 d each)
+constexpr int AB_T64 = 64 * 128 * 2;    // 16 KB tile of 64 rows x 128 d: two 8 KB chunks
+constexpr int AB_P = 128 * 64 * 2;      // 16 KB: 128 rows x 64 bf16 (one 128-byte swizzle row each)
+
+struct BwdParams {
+  const int32_t* cu_seqlens;
+  const float* lse;     // [heads, rows_cap] log2-domain log-sum-exp (forward)
+  const float* delta;   // [heads, rows_cap] rowsum(dO * O)
+  const int32_t* token_to_sorted;
+  const int32_t* token_to_flat;
+  const int64_t* position_ids;
+  const __nv_bfloat16* rope_cos;
+  const __nv_bfloat16* rope_sin;
+  __nv_bfloat16* dqkv;
+  int heads, rows_cap, rope_len;
+  float scale, scale_log2;
+};
+
+// ---------------------------------------------------------------------------------------------
+// delta[h, t] = sum_d dO[t, h, d] * O[token_to_sorted[t], h, d]   (one warp per token, 16 lanes per head)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k9_attn_delta(const __nv_bfloat16* __restrict__ d_out_tok, const __nv_bfloat16* __restrict__ out_sorted,
+                  const int32_t* __restrict__ token_to_sorted, const int32_t* __restrict__ cu_seqlens, int B,
+                  float* __restrict__ delta, int heads, int rows_cap) {
+  const int T = min(cu_seqlens[B], rows_cap);
+  const int H = heads * 128;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int t = warp; t < T; t += n_warps) {
+    const int src = token_to_sorted ? token_to_sorted[t] : t;
+    const uint4* dp = reinterpret_cast<const uint4*>(d_out_tok + static_cast<int64_t>(t) * H);
+    const uint4* op = reinterpret_cast<const uint4*>(out_sorted + static_cast<int64_t>(src) * H);
+    for (int h0 = 0; h0 < heads; h0 += 2) {
+      const int head = h0 + (lane >> 4);
+      float acc = 0.f;
+      if (head < heads) {
+        const uint4 a = ld_stream(dp + head * 16 + (lane & 15)), b = ld_stream(op + head * 16 + (lane & 15));
+        const uint32_t au[4] = {a.x, a.y, a.z, a.w}, bu[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc = fmaf(bf16_lo(au[j]), bf16_lo(bu[j]), acc);
+          acc = fmaf(bf16_hi(au[j]), bf16_hi(bu[j]), acc);
+        }
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if ((lane & 15) == 0 && head < heads) delta[static_cast<int64_t>(head) * rows_cap + t] = acc;
+    }
+  }
+}
+
+// 32 fp32 values -> 16 packed bf16 pairs
+__device__ __forceinline__ void pack32(const float (&v)[32], uint32_t (&o)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+}
+
+// one 128-byte row (64 bf16 = 8 x 16 B) of a K-major SWIZZLE_128B tile; `half` selects columns [32*half, +32)
+__device__ __forceinline__ void store_row_half(uint32_t tile, int row, int half, const uint32_t (&o)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int chunk = half * 4 + i;
+    const uint32_t addr = tile + row * 128 + ((chunk ^ (row & 7)) << 4);
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o[4 * i]), "r"(o[4 * i + 1]),
+                 "r"(o[4 * i + 2]), "r"(o[4 * i + 3])
+                 : "memory");
+  }
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
+// gradient row (128 fp32 in TMEM at taddr) -> optional rotary transpose * mul -> bf16 -> dst[0..128)
+//   forward: y[j] = x[j] c[j] - x[j+64] s[j],  y[j+64] = x[j+64] c[j+64] + x[j] s[j+64]          (j < 64)
+//   adjoint: dx[j] = dy[j] c[j] + dy[j+64] s[j+64],  dx[j+64] = dy[j+64] c[j+64] - dy[j] s[j]
+__device__ __forceinline__ void ld_bf16x32(const __nv_bfloat16* p, float (&o)[32]) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 u = __ldg(q + i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      o[8 * i + 2 * j] = bf16_lo(w[j]);
+      o[8 * i + 2 * j + 1] = bf16_hi(w[j]);
+    }
+  }
+}
+
+__device__ __forceinline__ void st_packed32(__nv_bfloat16* dst, const uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<uint4*>(dst + i * 8) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+}
+
+__device__ __forceinline__ void store_grad_row(uint32_t taddr, bool rope, const __nv_bfloat16* cos_row,
+                                               const __nv_bfloat16* sin_row, float mul, __nv_bfloat16* dst,
+                                               bool valid) {
+#pragma unroll 1
+  for (int q = 0; q < 2; ++q) {
+    uint32_t lo[32], hi[32];
+    tmem_ld_32x32b_x32(taddr + q * 32, lo);       // columns [32q, 32q + 32)
+    tmem_ld_32x32b_x32(taddr + 64 + q * 32, hi);  // their rotary partners, + 64
+    tmem_ld_wait();
+    if (valid) {
+      float o[32];
+      uint32_t pk[16];
+      if (rope) {
+        float c[32], sn[32];
+        ld_bf16x32(cos_row + q * 32, c);
+        ld_bf16x32(sin_row + 64 + q * 32, sn);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = mul * (__uint_as_float(lo[j]) * c[j] + __uint_as_float(hi[j]) * sn[j]);
+        pack32(o, pk);
+        st_packed32(dst + q * 32, pk);
+        ld_bf16x32(cos_row + 64 + q * 32, c);
+        ld_bf16x32(sin_row + q * 32, sn);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = mul * (__uint_as_float(hi[j]) * c[j] - __uint_as_float(lo[j]) * sn[j]);
+        pack32(o, pk);
+        st_packed32(dst + 64 + q * 32, pk);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = mul * __uint_as_float(lo[j]);
+        pack32(o, pk);
+        st_packed32(dst + q * 32, pk);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = mul * __uint_as_float(hi[j]);
+        pack32(o, pk);
+        st_packed32(dst + 64 + q * 32, pk);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// =============================================================================================
+// dK, dV
+// =============================================================================================
+struct BarsA {
+  uint64_t kv_full, q_full[2], q_empty[2], s_full[2], p_full[2], p_empty[2], acc_full;
+  uint32_t tmem_base;
+};
+constexpr int ABA_SMEM = 2 * AB_T128 + 4 * AB_T64 + 4 * AB_P + 2 * 128 * 4 + 256 + 1024;
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+    k9_attn_bwd_dkdv(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_constant__ CUtensorMap tm_qkv64,
+                     const __grid_constant__ CUtensorMap tm_do64, const BwdParams p) {
+  const int b = blockIdx.z, h = blockIdx.y, jb = blockIdx.x;
+  const int seq0 = p.cu_seqlens[b], len = p.cu_seqlens[b + 1] - seq0;
+  const int kv0 = jb * 128;
+  if (kv0 >= len) return;
+  const int i0 = 2 * jb;                        // first 64-query step touching this key block
+  const int n_steps = (len + 63) / 64 - i0;     // >= 1
+  const int H = p.heads * 128;
+
+  extern __shared__ uint8_t ab_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ab_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + AB_T128;
+  uint8_t* sQ = smem + 2 * AB_T128;              // 2 stages of AB_T64
+  uint8_t* sdO = sQ + 2 * AB_T64;                // 2 stages
+  uint8_t* sP = sdO + 2 * AB_T64;                // 2 stages of AB_P
+  uint8_t* sdS = sP + 2 * AB_P;                  // 2 stages
+  float* sStat = reinterpret_cast<float*>(sdS + 2 * AB_P);  // [2][128]: lse (64) | delta (64) of the step's queries
+  BarsA* bars = reinterpret_cast<BarsA*>(sStat + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars->kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->q_full[i], 1);
+      mbar_init(&bars->q_empty[i], 1);
+      mbar_init(&bars->s_full[i], 1);
+      mbar_init(&bars->p_full[i], 4);
+      mbar_init(&bars->p_empty[i], 1);
+    }
+    mbar_init(&bars->acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv128);
+    tma_prefetch_desc(&tm_qkv64);
+    tma_prefetch_desc(&tm_do64);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 384;
+
+  if (warp == 0 && lane == 0) {
+    // =============================== TMA producer ===============================
+    const int colq = h * 128, colk = H + h * 128, colv = 2 * H + h * 128;
+    mbar_arrive_expect_tx(&bars->kv_full, 2 * AB_T128);
+    tma_load_2d(sK, &tm_qkv128, &bars->kv_full, colk, seq0 + kv0);
+    tma_load_2d(sK + AB_T128 / 2, &tm_qkv128, &bars->kv_full, colk + 64, seq0 + kv0);
+    tma_load_2d(sV, &tm_qkv128, &bars->kv_full, colv, seq0 + kv0);
+    tma_load_2d(sV + AB_T128 / 2, &tm_qkv128, &bars->kv_full, colv + 64, seq0 + kv0);
+    for (int s = 0; s < n_steps; ++s) {
+      const int st = s & 1;
+      const uint32_t ph = (s >> 1) & 1;
+      const int row = seq0 + (i0 + s) * 64;
+      mbar_wait(&bars->q_empty[st], ph ^ 1);
+      mbar_arrive_expect_tx(&bars->q_full[st], 2 * AB_T64);
+      tma_load_2d(sQ + st * AB_T64, &tm_qkv64, &bars->q_full[st], colq, row);
+      tma_load_2d(sQ + st * AB_T64 + AB_T64 / 2, &tm_qkv64, &bars->q_full[st], colq + 64, row);
+      tma_load_2d(sdO + st * AB_T64, &tm_do64, &bars->q_full[st], colq, row);
+      tma_load_2d(sdO + st * AB_T64 + AB_T64 / 2, &tm_do64, &bars->q_full[st], colq + 64, row);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // =============================== MMA issuer ===============================
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idesc_acc = umma_idesc_bf16(128, 128, 0, 1);  // B MN-major
+    const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
+    auto issue_s = [&](int s) {
+      const int st = s & 1;
+      mbar_wait(&bars->q_full[st], (s >> 1) & 1);
+      tc_fence_after();
+      const uint32_t aQ = smem_u32(sQ + st * AB_T64), adO = smem_u32(sdO + st * AB_T64);
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk)  // d = 128 in K = 16 steps
+        umma_ss(tS + st * 64, umma_desc_kmajor_sw128(aK + (kk >> 2) * (AB_T128 / 2) + (kk & 3) * 32),
+                umma_desc_kmajor_sw128(aQ + (kk >> 2) * (AB_T64 / 2) + (kk & 3) * 32), idesc_s, kk > 0);
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk)
+        umma_ss(tdP + st * 64, umma_desc_kmajor_sw128(aV + (kk >> 2) * (AB_T128 / 2) + (kk & 3) * 32),
+                umma_desc_kmajor_sw128(adO + (kk >> 2) * (AB_T64 / 2) + (kk & 3) * 32), idesc_s, kk > 0);
+      umma_commit(&bars->s_full[st]);
+    };
+    mbar_wait(&bars->kv_full, 0);
+    issue_s(0);
+    for (int s = 0; s < n_steps; ++s) {
+      if (s + 1 < n_steps) issue_s(s + 1);
+      const int st = s & 1;
+      mbar_wait(&bars->p_full[st], (s >> 1) & 1);
+      tc_fence_after();
+      const uint32_t aQ = smem_u32(sQ + st * AB_T64), adO = smem_u32(sdO + st * AB_T64);
+      const uint32_t aP = smem_u32(sP + st * AB_P), adS = smem_u32(sdS + st * AB_P);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)  // 64 queries in K = 16 steps
+        umma_ss(tdV, umma_desc_kmajor_sw128(aP + kk * 32), umma_desc_mnmajor_sw128(adO + kk * 2048, AB_T64 / 2, 1024),
+                idesc_acc, (s > 0) || (kk > 0));
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        umma_ss(tdK, umma_desc_kmajor_sw128(adS + kk * 32), umma_desc_mnmajor_sw128(aQ + kk * 2048, AB_T64 / 2, 1024),
+                idesc_acc, (s > 0) || (kk > 0));
+      umma_commit(&bars->q_empty[st]);
+      umma_commit(&bars->p_empty[st]);
+    }
+    umma_commit(&bars->acc_full);
+  } else if (warp >= 4) {
+    // =============================== softmax threads: one KEY row each ===============================
+    const int ew = warp - 4;
+    const int c = ew * 32 + lane;  // key row inside the block == TMEM lane
+    const uint32_t lane_sel = static_cast<uint32_t>(ew * 32) << 16;
+    const int kv_idx = kv0 + c;
+    const float* lse_h = p.lse + static_cast<int64_t>(h) * p.rows_cap;
+    const float* delta_h = p.delta + static_cast<int64_t>(h) * p.rows_cap;
+    for (int s = 0; s < n_steps; ++s) {
+      const int st = s & 1;
+      const uint32_t ph = (s >> 1) & 1;
+      const int q_base = (i0 + s) * 64;
+      {  // stage lse (threads 0..63) and delta (threads 64..127) of the step's 64 queries
+        const int qi = q_base + (c & 63);
+        float v = 0.f;
+        if (qi < len) v = (c < 64 ? lse_h : delta_h)[seq0 + qi];
+        sStat[st * 128 + c] = v;
+      }
+      named_bar_sync(1, 128);
+      mbar_wait(&bars->s_full[st], ph);
+      tc_fence_after();
+      mbar_wait(&bars->p_empty[st], ph ^ 1);  // the MMAs of step s - 2 have finished reading this P / dS buffer
+      const uint32_t aP = smem_u32(sP + st * AB_P), adS = smem_u32(sdS + st * AB_P);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t sraw[32], draw[32];
+        tmem_ld_32x32b_x32(tS + lane_sel + st * 64 + half * 32, sraw);
+        tmem_ld_32x32b_x32(tdP + lane_sel + st * 64 + half * 32, draw);
+        tmem_ld_wait();
+        float pv[32], dsv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = half * 32 + j;
+          const int q_idx = q_base + col;
+          const bool keep = (q_idx >= kv_idx) && (q_idx < len);
+          const float l2 = sStat[st * 128 + col], dl = sStat[st * 128 + 64 + col];
+          const float pr = keep ? exp2f(fmaf(__uint_as_float(sraw[j]), p.scale_log2, -l2)) : 0.f;
+          pv[j] = pr;
+          dsv[j] = keep ? pr * (__uint_as_float(draw[j]) - dl) : 0.f;
+        }
+        uint32_t pk[16];
+        pack32(pv, pk);
+        store_row_half(aP, c, half, pk);
+        pack32(dsv, pk);
+        store_row_half(adS, c, half, pk);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->p_full[st]);
+    }
+    // ---- epilogue: dV (plain), dK (scale, rotary transpose) -> dqkv[token_to_sorted[tok]] ----
+    mbar_wait(&bars->acc_full, 0);
+    tc_fence_after();
+    const bool valid = kv_idx < len;
+    const int tok = seq0 + kv_idx;
+    int dst = 0, pos = 0;
+    if (valid) {
+      dst = p.token_to_sorted ? p.token_to_sorted[tok] : tok;
+      const int64_t pz = p.position_ids[p.token_to_flat ? p.token_to_flat[tok] : tok];
+      pos = static_cast<int>(min(max(pz, int64_t(0)), int64_t(p.rope_len - 1)));
+    }
+    __nv_bfloat16* row = p.dqkv + static_cast<int64_t>(dst) * (3 * H) + h * 128;
+    store_grad_row(tdV + lane_sel, false, nullptr, nullptr, 1.0f, row + 2 * H, valid);
+    store_grad_row(tdK + lane_sel, true, p.rope_cos + static_cast<int64_t>(pos) * 128,
+                   p.rope_sin + static_cast<int64_t>(pos) * 128, p.scale, row + H, valid);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// =============================================================================================
+// dQ
+// =============================================================================================
+struct BarsB {
+  uint64_t q_full, kv_full[2], kv_empty[2], s_full[2], p_full[2], p_empty[2], acc_full;
+  uint32_t tmem_base;
+};
+constexpr int ABB_SMEM = 2 * AB_T128 + 4 * AB_T64 + 2 * AB_P + 256 + 1024;
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+    k9_attn_bwd_dq(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_constant__ CUtensorMap tm_qkv64,
+                   const __grid_constant__ CUtensorMap tm_do128, const BwdParams p) {
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int seq0 = p.cu_seqlens[b], len = p.cu_seqlens[b + 1] - seq0;
+  const int qb = gridDim.x - 1 - blockIdx.x;  // heaviest query blocks first
+  const int q0 = qb * 128;
+  if (q0 >= len) return;
+  const int n_steps = min((len + 63) / 64, 2 * qb + 2);  // 64-key steps at or below the diagonal
+  const int H = p.heads * 128;
+
+  extern __shared__ uint8_t ab_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ab_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sdO = smem + AB_T128;
+  uint8_t* sK = smem + 2 * AB_T128;  // 2 stages of AB_T64
+  uint8_t* sV = sK + 2 * AB_T64;     // 2 stages
+  uint8_t* sdS = sV + 2 * AB_T64;    // 2 stages of AB_P
+  BarsB* bars = reinterpret_cast<BarsB*>(sdS + 2 * AB_P);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars->q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->kv_full[i], 1);
+      mbar_init(&bars->kv_empty[i], 1);
+      mbar_init(&bars->s_full[i], 1);
+      mbar_init(&bars->p_full[i], 4);
+      mbar_init(&bars->p_empty[i], 1);
+    }
+    mbar_init(&bars->acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv128);
+    tma_prefetch_desc(&tm_qkv64);
+    tma_prefetch_desc(&tm_do128);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256;
+
+  if (warp == 0 && lane == 0) {
+    // =============================== TMA producer ===============================
+    const int colq = h * 128, colk = H + h * 128, colv = 2 * H + h * 128;
+    mbar_arrive_expect_tx(&bars->q_full, 2 * AB_T128);
+    tma_load_2d(sQ, &tm_qkv128, &bars->q_full, colq, seq0 + q0);
+    tma_load_2d(sQ + AB_T128 / 2, &tm_qkv128, &bars->q_full, colq + 64, seq0 + q0);
+    tma_load_2d(sdO, &tm_do128, &bars->q_full, colq, seq0 + q0);
+    tma_load_2d(sdO + AB_T128 / 2, &tm_do128, &bars->q_full, colq + 64, seq0 + q0);
+    for (int s = 0; s < n_steps; ++s) {
+      const int st = s & 1;
+      const uint32_t ph = (s >> 1) & 1;
+      const int row = seq0 + s * 64;
+      mbar_wait(&bars->kv_empty[st], ph ^ 1);
+      mbar_arrive_expect_tx(&bars->kv_full[st], 2 * AB_T64);
+      tma_load_2d(sK + st * AB_T64, &tm_qkv64, &bars->kv_full[st], colk, row);
+      tma_load_2d(sK + st * AB_T64 + AB_T64 / 2, &tm_qkv64, &bars->kv_full[st], colk + 64, row);
+      tma_load_2d(sV + st * AB_T64, &tm_qkv64, &bars->kv_full[st], colv, row);
+      tma_load_2d(sV + st * AB_T64 + AB_T64 / 2, &tm_qkv64, &bars->kv_full[st], colv + 64, row);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // =============================== MMA issuer ===============================
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idesc_acc = umma_idesc_bf16(128, 128, 0, 1);
+    const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO);
+    auto issue_s = [&](int s) {
+      const int st = s & 1;
+      mbar_wait(&bars->kv_full[st], (s >> 1) & 1);
+      tc_fence_after();
+      const uint32_t aK = smem_u32(sK + st * AB_T64), aV = smem_u32(sV + st * AB_T64);
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk)
+        umma_ss(tS + st * 64, umma_desc_kmajor_sw128(aQ + (kk >> 2) * (AB_T128 / 2) + (kk & 3) * 32),
+                umma_desc_kmajor_sw128(aK + (kk >> 2) * (AB_T64 / 2) + (kk & 3) * 32), idesc_s, kk > 0);
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk)
+        umma_ss(tdP + st * 64, umma_desc_kmajor_sw128(adO + (kk >> 2) * (AB_T128 / 2) + (kk & 3) * 32),
+                umma_desc_kmajor_sw128(aV + (kk >> 2) * (AB_T64 / 2) + (kk & 3) * 32), idesc_s, kk > 0);
+      umma_commit(&bars->s_full[st]);
+    };
+    mbar_wait(&bars->q_full, 0);
+    issue_s(0);
+    for (int s = 0; s < n_steps; ++s) {
+      if (s + 1 < n_steps) issue_s(s + 1);
+      const int st = s & 1;
+      mbar_wait(&bars->p_full[st], (s >> 1) & 1);
+      tc_fence_after();
+      const uint32_t aK = smem_u32(sK + st * AB_T64), adS = smem_u32(sdS + st * AB_P);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)  // 64 keys in K = 16 steps
+        umma_ss(tdQ, umma_desc_kmajor_sw128(adS + kk * 32), umma_desc_mnmajor_sw128(aK + kk * 2048, AB_T64 / 2, 1024),
+                idesc_acc, (s > 0) || (kk > 0));
+      umma_commit(&bars->kv_empty[st]);
+      umma_commit(&bars->p_empty[st]);
+    }
+    umma_commit(&bars->acc_full);
+  } else if (warp >= 4) {
+    // =============================== softmax threads: one QUERY row each ===============================
+    const int ew = warp - 4;
+    const int c = ew * 32 + lane;
+    const uint32_t lane_sel = static_cast<uint32_t>(ew * 32) << 16;
+    const int q_idx = q0 + c;
+    const bool valid = q_idx < len;
+    const int tok = seq0 + q_idx;
+    float l2 = 0.f, dl = 0.f;
+    if (valid) {
+      l2 = p.lse[static_cast<int64_t>(h) * p.rows_cap + tok];
+      dl = p.delta[static_cast<int64_t>(h) * p.rows_cap + tok];
+    }
+    for (int s = 0; s < n_steps; ++s) {
+      const int st = s & 1;
+      const uint32_t ph = (s >> 1) & 1;
+      mbar_wait(&bars->s_full[st], ph);
+      tc_fence_after();
+      mbar_wait(&bars->p_empty[st], ph ^ 1);
+      const uint32_t adS = smem_u32(sdS + st * AB_P);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t sraw[32], draw[32];
+        tmem_ld_32x32b_x32(tS + lane_sel + st * 64 + half * 32, sraw);
+        tmem_ld_32x32b_x32(tdP + lane_sel + st * 64 + half * 32, draw);
+        tmem_ld_wait();
+        float dsv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int kv_idx = s * 64 + half * 32 + j;
+          const bool keep = valid && (kv_idx <= q_idx);
+          const float pr = keep ? exp2f(fmaf(__uint_as_float(sraw[j]), p.scale_log2, -l2)) : 0.f;
+          dsv[j] = keep ? pr * (__uint_as_float(draw[j]) - dl) : 0.f;
+        }
+        uint32_t pk[16];
+        pack32(dsv, pk);
+        store_row_half(adS, c, half, pk);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->p_full[st]);
+    }
+    // ---- epilogue: dQ * scale through the rotary transpose -> dqkv[token_to_sorted[tok]] ----
+    mbar_wait(&bars->acc_full, 0);
+    tc_fence_after();
+    int dst = 0, pos = 0;
+    if (valid) {
+      dst = p.token_to_sorted ? p.token_to_sorted[tok] : tok;
+      const int64_t pz = p.position_ids[p.token_to_flat ? p.token_to_flat[tok] : tok];
+      pos = static_cast<int>(min(max(pz, int64_t(0)), int64_t(p.rope_len - 1)));
+    }
+    store_grad_row(tdQ + lane_sel, true, p.rope_cos + static_cast<int64_t>(pos) * 128,
+                   p.rope_sin + static_cast<int64_t>(pos) * 128, p.scale,
+                   p.dqkv + static_cast<int64_t>(dst) * (3 * H) + h * 128, valid);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace vex
+
+extern "C" int vex_attention_backward(const void* qkv, const void* out_sorted, void* d_out_tok, const float* lse,
+                                      float* delta_ws, const int32_t* cu_seqlens, const int32_t* token_to_sorted,
+                                      const int32_t* token_to_flat, const int64_t* position_ids, const void* rope_cos,
+                                      const void* rope_sin, int rope_len, int B, int max_len_cap, int heads, void* dqkv,
+                                      float scale, vexStream stream) {
+  using namespace vex;
+  if (!qkv || !out_sorted || !d_out_tok || !lse || !delta_ws || !cu_seqlens || !position_ids || !rope_cos ||
+      !rope_sin || !dqkv || B <= 0 || max_len_cap <= 0 || heads <= 0 || rope_len <= 0)
+    return VEX_E_INVALID;
+  if (B > 65535 || heads > 65535) return VEX_E_UNSUPPORTED;
+  const int64_t rows_cap64 = static_cast<int64_t>(B) * max_len_cap;
+  if (rows_cap64 > 0x7fffffff) return VEX_E_UNSUPPORTED;
+  const int rows_cap = static_cast<int>(rows_cap64);
+  const uint64_t H = static_cast<uint64_t>(heads) * 128;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  static bool configured = false;
+  if (!configured) {
+    VEX_CUDA_TRY(cudaFuncSetAttribute(k9_attn_bwd_dkdv, cudaFuncAttributeMaxDynamicSharedMemorySize, ABA_SMEM));
+    VEX_CUDA_TRY(cudaFuncSetAttribute(k9_attn_bwd_dq, cudaFuncAttributeMaxDynamicSharedMemorySize, ABB_SMEM));
+    configured = true;
+  }
+  CUtensorMap tm_qkv128, tm_qkv64, tm_do128, tm_do64;
+  int rc;
+  if ((rc = make_tmap_2d(&tm_qkv128, qkv, rows_cap, 3 * H, 3 * H, 128)) != VEX_OK) return rc;
+  if ((rc = make_tmap_2d(&tm_qkv64, qkv, rows_cap, 3 * H, 3 * H, 64)) != VEX_OK) return rc;
+  if ((rc = make_tmap_2d(&tm_do128, d_out_tok, rows_cap, H, H, 128)) != VEX_OK) return rc;
+  if ((rc = make_tmap_2d(&tm_do64, d_out_tok, rows_cap, H, H, 64)) != VEX_OK) return rc;
+  // rows [T, T + 128) of dO can be touched by the last tile: keep them finite (0 * NaN = NaN in the MMAs)
+  k9_zero_tail_rows<<<32, 256, 0, s>>>(static_cast<__nv_bfloat16*>(d_out_tok), cu_seqlens, B, rows_cap,
+                                       static_cast<int>(H));
+  VEX_LAUNCH_CHECK();
+  k9_attn_delta<<<std::min(ceil_div(rows_cap, 8), 148 * 8), 256, 0, s>>>(
+      static_cast<const __nv_bfloat16*>(d_out_tok), static_cast<const __nv_bfloat16*>(out_sorted), token_to_sorted,
+      cu_seqlens, B, delta_ws, heads, rows_cap);
+  VEX_LAUNCH_CHECK();
+  BwdParams p;
+  p.cu_seqlens = cu_seqlens;
+  p.lse = lse;
+  p.delta = delta_ws;
+  p.token_to_sorted = token_to_sorted;
+  p.token_to_flat = token_to_flat;
+  p.position_ids = position_ids;
+  p.rope_cos = static_cast<const __nv_bfloat16*>(rope_cos);
+  p.rope_sin = static_cast<const __nv_bfloat16*>(rope_sin);
+  p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  p.heads = heads;
+  p.rows_cap = rows_cap;
+  p.rope_len = rope_len;
+  p.scale = scale;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid(ceil_div(max_len_cap, 128), heads, B);
+  k9_attn_bwd_dkdv<<<grid, AB_THREADS, ABA_SMEM, s>>>(tm_qkv128, tm_qkv64, tm_do64, p);
+  VEX_LAUNCH_CHECK();
+  k9_attn_bwd_dq<<<grid, AB_THREADS, ABB_SMEM, s>>>(tm_qkv128, tm_qkv64, tm_do128, p);
+  VEX_LAUNCH_CHECK();
+  return VEX_OK;
+}

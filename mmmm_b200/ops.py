@@ -252,11 +252,7 @@ def grouped_gemm_dgrad(dy: torch.Tensor, w: List[Optional[torch.Tensor]], out: t
 
 
 # ------------------------------------------------------------------------------------------ K4
-@torch.library.custom_op("vex::attention", mutates_args=("out",))
-def attention(qkv: torch.Tensor, cu_seqlens: torch.Tensor, batch: int, max_len_cap: int, heads: int,
-              out_row_map: Optional[torch.Tensor], out: torch.Tensor, scale: float) -> None:
-    """K4 (vex_attention): causal block-diagonal attention over token-order QKV [T, 3, heads, 128]
-    (attention_fn prefill branch, modeling_cogvlm.py:106-128)."""
+def _attention_impl(qkv, cu_seqlens, batch, max_len_cap, heads, out_row_map, out, scale, lse):
     _dev(qkv, "qkv", _BF16)
     _dev(out, "out", _BF16)
     _dev(cu_seqlens, "cu_seqlens", torch.int32)
@@ -264,10 +260,62 @@ def attention(qkv: torch.Tensor, cu_seqlens: torch.Tensor, batch: int, max_len_c
         raise ValueError("qkv rows must be [3 * heads * 128] wide (head_dim 128 only)")
     if out_row_map is not None:
         _dev(out_row_map, "out_row_map", torch.int32)
+    if lse is not None:
+        _dev(lse, "lse", torch.float32)
+        if lse.numel() < heads * batch * max_len_cap:
+            raise ValueError("lse must hold heads * B * max_len_cap floats")
     with instrument.region("attention", 2):  # tail-row zeroing + the attention kernel
-      rc = _lib.lib().vex_attention(qkv.data_ptr(), cu_seqlens.data_ptr(), batch, max_len_cap, heads,
-                                  _ptr(out_row_map), out.data_ptr(), float(scale), _stream())
+      rc = _lib.lib().vex_attention_lse(qkv.data_ptr(), cu_seqlens.data_ptr(), batch, max_len_cap, heads,
+                                      _ptr(out_row_map), out.data_ptr(), float(scale), _ptr(lse), _stream())
     _lib.check(rc, "vex_attention")
+
+
+@torch.library.custom_op("vex::attention", mutates_args=("out",))
+def attention(qkv: torch.Tensor, cu_seqlens: torch.Tensor, batch: int, max_len_cap: int, heads: int,
+              out_row_map: Optional[torch.Tensor], out: torch.Tensor, scale: float) -> None:
+    """K4 (vex_attention): causal block-diagonal attention over token-order QKV [T, 3, heads, 128]
+    (attention_fn prefill branch, modeling_cogvlm.py:106-128)."""
+    _attention_impl(qkv, cu_seqlens, batch, max_len_cap, heads, out_row_map, out, scale, None)
+
+
+@torch.library.custom_op("vex::attention_train", mutates_args=("out", "lse"))
+def attention_train(qkv: torch.Tensor, cu_seqlens: torch.Tensor, batch: int, max_len_cap: int, heads: int,
+                    out_row_map: Optional[torch.Tensor], out: torch.Tensor, scale: float, lse: torch.Tensor) -> None:
+    """K4 for the training step (vex_attention_lse): also writes the log2-domain log-sum-exp, fp32 [heads, B*L]."""
+    _attention_impl(qkv, cu_seqlens, batch, max_len_cap, heads, out_row_map, out, scale, lse)
+
+
+@torch.library.custom_op("vex::attention_backward", mutates_args=("d_out_tok", "delta_ws", "dqkv"))
+def attention_backward(qkv: torch.Tensor, out_sorted: torch.Tensor, d_out_tok: torch.Tensor, lse: torch.Tensor,
+                       delta_ws: torch.Tensor, cu_seqlens: torch.Tensor, token_to_sorted: Optional[torch.Tensor],
+                       token_to_flat: Optional[torch.Tensor], position_ids: torch.Tensor, cos: torch.Tensor,
+                       sin: torch.Tensor, batch: int, max_len_cap: int, heads: int, dqkv: torch.Tensor,
+                       scale: float) -> None:
+    """K9 (vex_attention_backward): adjoint of the causal varlen attention and of the rotary embedding
+    (modeling_cogvlm.py:106-128, :188-193 under autograd); ``dqkv`` receives d(pre-rotary q | k | v) in sorted order."""
+    for n, t in (("qkv", qkv), ("out_sorted", out_sorted), ("d_out_tok", d_out_tok), ("dqkv", dqkv), ("cos", cos),
+                 ("sin", sin)):
+        _dev(t, n, _BF16)
+    _dev(lse, "lse", torch.float32), _dev(delta_ws, "delta_ws", torch.float32)
+    _dev(cu_seqlens, "cu_seqlens", torch.int32), _dev(position_ids, "position_ids", torch.int64)
+    H = heads * 128
+    cap = batch * max_len_cap
+    if qkv.shape[-1] != 3 * H or dqkv.shape[-1] != 3 * H or out_sorted.shape[-1] != H or d_out_tok.shape[-1] != H:
+        raise ValueError("row widths must be 3*heads*128 (qkv, dqkv) and heads*128 (out, d_out)")
+    for n, t, w in (("qkv", qkv, 3 * H), ("dqkv", dqkv, 3 * H), ("out_sorted", out_sorted, H), ("d_out_tok", d_out_tok, H)):
+        if t.numel() < cap * w:
+            raise ValueError(f"{n} must have B * max_len_cap rows")
+    if lse.numel() < heads * cap or delta_ws.numel() < heads * cap:
+        raise ValueError("lse / delta_ws must hold heads * B * max_len_cap floats")
+    if cos.shape[-1] != 128 or cos.shape != sin.shape:
+        raise ValueError("rotary tables must be [S, 128]")
+    maps = [None if m is None else _dev(m, "row map", torch.int32) for m in (token_to_sorted, token_to_flat)]
+    with instrument.region("attention_backward", 4):
+      rc = _lib.lib().vex_attention_backward(qkv.data_ptr(), out_sorted.data_ptr(), d_out_tok.data_ptr(), lse.data_ptr(),
+                                             delta_ws.data_ptr(), cu_seqlens.data_ptr(), _ptr(maps[0]), _ptr(maps[1]),
+                                             position_ids.data_ptr(), cos.data_ptr(), sin.data_ptr(), cos.shape[0],
+                                             batch, max_len_cap, heads, dqkv.data_ptr(), float(scale), _stream())
+    _lib.check(rc, "vex_attention_backward")
 
 
 @torch.library.custom_op("vex::attention_decode", mutates_args=("out",))
@@ -368,6 +416,6 @@ def lora_wgrad(x: torch.Tensor, y: torch.Tensor, out_vision: Optional[torch.Tens
     _lib.check(rc, "vex_lora_wgrad")
 
 
-for _op in (lora_wgrad, gather_rows, silu_mul_backward, rmsnorm_backward, grouped_gemm_dgrad, attention_decode, partition, rmsnorm_gather, silu_mul, residual_scatter, copy_padded_rows, grouped_gemm, grouped_gemm_fused,
+for _op in (attention_train, attention_backward, lora_wgrad, gather_rows, silu_mul_backward, rmsnorm_backward, grouped_gemm_dgrad, attention_decode, partition, rmsnorm_gather, silu_mul, residual_scatter, copy_padded_rows, grouped_gemm, grouped_gemm_fused,
             attention):
     _op.register_fake(lambda *a, **k: None)

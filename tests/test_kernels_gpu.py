@@ -493,3 +493,67 @@ def test_k4_attention_vs_oracle(lens, impl, monkeypatch):
     ops.attention(qkv_buf.cuda(), cu.cuda(), B, Lmax, heads, rmap.cuda(), out, 128 ** -0.5)
     got = out.cpu()[rmap[:T].long()]
     torch.testing.assert_close(got.float(), tok(want).reshape(T, heads * 128).float(), rtol=2e-2, atol=2e-2)
+
+
+# ------------------------------------------------------------------------------------------ K9 (attention backward)
+@pytest.mark.parametrize("lens", [[1], [64], [65, 3, 128], [129, 128, 127], [300, 17, 1, 255], [700, 1485]])
+def test_k9_attention_backward_vs_autograd(lens):
+    """dq / dk / dv w.r.t. the PRE-rotary projections (attention + rotary adjoints fused, scattered to sorted order)
+    against torch.autograd over the oracle's apply_rotary + attention in fp32."""
+    ops = _ops()
+    heads = 3
+    H = heads * 128
+    B, Lmax = len(lens), max(lens)
+    T = sum(lens)
+    cap = B * Lmax
+    g = torch.Generator().manual_seed(sum(lens) + 1)
+    pm = torch.zeros(B, Lmax, dtype=torch.bool)
+    for b, n in enumerate(lens):
+        pm[b, :n] = True
+    pos = torch.randint(0, 300, (B, Lmax), generator=g)
+    cos, sin = O.rotary_tables(O.default_inv_freq(128).bfloat16(), 512)
+    q0, k0, v0 = [torch.randn(B, heads, Lmax, 128, generator=g).bfloat16() for _ in range(3)]
+    d_out = torch.randn(B, heads, Lmax, 128, generator=g).bfloat16()
+    # ---- reference: fp32 autograd on the GPU over the oracle functions
+    qa, ka, va = [t.cuda().float().requires_grad_(True) for t in (q0, k0, v0)]
+    qr, kr = O.apply_rotary(qa, ka, cos.cuda().float(), sin.cuda().float(), pos.cuda())
+    out_ref = O.attention(qr, kr, va, pm.cuda())
+    (out_ref * (d_out.cuda().float() * pm.cuda()[:, None, :, None])).sum().backward()
+    tok = lambda t: t.permute(0, 2, 1, 3)[pm.to(t.device)].reshape(T, H)        # [T, heads*128] token order
+    want = torch.cat([tok(qa.grad), tok(ka.grad), tok(va.grad)], dim=-1).cpu()
+    # ---- ours: forward (rotated q/k in bf16 like the QKV epilogue produces them) with lse, then backward
+    qr16, kr16 = O.apply_rotary(q0, k0, cos, sin, pos)
+    qkv = torch.full((cap + 0, 3 * H), float("nan"), dtype=torch.bfloat16)
+    qkv[:T] = torch.cat([tok(qr16), tok(kr16), tok(v0)], dim=-1)
+    cu = torch.zeros(B + 1, dtype=torch.int32)
+    cu[1:] = torch.tensor(lens).cumsum(0)
+    t2s = torch.randperm(cap, generator=g).int()                                 # arbitrary token -> sorted row map
+    t2f = torch.full((cap,), -1, dtype=torch.int32)
+    t2f[:T] = torch.nonzero(pm.reshape(-1))[:, 0].int()
+    qkv_c = qkv.cuda()
+    out_sorted = torch.zeros(cap, H, dtype=torch.bfloat16).cuda()
+    lse = torch.zeros(heads, cap, dtype=torch.float32).cuda()
+    ops.attention_train(qkv_c, cu.cuda(), B, Lmax, heads, t2s.cuda(), out_sorted, 128 ** -0.5, lse)
+    got_out = out_sorted.cpu()[t2s[:T].long()]
+    torch.testing.assert_close(got_out.float(), tok(out_ref.detach()).cpu(), rtol=2e-2, atol=2e-2)
+    d_tok = torch.full((cap, H), float("nan"), dtype=torch.bfloat16)            # tail rows are garbage
+    d_tok[:T] = tok(d_out)
+    dqkv = torch.zeros(cap, 3 * H, dtype=torch.bfloat16).cuda()
+    delta = torch.empty(heads, cap, dtype=torch.float32).cuda()
+    ops.attention_backward(qkv_c, out_sorted, d_tok.cuda(), lse, delta, cu.cuda(), t2s.cuda(), t2f.cuda(),
+                           pos.reshape(-1).cuda(), cos.cuda().contiguous(), sin.cuda().contiguous(), B, Lmax, heads,
+                           dqkv, 128 ** -0.5)
+    got = dqkv.cpu()[t2s[:T].long()].float()
+    # dq / dk vanish identically for single-token samples (dP == delta): floor the denominators with dv's scale
+    floor_max, floor_fro = 0.05 * float(want.abs().max()), 0.05 * float(want[:, 2 * H:].norm())
+    report = {}
+    for name, sl in (("dq", slice(0, H)), ("dk", slice(H, 2 * H)), ("dv", slice(2 * H, 3 * H))):
+        w, gt = want[:, sl], got[:, sl]
+        err = float((gt - w).abs().max() / max(float(w.abs().max()), floor_max))
+        fro = float((gt - w).norm() / max(float(w.norm()), floor_fro))
+        report[name] = (round(err, 4), round(fro, 4))
+    assert all(e <= 2e-2 and f <= 1.5e-2 for e, f in report.values()), report
+    # rows that belong to no token stay untouched
+    untouched = torch.ones(cap, dtype=torch.bool)
+    untouched[t2s[:T].long()] = False
+    assert (dqkv.cpu()[untouched] == 0).all()
