@@ -260,7 +260,8 @@ def visual_expert_layer_forward(layer: "CogVLMDecoderLayer", hidden_states: torc
                                 position_ids: torch.Tensor, *, use_cache: bool = False,
                                 fuse_epilogue: Optional[bool] = None, keep: Optional[dict] = None):
     """The whole layer on the device; returns (out [B, L, H], present_kv or None).  ``keep`` (training recompute):
-    a dict that receives the intermediates the backward needs (gate/up are then materialised separately)."""
+    a dict that receives the intermediates the backward needs (gate/up are then materialised separately, the
+    attention also writes its log-sum-exp, and the call returns (None, None) right before the down projection)."""
     fuse = _fuse_default() if fuse_epilogue is None else fuse_epilogue
     attn, mlp = layer.self_attn, layer.mlp
     B, L, H = hidden_states.shape
@@ -293,7 +294,11 @@ def visual_expert_layer_forward(layer: "CogVLMDecoderLayer", hidden_states: torc
     ops.grouped_gemm_fused(keep["xn1"] if keep is not None else xn, W(qkv_s), qkv, counts, ops.EPI_ROPE, plan.sorted_to_token, None, [t, None],
                            [lb[0], None, lb[1], None], r, [cos, sin, pos_flat, s2f], 2 * H, False, 1.0)
     ctx = new(cap, H)      # expert-sorted order again: the A operand of the dense GEMM
-    ops.attention(qkv, plan.cu_seqlens, B, L, heads, plan.token_to_sorted, ctx, HEAD_DIM ** -0.5)
+    if keep is not None:   # training recompute: the backward kernels need the log-sum-exp
+        keep["lse"] = torch.empty(heads, cap, dtype=torch.float32, device=dev)
+        ops.attention_train(qkv, plan.cu_seqlens, B, L, heads, plan.token_to_sorted, ctx, HEAD_DIM ** -0.5, keep["lse"])
+    else:
+        ops.attention(qkv, plan.cu_seqlens, B, L, heads, plan.token_to_sorted, ctx, HEAD_DIM ** -0.5)
     h1 = new(B, L, H)
     ops.copy_padded_rows(hf, plan.flat_to_sorted, h1.view(cap, H))
     t, r, lb = _lora_t(ctx, dense_s, counts)
@@ -331,8 +336,9 @@ def visual_expert_layer_forward(layer: "CogVLMDecoderLayer", hidden_states: torc
         if keep is not None:
             keep.update(gate=g, up=u)
     t, r, lb = _lora_t(act, down_s, counts)
-    if keep is not None:
-        keep.update(act=act, t_down=t, h1=h1.clone())  # h1 is overwritten in place by the down projection below
+    if keep is not None:  # the recompute stops here: the down projection's output is not needed by the backward
+        keep.update(act=act, t_down=t, h1=h1)
+        return None, None
     if fuse:  # in place: h1[row] += down(act)[row]; padded rows of h1 already hold the input
         ops.grouped_gemm_fused(act, W(down_s), h1.view(cap, H), counts, ops.EPI_RESIDUAL, s2f, None, [t, None],
                                [lb[0], None, lb[1], None], r, [], 0, False, 1.0)

@@ -2,152 +2,132 @@
 
 Forward = the fused sm_100a path (``visual_expert_layer_forward``).  The layer checkpoints itself the way the
 reference trains (non-reentrant gradient checkpointing is always on, mmmm/models/mmmm.py:287-291): only the
-layer input is saved; the backward re-runs the native forward keeping the intermediates, then propagates
+layer input is saved; the backward re-runs the native forward up to the down projection keeping the
+intermediates, then propagates with the native backward kernels
 
-    d_out -> down_proj (+LoRA) -> SwiGLU -> gate/up (+LoRA) -> RMSNorm -> dense (+LoRA) -> attention -> rotary
-          -> QKV (+LoRA) -> RMSNorm -> d_hidden
+    d_out -> gather to sorted rows (K7) -> down_proj dgrad (+LoRA) [K3, MN-major B] -> SwiGLU backward (K7)
+          -> gate/up dgrad (+LoRA, accumulated) -> RMSNorm backward + residual add (K7) -> dense dgrad (+LoRA,
+          scattered to token order) -> attention backward + rotary adjoint (K9) -> QKV dgrad (+LoRA)
+          -> RMSNorm backward + residual add, scattered to [B, L] (K7)
 
-Gradients are produced for the layer input, every active ``lora_A`` / ``lora_B`` and the (modules_to_save) RMSNorm
-weights; the base Linear weights are frozen, as under PEFT.
+and the ten LoRA weight gradients with K8 (tcgen05, reduction over tokens).  Gradients are produced for the layer
+input, every active ``lora_A`` / ``lora_B`` and the (modules_to_save) RMSNorm weights; the base Linear weights are
+frozen, as under PEFT.  No host synchronisation anywhere: expert row counts stay on the device.
 
-STATUS (round 1): the backward ARITHMETIC below is an interim implementation with PyTorch device ops (cuBLAS
-matmuls, SDPA attention backward) over the expert-sorted buffers the native forward produces -- it reads the
-two expert row counts on the host (one sync per layer backward).  It fixes the autograd contract, the gradient
-parity tests and the LoRA-gradient all-reduce plumbing; the native dgrad / wgrad / attention-backward kernels
-replace these ops one by one.  The forward path never uses any of this.
+What autograd would do on the reference is restated here per op; ``tests/test_layer_gpu.py`` checks every gradient
+against torch.autograd over the oracle layer.
 """
 from __future__ import annotations
 
 from typing import Dict, List, Optional, Tuple
 
 import torch
-import torch.nn.functional as F
 
+from . import ops
 from .peft_compat import LinearSpec
 
 HEAD_DIM = 128
 
 
-# --------------------------------------------------------------------------------------------------
-# pieces of the backward (row-wise formulas over expert-sorted rows)
-# --------------------------------------------------------------------------------------------------
-def _rmsnorm_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, eps: float):
-    """y = w * (x * rsqrt(mean(x^2) + eps)); returns (dx, dw) in fp32 math."""
-    xf, dyf, wf = x.float(), dy.float(), w.float()
-    inv = torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
-    xhat = xf * inv
-    dyw = dyf * wf
-    dx = inv * (dyw - xhat * (dyw * xhat).mean(-1, keepdim=True))
-    dw = (dyf * xhat).sum(0)
-    return dx.to(x.dtype), dw
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    from .modeling_cogvlm import _bf16 as cast
+    return cast(t)
 
 
-def _linear_bwd(dy: torch.Tensor, x: torch.Tensor, t: Optional[torch.Tensor], spec: LinearSpec):
-    """y = x W^T + (s x A^T) B^T, T = s x A^T (bf16, as the forward produced it).
-    Returns dx, (dA, dB) or None."""
-    dx = dy @ spec.weight.detach()
-    grads = None
-    if spec.lora_A is not None:
-        A, Bm, s = spec.lora_A.detach().to(dy.dtype), spec.lora_B.detach().to(dy.dtype), spec.scaling
-        dT = dy @ Bm                                    # [n, r]
-        dB = dy.float().t() @ t.float()                 # [out, r]   (T already carries the scaling)
-        dA = (dT.float().t() @ x.float()) * s           # [r, in]
-        dx = dx + (dT @ A) * s
-        grads = (dA, dB)
-    return dx, grads
+class _GradSink:
+    """fp32 accumulators for the trainable tensors of one layer backward (K8 / K7 add into them atomically)."""
+
+    def __init__(self):
+        self.items: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
+
+    def buffer(self, p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        if p is None or not p.requires_grad:
+            return None
+        if id(p) not in self.items:
+            self.items[id(p)] = (p, torch.zeros(p.shape, dtype=torch.float32, device=p.device))
+        return self.items[id(p)][1]
+
+    def result(self):
+        return [(p, g if g.dtype == p.dtype else g.to(p.dtype)) for p, g in self.items.values()]
 
 
-def _rotate_half_t(z: torch.Tensor) -> torch.Tensor:
-    """Transpose of rotate_half: R(x) = cat(-x2, x1)  =>  R^T(z) = cat(z2, -z1)."""
-    half = z.shape[-1] // 2
-    return torch.cat((z[..., half:], -z[..., :half]), dim=-1)
+def _routed_linear_backward(dy: torch.Tensor, x: torch.Tensor, t: Optional[torch.Tensor],
+                            pair: Tuple[LinearSpec, LinearSpec], counts: torch.Tensor, out: torch.Tensor,
+                            sink: _GradSink, *, accumulate: bool = False, row_map: Optional[torch.Tensor] = None):
+    """Backward of the routed (vision / language) Linear + LoRA: y = x W_e^T + T B_e^T with T = s x A_e^T.
+        dx = dy W_e + dT A_e   (dT = s dy B_e)        dB_e = dy^T T        dA_e = dT^T x
+    ``dy`` / ``x`` / ``t`` are expert-sorted [cap, *]; ``out`` receives dx (through ``row_map`` / accumulated)."""
+    sv, sl = pair
+    both = sl.lora_A is not None
+    dt, r, lora_a = None, 0, [None, None]
+    if sv.lora_A is not None:
+        r = sv.r
+        dt = torch.empty(dy.shape[0], r, dtype=torch.bfloat16, device=dy.device)
+        # dT = s * dy . B  (B stored [out, r]: the small-N transposed GEMM; language rows stay unused without an adapter)
+        ops.grouped_gemm_dgrad(dy, [_bf16(sv.lora_B), _bf16(sl.lora_B) if both else None], dt, counts, False, None, None,
+                               [None, None], 0, not both, float(sv.scaling))
+        lora_a = [_bf16(sv.lora_A), _bf16(sl.lora_A) if both else None]
+        gB = (sink.buffer(sv.lora_B), sink.buffer(sl.lora_B) if both else None)
+        gA = (sink.buffer(sv.lora_A), sink.buffer(sl.lora_A) if both else None)
+        if gB[0] is not None or gB[1] is not None:
+            ops.lora_wgrad(dy, t, gB[0], gB[1], False, counts)
+        if gA[0] is not None or gA[1] is not None:
+            ops.lora_wgrad(x, dt, gA[0], gA[1], True, counts)
+    ops.grouped_gemm_dgrad(dy, [_bf16(sv.weight), _bf16(sl.weight)], out, counts, accumulate, row_map, dt, lora_a, r,
+                           False, 1.0)
 
 
 def layer_backward(layer, plan, position_ids: torch.Tensor, hidden_states: torch.Tensor, d_out: torch.Tensor):
-    """Returns (d_hidden [B, L, H], {param tensor id -> grad}) -- see the module docstring."""
+    """Returns (d_hidden [B, L, H], [(param, grad), ...]) -- see the module docstring."""
     from .modeling_cogvlm import visual_expert_layer_forward
     B, L, H = hidden_states.shape
     cap = B * L
-    attn = layer.self_attn
+    attn, mlp = layer.self_attn, layer.mlp
     heads = attn.num_heads
+    I = mlp.vision_mlp.intermediate_size
+    dev = hidden_states.device
     keep: Dict = {}
     with torch.no_grad():
         visual_expert_layer_forward(layer, hidden_states, plan, position_ids, keep=keep)
-    Tv, Tl = plan.counts[:2].tolist()   # interim: host sync (the native kernels read the counts on the device)
-    T = Tv + Tl
-    seg = ((0, Tv), (Tv, T))
-    s2f = plan.sorted_to_flat[:T].long()
-    s2t = plan.sorted_to_token[:T].long()
     specs = keep["specs"]
-    grads: Dict[int, torch.Tensor] = {}
-    params: Dict[int, torch.Tensor] = {}
-
-    def add_grad(p: torch.Tensor, g: torch.Tensor):
-        if p.requires_grad:
-            params[id(p)] = p
-            grads[id(p)] = grads[id(p)] + g.to(p.dtype) if id(p) in grads else g.to(p.dtype)
-
-    def routed_linear_bwd(dy, x, t, pair):
-        dx = torch.empty(T, pair[0].weight.shape[1], dtype=dy.dtype, device=dy.device)
-        for (lo, hi), spec in zip(seg, pair):
-            if hi == lo:
-                continue
-            dxe, g = _linear_bwd(dy[lo:hi], x[lo:hi], None if t is None else t[lo:hi], spec)
-            dx[lo:hi] = dxe
-            if g is not None:
-                add_grad(spec.lora_A, g[0])
-                add_grad(spec.lora_B, g[1])
-        return dx
-
+    counts, s2f, n_valid = plan.counts, plan.sorted_to_flat, plan.n_valid
+    new = lambda *shape: torch.empty(*shape, dtype=torch.bfloat16, device=dev)
+    sink = _GradSink()
     hf = hidden_states.view(cap, H)
-    dof = d_out.reshape(cap, H)
-    dy = dof[s2f]                                                      # [T, H] sorted
+    dof = d_out.view(cap, H)
+
+    dy = new(cap, H)                                                   # d_out in expert-sorted order
+    ops.gather_rows(dof, s2f, n_valid, dy)
     # ---- MLP block ----
-    dact = routed_linear_bwd(dy, keep["act"][:T], keep["t_down"], specs["down"])
-    g, u = keep["gate"][:T].float(), keep["up"][:T].float()
-    sig = torch.sigmoid(g)
-    silu = (g * sig).to(dy.dtype).float()                              # forward rounds silu(g) to bf16
-    dactf = dact.float()
-    du = (dactf * silu).to(dy.dtype)
-    dg = (dactf * u * (sig * (1 + g * (1 - sig)))).to(dy.dtype)
-    xn2 = keep["xn2"][:T]
-    dxn2 = routed_linear_bwd(dg, xn2, keep["t_gate"], specs["gate"]) + \
-        routed_linear_bwd(du, xn2, keep["t_up"], specs["up"])
-    h1s = keep["h1"].view(cap, H)[s2f]
-    dx2, dw2 = _rmsnorm_bwd(dxn2, h1s, keep["ln2"].weight.detach(), keep["ln2"].variance_epsilon)
-    add_grad(keep["ln2"].weight, dw2)
-    dh1 = dy + dx2                                                     # grad w.r.t. h1 rows (sorted)
+    dact = new(cap, I)
+    _routed_linear_backward(dy, keep["act"], keep["t_down"], specs["down"], counts, dact, sink)
+    dg, du = new(cap, I), new(cap, I)
+    ops.silu_mul_backward(dact, keep["gate"], keep["up"], n_valid, dg, du)
+    del dact
+    dxn2 = new(cap, H)
+    _routed_linear_backward(dg, keep["xn2"], keep["t_gate"], specs["gate"], counts, dxn2, sink)
+    _routed_linear_backward(du, keep["xn2"], keep["t_up"], specs["up"], counts, dxn2, sink, accumulate=True)
+    del dg, du
+    ln1, ln2 = keep["ln1"], keep["ln2"]
+    dh1 = new(cap, H)                                                  # grad w.r.t. h1 rows (sorted): dy + norm branch
+    ops.rmsnorm_backward(dxn2, keep["h1"].view(cap, H), s2f, ln2.weight.detach(), ln2.variance_epsilon, dy, None, dh1,
+                         None, sink.buffer(ln2.weight), n_valid)
     # ---- attention block ----
-    dctx = routed_linear_bwd(dh1, keep["ctx"][:T], keep["t_dense"], specs["dense"])
-    qkv = keep["qkv"][:T].view(T, 3, heads, HEAD_DIM)                  # token order
-    dctx_tok = torch.empty_like(dctx)
-    dctx_tok[s2t] = dctx
-    dctx_tok = dctx_tok.view(T, heads, HEAD_DIM)
-    dqkv = torch.empty(T, 3, heads, HEAD_DIM, dtype=dy.dtype, device=dy.device)
-    cu = plan.cu_seqlens.tolist()
-    for b in range(B):                                                 # interim: SDPA backward per sample
-        lo, hi = cu[b], cu[b + 1]
-        if hi == lo:
-            continue
-        with torch.enable_grad():
-            q, k, v = (qkv[lo:hi, i].transpose(0, 1).unsqueeze(0).detach().requires_grad_(True) for i in range(3))
-            o = F.scaled_dot_product_attention(q, k, v, is_causal=True)
-            gq, gk, gv = torch.autograd.grad(o, (q, k, v), dctx_tok[lo:hi].transpose(0, 1).unsqueeze(0))
-        for i, gi in enumerate((gq, gk, gv)):
-            dqkv[lo:hi, i] = gi[0].transpose(0, 1)
-    # rotary backward on q and k (token order): y = x c + R(x) s  =>  dx = dy c + R^T(dy s)
-    pos = position_ids.reshape(-1)[plan.token_to_flat[:T].long()]
-    c = keep["cos"][pos].unsqueeze(1)
-    s_ = keep["sin"][pos].unsqueeze(1)
-    dqk = dqkv[:, :2]
-    dqkv[:, :2] = (dqk * c.unsqueeze(1)) + _rotate_half_t(dqk * s_.unsqueeze(1))
-    dqkv_sorted = dqkv.view(T, 3 * H)[s2t]                             # back to expert-sorted rows
-    dxn1 = routed_linear_bwd(dqkv_sorted, keep["xn1"][:T], keep["t_qkv"], specs["qkv"])
-    dx1, dw1 = _rmsnorm_bwd(dxn1, hf[s2f], keep["ln1"].weight.detach(), keep["ln1"].variance_epsilon)
-    add_grad(keep["ln1"].weight, dw1)
-    d_hidden = d_out.clone().view(cap, H)                              # residual path (and padded rows)
-    d_hidden[s2f] = (dh1 + dx1).to(d_hidden.dtype)
-    return d_hidden.view(B, L, H), [(params[i], grads[i]) for i in grads]
+    dctx_tok = new(cap, H)                                             # token order (K9 zeroes its tail rows)
+    _routed_linear_backward(dh1, keep["ctx"], keep["t_dense"], specs["dense"], counts, dctx_tok, sink,
+                            row_map=plan.sorted_to_token)
+    dqkv = new(cap, 3 * H)                                             # d(pre-rotary q | k | v), sorted order
+    delta = torch.empty(heads, cap, dtype=torch.float32, device=dev)
+    ops.attention_backward(keep["qkv"], keep["ctx"], dctx_tok, keep["lse"], delta, plan.cu_seqlens,
+                           plan.token_to_sorted, plan.token_to_flat, position_ids.reshape(-1), keep["cos"], keep["sin"],
+                           B, L, heads, dqkv, HEAD_DIM ** -0.5)
+    dxn1 = dxn2                                                        # reuse
+    _routed_linear_backward(dqkv, keep["xn1"], keep["t_qkv"], specs["qkv"], counts, dxn1, sink)
+    d_hidden = torch.empty_like(d_out)
+    ops.copy_padded_rows(dof, plan.flat_to_sorted, d_hidden.view(cap, H))   # padded rows: identity path only
+    ops.rmsnorm_backward(dxn1, hf, s2f, ln1.weight.detach(), ln1.variance_epsilon, dh1, None, d_hidden.view(cap, H), s2f,
+                         sink.buffer(ln1.weight), n_valid)
+    return d_hidden, sink.result()
 
 
 # --------------------------------------------------------------------------------------------------
@@ -172,7 +152,8 @@ class _LayerFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out):
         (hidden_states,) = ctx.saved_tensors
-        d_hidden, pg = layer_backward(ctx.layer, ctx.plan, ctx.position_ids, hidden_states, d_out.contiguous())
+        with torch.no_grad():
+            d_hidden, pg = layer_backward(ctx.layer, ctx.plan, ctx.position_ids, hidden_states, d_out.contiguous())
         by_id = {id(p): g for p, g in pg}
         tr = tuple(by_id.get(id(p)) for p in ctx.trainables)
         return (None, None, None, d_hidden if ctx.needs_input_grad[3] else None, *tr)
