@@ -39,7 +39,7 @@ __global__ void k9_zero_tail_rows(__nv_bfloat16* buf, const int32_t* __restrict_
     p[i] = make_uint4(0, 0, 0, 0);
 }
 
-constexpr int AB_THREADS = 256;
+constexpr int AB_THREADS = 384;  // TMA, MMA, TMEM-alloc, idle + 8 softmax warps (2 threads per row)
 constexpr int AB_T128 = 128 * 128 * 2;  // 32 KB tile of 128 rows x 128 d: two 16 KB atoms (64 d each)
 constexpr int AB_T64 = 64 * 128 * 2;    // 16 KB tile of 64 rows x 128 d: two 8 KB chunks
 constexpr int AB_P = 128 * 64 * 2;      // 16 KB: 128 rows x 64 bf16 (one 128-byte swizzle row each)
@@ -110,6 +110,12 @@ __device__ __forceinline__ void store_row_half(uint32_t tile, int row, int half,
   }
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int n) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
@@ -139,9 +145,9 @@ __device__ __forceinline__ void st_packed32(__nv_bfloat16* dst, const uint32_t (
 
 __device__ __forceinline__ void store_grad_row(uint32_t taddr, bool rope, const __nv_bfloat16* cos_row,
                                                const __nv_bfloat16* sin_row, float mul, __nv_bfloat16* dst,
-                                               bool valid) {
+                                               bool valid, int q_begin, int q_end) {
 #pragma unroll 1
-  for (int q = 0; q < 2; ++q) {
+  for (int q = q_begin; q < q_end; ++q) {
     uint32_t lo[32], hi[32];
     tmem_ld_32x32b_x32(taddr + q * 32, lo);       // columns [32q, 32q + 32)
     tmem_ld_32x32b_x32(taddr + 64 + q * 32, hi);  // their rotary partners, + 64
@@ -216,7 +222,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
       mbar_init(&bars->q_full[i], 1);
       mbar_init(&bars->q_empty[i], 1);
       mbar_init(&bars->s_full[i], 1);
-      mbar_init(&bars->p_full[i], 4);
+      mbar_init(&bars->p_full[i], 8);
       mbar_init(&bars->p_empty[i], 1);
     }
     mbar_init(&bars->acc_full, 1);
@@ -295,51 +301,82 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     }
     umma_commit(&bars->acc_full);
   } else if (warp >= 4) {
-    // =============================== softmax threads: one KEY row each ===============================
-    const int ew = warp - 4;
-    const int c = ew * 32 + lane;  // key row inside the block == TMEM lane
+    // =============================== softmax threads: two per KEY row (32 queries each) =====================
+    const int sw = warp - 4;           // 0..7
+    const int ew = sw & 3;             // TMEM lane quarter
+    const int half = sw >> 2;          // which 32 of the step's 64 query columns
+    const int c = ew * 32 + lane;      // key row inside the block == TMEM lane
+    const int sid = sw * 32 + lane;    // 0..255
     const uint32_t lane_sel = static_cast<uint32_t>(ew * 32) << 16;
     const int kv_idx = kv0 + c;
     const float* lse_h = p.lse + static_cast<int64_t>(h) * p.rows_cap;
     const float* delta_h = p.delta + static_cast<int64_t>(h) * p.rows_cap;
+    // lse (threads 0..63) / delta (threads 64..127) of the 64 queries of a step, prefetched one step ahead
+    auto load_stat = [&](int s) {
+      float v = 0.f;
+      if (sid < 128 && s < n_steps) {
+        const int qi = (i0 + s) * 64 + (sid & 63);
+        if (qi < len) v = (sid < 64 ? lse_h : delta_h)[seq0 + qi];
+      }
+      return v;
+    };
+    float stat_next = load_stat(0);
     for (int s = 0; s < n_steps; ++s) {
       const int st = s & 1;
       const uint32_t ph = (s >> 1) & 1;
       const int q_base = (i0 + s) * 64;
-      {  // stage lse (threads 0..63) and delta (threads 64..127) of the step's 64 queries
-        const int qi = q_base + (c & 63);
-        float v = 0.f;
-        if (qi < len) v = (c < 64 ? lse_h : delta_h)[seq0 + qi];
-        sStat[st * 128 + c] = v;
-      }
-      named_bar_sync(1, 128);
+      if (sid < 128) sStat[st * 128 + sid] = stat_next;
+      stat_next = load_stat(s + 1);
+      named_bar_sync(1, 256);
       mbar_wait(&bars->s_full[st], ph);
       tc_fence_after();
-      mbar_wait(&bars->p_empty[st], ph ^ 1);  // the MMAs of step s - 2 have finished reading this P / dS buffer
-      const uint32_t aP = smem_u32(sP + st * AB_P), adS = smem_u32(sdS + st * AB_P);
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        uint32_t sraw[32], draw[32];
-        tmem_ld_32x32b_x32(tS + lane_sel + st * 64 + half * 32, sraw);
-        tmem_ld_32x32b_x32(tdP + lane_sel + st * 64 + half * 32, draw);
-        tmem_ld_wait();
-        float pv[32], dsv[32];
+      uint32_t sraw[32], draw[32];
+      tmem_ld_32x32b_x32(tS + lane_sel + st * 64 + half * 32, sraw);
+      tmem_ld_32x32b_x32(tdP + lane_sel + st * 64 + half * 32, draw);
+      tmem_ld_wait();
+      const float4* l4 = reinterpret_cast<const float4*>(sStat + st * 128 + half * 32);
+      const float4* d4 = reinterpret_cast<const float4*>(sStat + st * 128 + 64 + half * 32);
+      uint32_t pk[16], dk[16];
+      // interior steps (every query at or after every key of the block, all inside the sample) need no masks
+      const bool interior = (q_base >= kv0 + 127) && (q_base + 64 <= len);
+      if (interior) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = half * 32 + j;
-          const int q_idx = q_base + col;
-          const bool keep = (q_idx >= kv_idx) && (q_idx < len);
-          const float l2 = sStat[st * 128 + col], dl = sStat[st * 128 + 64 + col];
-          const float pr = keep ? exp2f(fmaf(__uint_as_float(sraw[j]), p.scale_log2, -l2)) : 0.f;
-          pv[j] = pr;
-          dsv[j] = keep ? pr * (__uint_as_float(draw[j]) - dl) : 0.f;
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 l = l4[j4], d = d4[j4];
+          const float lv[4] = {l.x, l.y, l.z, l.w}, dv[4] = {d.x, d.y, d.z, d.w};
+          float pr[4], ds[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            pr[k] = ex2_approx(fmaf(__uint_as_float(sraw[4 * j4 + k]), p.scale_log2, -lv[k]));
+            ds[k] = pr[k] * (__uint_as_float(draw[4 * j4 + k]) - dv[k]);
+          }
+          pk[2 * j4] = pack_bf16(pr[0], pr[1]);
+          pk[2 * j4 + 1] = pack_bf16(pr[2], pr[3]);
+          dk[2 * j4] = pack_bf16(ds[0], ds[1]);
+          dk[2 * j4 + 1] = pack_bf16(ds[2], ds[3]);
         }
-        uint32_t pk[16];
-        pack32(pv, pk);
-        store_row_half(aP, c, half, pk);
-        pack32(dsv, pk);
-        store_row_half(adS, c, half, pk);
+      } else {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 l = l4[j4], d = d4[j4];
+          const float lv[4] = {l.x, l.y, l.z, l.w}, dv[4] = {d.x, d.y, d.z, d.w};
+          float pr[4], ds[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int q_idx = q_base + half * 32 + 4 * j4 + k;
+            const bool keep = (q_idx >= kv_idx) && (q_idx < len);
+            pr[k] = keep ? ex2_approx(fmaf(__uint_as_float(sraw[4 * j4 + k]), p.scale_log2, -lv[k])) : 0.f;
+            ds[k] = keep ? pr[k] * (__uint_as_float(draw[4 * j4 + k]) - dv[k]) : 0.f;
+          }
+          pk[2 * j4] = pack_bf16(pr[0], pr[1]);
+          pk[2 * j4 + 1] = pack_bf16(pr[2], pr[3]);
+          dk[2 * j4] = pack_bf16(ds[0], ds[1]);
+          dk[2 * j4 + 1] = pack_bf16(ds[2], ds[3]);
+        }
       }
+      mbar_wait(&bars->p_empty[st], ph ^ 1);  // the MMAs of step s - 2 have finished reading this P / dS buffer
+      store_row_half(smem_u32(sP + st * AB_P), c, half, pk);
+      store_row_half(smem_u32(sdS + st * AB_P), c, half, dk);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
@@ -357,9 +394,11 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
       pos = static_cast<int>(min(max(pz, int64_t(0)), int64_t(p.rope_len - 1)));
     }
     __nv_bfloat16* row = p.dqkv + static_cast<int64_t>(dst) * (3 * H) + h * 128;
-    store_grad_row(tdV + lane_sel, false, nullptr, nullptr, 1.0f, row + 2 * H, valid);
-    store_grad_row(tdK + lane_sel, true, p.rope_cos + static_cast<int64_t>(pos) * 128,
-                   p.rope_sin + static_cast<int64_t>(pos) * 128, p.scale, row + H, valid);
+    if (half == 0)
+      store_grad_row(tdV + lane_sel, false, nullptr, nullptr, 1.0f, row + 2 * H, valid, 0, 2);
+    else
+      store_grad_row(tdK + lane_sel, true, p.rope_cos + static_cast<int64_t>(pos) * 128,
+                     p.rope_sin + static_cast<int64_t>(pos) * 128, p.scale, row + H, valid, 0, 2);
   }
 
   tc_fence_before();
@@ -406,7 +445,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
       mbar_init(&bars->kv_full[i], 1);
       mbar_init(&bars->kv_empty[i], 1);
       mbar_init(&bars->s_full[i], 1);
-      mbar_init(&bars->p_full[i], 4);
+      mbar_init(&bars->p_full[i], 8);
       mbar_init(&bars->p_empty[i], 1);
     }
     mbar_init(&bars->acc_full, 1);
@@ -480,8 +519,10 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     }
     umma_commit(&bars->acc_full);
   } else if (warp >= 4) {
-    // =============================== softmax threads: one QUERY row each ===============================
-    const int ew = warp - 4;
+    // =============================== softmax threads: two per QUERY row (32 keys each) ======================
+    const int sw = warp - 4;
+    const int ew = sw & 3;
+    const int half = sw >> 2;
     const int c = ew * 32 + lane;
     const uint32_t lane_sel = static_cast<uint32_t>(ew * 32) << 16;
     const int q_idx = q0 + c;
@@ -497,26 +538,33 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
       const uint32_t ph = (s >> 1) & 1;
       mbar_wait(&bars->s_full[st], ph);
       tc_fence_after();
-      mbar_wait(&bars->p_empty[st], ph ^ 1);
-      const uint32_t adS = smem_u32(sdS + st * AB_P);
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        uint32_t sraw[32], draw[32];
-        tmem_ld_32x32b_x32(tS + lane_sel + st * 64 + half * 32, sraw);
-        tmem_ld_32x32b_x32(tdP + lane_sel + st * 64 + half * 32, draw);
-        tmem_ld_wait();
-        float dsv[32];
+      uint32_t sraw[32], draw[32];
+      tmem_ld_32x32b_x32(tS + lane_sel + st * 64 + half * 32, sraw);
+      tmem_ld_32x32b_x32(tdP + lane_sel + st * 64 + half * 32, draw);
+      tmem_ld_wait();
+      uint32_t dk[16];
+      // interior steps: every key of the step is at or before every query of the block, block inside the sample
+      const bool interior = (s * 64 + 63 <= q0) && (q0 + 128 <= len);
+      if (interior) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int kv_idx = s * 64 + half * 32 + j;
-          const bool keep = valid && (kv_idx <= q_idx);
-          const float pr = keep ? exp2f(fmaf(__uint_as_float(sraw[j]), p.scale_log2, -l2)) : 0.f;
-          dsv[j] = keep ? pr * (__uint_as_float(draw[j]) - dl) : 0.f;
+        for (int j = 0; j < 32; j += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sraw[j]), p.scale_log2, -l2));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sraw[j + 1]), p.scale_log2, -l2));
+          dk[j >> 1] = pack_bf16(p0 * (__uint_as_float(draw[j]) - dl), p1 * (__uint_as_float(draw[j + 1]) - dl));
         }
-        uint32_t pk[16];
-        pack32(dsv, pk);
-        store_row_half(adS, c, half, pk);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const int kv_idx = s * 64 + half * 32 + j;
+          const bool k0 = valid && (kv_idx <= q_idx), k1 = valid && (kv_idx + 1 <= q_idx);
+          const float p0 = k0 ? ex2_approx(fmaf(__uint_as_float(sraw[j]), p.scale_log2, -l2)) : 0.f;
+          const float p1 = k1 ? ex2_approx(fmaf(__uint_as_float(sraw[j + 1]), p.scale_log2, -l2)) : 0.f;
+          dk[j >> 1] = pack_bf16(k0 ? p0 * (__uint_as_float(draw[j]) - dl) : 0.f,
+                                 k1 ? p1 * (__uint_as_float(draw[j + 1]) - dl) : 0.f);
+        }
       }
+      mbar_wait(&bars->p_empty[st], ph ^ 1);
+      store_row_half(smem_u32(sdS + st * AB_P), c, half, dk);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
@@ -533,7 +581,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     }
     store_grad_row(tdQ + lane_sel, true, p.rope_cos + static_cast<int64_t>(pos) * 128,
                    p.rope_sin + static_cast<int64_t>(pos) * 128, p.scale,
-                   p.dqkv + static_cast<int64_t>(dst) * (3 * H) + h * 128, valid);
+                   p.dqkv + static_cast<int64_t>(dst) * (3 * H) + h * 128, valid, half, half + 1);
   }
 
   tc_fence_before();
