@@ -423,7 +423,7 @@ def run_train(args):
 
     for _ in range(args.warmup):
         step()
-    kernels = instrument.profile(step, iters=2) if rank == 0 else None
+    kernels = instrument.profile(step, iters=2)  # every rank: the step contains the all-reduce (a collective)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
