@@ -202,7 +202,7 @@ def run_ours(args):
     from mmmm_b200._lib import lib
     from mmmm_b200.graph import GraphedPrefill
     from mmmm_b200.inputs import make_inputs
-    from mmmm_b200.sharding import max_over_ranks
+    from mmmm_b200.sharding import bind_to_gpu_numa_node, max_over_ranks
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -211,6 +211,7 @@ def run_ours(args):
         raise SystemExit("--gpus N > 1 must be launched with torchrun (one rank per GPU)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else {"numa_node": None}
     if lib().vex_device_check() != 0:
         raise SystemExit("no sm_100 device: the visual-expert kernels only run on B200")
     if world > 1:
@@ -371,7 +372,7 @@ def run_ours(args):
         "e2e": {"value": total_tokens / (ms_e2e / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
                 "how": "layer(...) on pinned host inputs; 2 requests in flight (H2D / compute / D2H streams)"},
-        "gpu_launches": launches, "clocks": clocks, "peaks": pk,
+        "gpu_launches": launches, "clocks": clocks, "peaks": pk, "host_numa": numa,
     }))
     if world > 1:
         dist.destroy_process_group()

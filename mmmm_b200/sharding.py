@@ -42,3 +42,41 @@ def sum_over_ranks(value: float, device=None) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=device or "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def _parse_cpulist(text: str):
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pins the calling process to the CPUs of the NUMA node the GPU hangs off (sysfs: the PCI device's
+    ``numa_node`` and the node's ``cpulist``), so that pinned host buffers allocated afterwards are node-local
+    (first-touch / local allocation policy) and H2D / D2H copies do not cross the socket interconnect.  With one
+    process per GPU (the reference's DDP launch, conf/phase-vlm/fit.yaml:11-15) eight ranks otherwise share whatever
+    node their pages landed on.  Best effort: returns what it did, never raises."""
+    import os
+    info = {"numa_node": None, "cpus": None}
+    try:
+        prop = torch.cuda.get_device_properties(device_index)
+        dom, bus, dev = getattr(prop, "pci_domain_id", 0), prop.pci_bus_id, prop.pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        with open(path) as f:
+            node = int(f.read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus"] = len(allowed)
+    except Exception as e:  # sysfs not mounted, attribute missing, ...
+        info["error"] = f"{type(e).__name__}: {e}"
+    return info
