@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 3)
   const int warp = threadIdx.x >> 5;
   const int slot = warp / WPR, half = warp % WPR;
   const int n_rows = min(*n_rows_ptr, rows_cap);
-  // CTA-uniform trip count (the pair barrier below is a CTA barrier when WPR == 2)
+  // trip count uniform per warp pair (both warps of a row take the pair barrier below)
   for (int r0 = blockIdx.x * ROWS; r0 < n_rows; r0 += gridDim.x * ROWS) {
     const int r = r0 + slot;
     const bool live = r < n_rows;
@@ -61,10 +61,12 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 3)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     if constexpr (WPR == 2) {
+      // pair-scoped named barrier (id 1 + slot, 64 threads): the two warps of a row meet, the other rows of the
+      // CTA keep streaming -- a CTA-wide barrier would put all 8 warps in lock-step load / store phases
       if (lane == 0) part[warp] = ss;
-      __syncthreads();
+      asm volatile("bar.sync %0, 64;" ::"r"(slot + 1) : "memory");
       ss = part[slot * 2] + part[slot * 2 + 1];
-      __syncthreads();  // part[] is rewritten in the next iteration
+      asm volatile("bar.sync %0, 64;" ::"r"(slot + 1) : "memory");  // part[] is rewritten in the next iteration
     }
     if (live) {
       const float inv = rsqrtf(ss * (1.0f / H) + eps);

@@ -138,10 +138,10 @@ __global__ void __launch_bounds__(K7_WARPS * 32, NCHUNK >= 8 ? 1 : 2)
         part[warp][0] = ss;
         part[warp][1] = sd;
       }
-      __syncthreads();
+      asm volatile("bar.sync %0, 64;" ::"r"(slot + 1) : "memory");  // pair-scoped: other rows keep streaming
       ss = part[slot * 2][0] + part[slot * 2 + 1][0];
       sd = part[slot * 2][1] + part[slot * 2 + 1][1];
-      __syncthreads();
+      asm volatile("bar.sync %0, 64;" ::"r"(slot + 1) : "memory");
     }
     if (live) {
       const float inv = rsqrtf(ss * (1.0f / H) + eps);

@@ -64,6 +64,29 @@ def bench_gemm(Tv=9808, Tl=2072):
                           "cublas_single_expert_ms": ref, "cublas_tflops": 2.0 * cap * N * K / ref / 1e9}))
 
 
+def bench_rowwise(T=11880, H=4096, I=11008):
+    """HBM-bound kernels at config-2 sizes: achieved GB/s = algorithmic bytes / time."""
+    dev = "cuda"
+    n = torch.tensor([T], dtype=torch.int32, device=dev)
+    perm = torch.randperm(T, device=dev).int()
+    x = torch.randn(T, H, device=dev).bfloat16()
+    w = torch.ones(H, device=dev, dtype=torch.bfloat16)
+    y = torch.empty_like(x)
+    big = [torch.randn(T, I, device=dev).bfloat16() for _ in range(5)]
+    dw = torch.zeros(H, device=dev, dtype=torch.float32)
+    cases = {
+        "k2_rmsnorm_gather": (lambda: ops.rmsnorm_gather(x, w, 1e-6, perm, n, y), 2 * T * H * 2),
+        "k5_silu_mul": (lambda: ops.silu_mul(big[0], big[1], n, big[2]), 3 * T * I * 2),
+        "k6_residual_scatter": (lambda: ops.residual_scatter(x, y, perm, n, y), 3 * T * H * 2),
+        "k7_gather_rows": (lambda: ops.gather_rows(x, perm, n, y), 2 * T * H * 2),
+        "k7_silu_mul_backward": (lambda: ops.silu_mul_backward(big[0], big[1], big[2], n, big[3], big[4]), 5 * T * I * 2),
+        "k7_rmsnorm_backward": (lambda: ops.rmsnorm_backward(x, x, perm, w, 1e-6, x, None, y, perm, dw, n), 4 * T * H * 2),
+    }
+    for name, (fn, nbytes) in cases.items():
+        ms = timeit(fn, iters=50)
+        print(json.dumps({"kernel": name, "rows": T, "ms": ms, "GBps": nbytes / ms / 1e6}))
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("all", "attention"):
@@ -71,3 +94,5 @@ if __name__ == "__main__":
         bench_attention(B=2, nv=2048, nt=512)
     if which in ("all", "gemm"):
         bench_gemm()
+    if which in ("all", "rowwise"):
+        bench_rowwise()
