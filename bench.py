@@ -164,7 +164,7 @@ def config_dict(args, tokens_per_gpu):
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
-def make_gpu_layer(device, lora_r: int, seed: int = 0):
+def make_gpu_layer(device, lora_r: int, seed: int = 0, lora_dropout: float = 0.0):
     """Random-init layer with the reference's init (Linear ~ N(0, 0.02)), generated on the device."""
     from mmmm_b200.modeling_cogvlm import CogVLMDecoderLayer, VexConfig
     from mmmm_b200.peft_compat import attach_mock_lora
@@ -182,7 +182,7 @@ def make_gpu_layer(device, lora_r: int, seed: int = 0):
         rot.inv_freq = (1.0 / (rot.base ** (torch.arange(0, 128, 2, device=device) / 128))).to(torch.bfloat16)
     if lora_r:
         torch.manual_seed(seed)
-        attach_mock_lora(layer, r=lora_r, lora_alpha=8, b_std=0.02)
+        attach_mock_lora(layer, r=lora_r, lora_alpha=8, b_std=0.02, lora_dropout=lora_dropout)
     return layer.eval()
 
 
@@ -397,7 +397,7 @@ def run_train(args):
         dist.init_process_group("nccl", device_id=dev)
     r = args.lora or 64
     b, nv, nt = WORKLOADS[args.workload]
-    layers = [make_gpu_layer(dev, r, seed=i).train() for i in range(args.layers)]
+    layers = [make_gpu_layer(dev, r, seed=i, lora_dropout=args.lora_dropout).train() for i in range(args.layers)]
     params = [p for l in layers for p in l.parameters() if p.requires_grad]
     reducer = LoraGradReducer(params)
     inp = make_inputs(b, nv, nt, H, seed=rank).to(dev)
@@ -458,7 +458,8 @@ def run_train(args):
             "metric": "visual-expert LoRA train tokens/s", "value": total / (ms_step / 1e3), "unit": "tokens/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": dict(config_dict(args, tokens), lora_r=r, mode="train: fwd + recompute + bwd + LoRA-grad allreduce"),
+            "config": dict(config_dict(args, tokens), lora_r=r, lora_dropout=args.lora_dropout,
+                           mode="train: fwd + recompute + bwd + LoRA-grad allreduce"),
             "allreduce_ms": allreduce_ms, "allreduce_bytes": reducer.nbytes, "trainable_params": reducer.flat.numel(),
             "gpu_launches": launches, "kernels": kernels,
             "step_tflops_per_gpu": flop / (ms_step / 1e3) / 1e12,
@@ -481,6 +482,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--layers", type=int, default=1, help="decoder layers per step (32 = the full stack, config 3/4)")
     ap.add_argument("--train", action="store_true", help="config 5: LoRA fwd+bwd training step + grad all-reduce")
+    ap.add_argument("--lora-dropout", type=float, default=0.0, help="--train: lora_dropout (the reference uses 0.05)")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the forward as one CUDA graph (default), 0: eager")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

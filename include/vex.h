@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VEX_ABI_VERSION 2
+#define VEX_ABI_VERSION 3
 
 #define VEX_OK 0
 #define VEX_E_INVALID (-1)     /* bad argument (null pointer, size, alignment) */
@@ -112,6 +112,8 @@ int vex_copy_padded_rows(const void* x, const int32_t* flat_to_sorted, void* out
                               (apply_rotary_pos_emb_index_bhs :188-193 fused) */
 #define VEX_EPI_SWIGLU 2   /* gate/up pair: out = silu(A.Wg^T) * (A.Wu^T)  (MLP.forward :55 fused) */
 #define VEX_EPI_RESIDUAL 3 /* out[map(r)] = bf16(acc) + residual[map(r)]  (:321, :330 fused) */
+#define VEX_EPI_DROPOUT_ACC 4 /* out[map(r)] = residual[map(r)] + bf16(keep(r, col) * alpha / (1 - p) * acc): adjoint of
+                                 the LoRA input dropout (PEFT lora.Linear: lora_A(dropout(x))), mask as vex_dropout_rows */
 
 typedef struct vexGemmArgs {
   const void* a;            /* [rows_cap, K] bf16, sorted row order, row stride lda elements */
@@ -143,8 +145,10 @@ typedef struct vexGemmArgs {
   int32_t w_transposed;     /* 0: w is [N, K] (forward, out = A . W^T).  1: w is [K, N] row-major and out = A . W --
                                the backward form dX = dY . W that reads the nn.Linear weight [out, in] as stored
                                (K = out features, N = in features; what autograd does for :244-245 etc.).  lora_b[e][0]
-                               is then lora_A [r, N] and lora_t = scaling * dY . lora_B.  PLAIN / RESIDUAL only;
-                               K % 64 == 0 */
+                               is then lora_A [r, N] and lora_t = scaling * dY . lora_B.  PLAIN / RESIDUAL /
+                               DROPOUT_ACC only */
+  float dropout_p;          /* VEX_EPI_DROPOUT_ACC: drop probability and seed of the forward vex_dropout_rows call; */
+  uint64_t dropout_seed;    /*   the mask index is sorted_row * N + col */
 } vexGemmArgs;
 
 int vex_grouped_gemm(const vexGemmArgs* args, vexStream stream);
@@ -184,6 +188,13 @@ int vex_attention_decode(const void* q, int64_t ldq, const void* k, const void* 
  * expert-sorted order -- the adjoint of the out[mask] = ... scatters (:96-97, :278-279). */
 int vex_gather_rows(const void* x, const int32_t* row_src, const int32_t* n_rows, void* out, int rows_cap, int H,
                     vexStream stream);
+
+/* LoRA input dropout (PEFT lora.Linear.forward: lora_B(lora_A(dropout(x))) * scaling, conf/lora.yaml lora_dropout):
+ * out[r, c] = keep(r, c) ? bf16(x[r, c] / (1 - p)) : 0 for r < *n_rows, keep from a counter-based hash of
+ * (r * K + c, seed) -- reproducible, so the checkpointed recompute and VEX_EPI_DROPOUT_ACC regenerate the same mask.
+ * (PyTorch's Philox stream cannot be reproduced bit-for-bit; the mask distribution is the same Bernoulli(1 - p).) */
+int vex_dropout_rows(const void* x, void* out, const int32_t* n_rows, int rows_cap, int K, float p, uint64_t seed,
+                     vexStream stream);
 
 /* Adjoint of K5 / the SwiGLU epilogue (MLP.forward :55): given d(act), gate = gate_proj(x), up = up_proj(x)
  * (bf16, [rows_cap, I]) writes dgate and dup with the eager-bf16 rounding points

@@ -51,6 +51,24 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+// Counter-based dropout mask shared by the forward dropout kernel (K7) and the dgrad epilogue (K3): one 32-bit
+// hash per PAIR of adjacent elements (pair index = element index / 2), 16 bits each; element kept iff its 16 bits
+// >= thresh16 = round(p * 65536).  lowbias32 mixer over (pair index, seed).
+__device__ __forceinline__ uint32_t dropout_hash(uint64_t pair_index, uint32_t seed_lo, uint32_t seed_hi) {
+  uint32_t x = static_cast<uint32_t>(pair_index) * 0x9E3779B1u + seed_lo;
+  x ^= static_cast<uint32_t>(pair_index >> 32) * 0x85EBCA77u + seed_hi;
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  x += seed_hi;
+  x ^= x >> 15;
+  x *= 0x2c1b3c6du;
+  x ^= x >> 12;
+  return x;
+}
+
 // streaming 16-byte global accesses (no L1 allocation: every byte is touched once)
 __device__ __forceinline__ uint4 ld_stream(const void* p) {
   uint4 r;

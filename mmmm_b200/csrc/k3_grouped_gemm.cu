@@ -65,6 +65,7 @@ struct GemmDev {
   int lora_steps;  // 64-wide k-blocks along r (0 = no LoRA)
   int lora_mask;   // bit e: expert e has an adapter
   int trans_b;     // 1: weights are [K, N] row-major (MN-major B operand): out = A . W  (backward dgrad)
+  uint32_t drop_thresh16, drop_seed_lo, drop_seed_hi;  // VEX_EPI_DROPOUT_ACC: mask of dropout_hash(s_row * N + col)
 };
 
 template <int BN>
@@ -294,6 +295,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, int e, int m, in
           if (p.mode == VEX_EPI_PLAIN) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
+          } else if (p.mode == VEX_EPI_DROPOUT_ACC) {
+            // adjoint of the LoRA input dropout: keep(s_row, col) * alpha * acc, same hash as k7_dropout_rows
+            const uint64_t pair0 = (static_cast<uint64_t>(s_row) * p.N + (col0 + q * 32)) >> 1;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const uint32_t hsh = dropout_hash(pair0 + (j >> 1), p.drop_seed_lo, p.drop_seed_hi);
+              v[j] = (hsh & 0xffffu) >= p.drop_thresh16 ? __uint_as_float(raw[j]) * p.alpha : 0.f;
+              v[j + 1] = (hsh >> 16) >= p.drop_thresh16 ? __uint_as_float(raw[j + 1]) * p.alpha : 0.f;
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
@@ -306,7 +316,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, int e, int m, in
       } else {
         __syncwarp();
       }
-      write_panel(g_row, col0, p.mode == VEX_EPI_RESIDUAL);
+      write_panel(g_row, col0, p.mode == VEX_EPI_RESIDUAL || p.mode == VEX_EPI_DROPOUT_ACC);
       __syncwarp();
     }
   }
@@ -863,11 +873,13 @@ extern "C" int vex_grouped_gemm(const vexGemmArgs* a, vexStream stream) {
   if (a->rows_cap <= 0 || a->N <= 0 || a->K <= 0) return VEX_E_INVALID;
   if (a->N % 8 != 0 || a->K % 8 != 0 || a->ldo % 8 != 0 || a->lda % 8 != 0 || a->ldw % 8 != 0)
     return VEX_E_UNSUPPORTED;
-  if (a->mode < VEX_EPI_PLAIN || a->mode > VEX_EPI_RESIDUAL) return VEX_E_INVALID;
+  if (a->mode < VEX_EPI_PLAIN || a->mode > VEX_EPI_DROPOUT_ACC) return VEX_E_INVALID;
   const bool swiglu = a->mode == VEX_EPI_SWIGLU;
   if (!a->single_expert && !a->w[1][0]) return VEX_E_INVALID;
   if (swiglu && (!a->w[0][1] || (!a->single_expert && !a->w[1][1]))) return VEX_E_INVALID;
-  if (a->mode == VEX_EPI_RESIDUAL && !a->residual) return VEX_E_INVALID;
+  if ((a->mode == VEX_EPI_RESIDUAL || a->mode == VEX_EPI_DROPOUT_ACC) && !a->residual) return VEX_E_INVALID;
+  if (a->mode == VEX_EPI_DROPOUT_ACC && (!(a->dropout_p >= 0.f && a->dropout_p < 1.f) || a->N % 2 != 0))
+    return VEX_E_INVALID;
   if (a->mode == VEX_EPI_ROPE) {
     if (!a->rope_cos || !a->rope_sin || !a->position_ids || !a->sorted_to_flat || a->rope_len <= 0)
       return VEX_E_INVALID;
@@ -875,7 +887,6 @@ extern "C" int vex_grouped_gemm(const vexGemmArgs* a, vexStream stream) {
   }
   const bool tb = a->w_transposed != 0;
   if (tb && (swiglu || a->mode == VEX_EPI_ROPE)) return VEX_E_UNSUPPORTED;
-  if (tb && (a->K % 64 != 0 || (a->lora_r > 0 && a->lora_r % 8 != 0))) return VEX_E_UNSUPPORTED;
   const bool small_n = a->N <= 64 && a->mode == VEX_EPI_PLAIN;
   const int BN = small_n ? 64 : 256;
   const int half_rows = swiglu ? 128 : BN / 2;
@@ -937,6 +948,12 @@ extern "C" int vex_grouped_gemm(const vexGemmArgs* a, vexStream stream) {
   dev.mode = a->mode;
   dev.single_expert = a->single_expert;
   dev.trans_b = tb;
+  if (a->mode == VEX_EPI_DROPOUT_ACC) {
+    dev.drop_thresh16 = static_cast<uint32_t>(a->dropout_p * 65536.0f + 0.5f);
+    dev.drop_seed_lo = static_cast<uint32_t>(a->dropout_seed);
+    dev.drop_seed_hi = static_cast<uint32_t>(a->dropout_seed >> 32);
+    dev.alpha = a->alpha / (1.0f - a->dropout_p);
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (tb) {
     if (small_n) return launch_gemm<64, true>(tm, dev, s);

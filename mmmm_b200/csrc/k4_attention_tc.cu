@@ -28,16 +28,19 @@ namespace vex {
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
 constexpr int TC_BQ = 128, TC_BK = 128, TC_D = 128;
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;  // TMA, MMA, TMEM-alloc, idle + 8 softmax warps
 constexpr int TC_TILE = 128 * 128 * 2;    // 32 KB: one 128 x 128 bf16 tile = two 64-column atoms of 16 KB
 constexpr int TC_ATOM = 128 * 64 * 2;     // 16 KB
-constexpr int TC_SMEM = 6 * TC_TILE + 256 + 1024;  // Q, K x2, V x2, P + barriers + alignment slack
+constexpr int TC_SMEM = 6 * TC_TILE + 256 + 2048 + 1024;  // Q, K x2, V x2, P + barriers + alignment slack
 constexpr float TC_RESCALE_THRESHOLD = 8.0f;        // log2 units
 
 struct AttnBars {
   uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full, pv_done;
   uint32_t tmem_base;
+  float xchg[2 * 2 * 128];  // row-max / row-sum exchange between the two threads of a query row
 };
+
+__device__ __forceinline__ void named_bar_sync_256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __global__ void zero_tail_rows(__nv_bfloat16* buf, const int32_t* __restrict__ cu_seqlens, int B, int rows_cap,
                                int row_elems) {
@@ -81,7 +84,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_init(&bars->v_empty[i], 1);
       mbar_init(&bars->s_full[i], 1);
     }
-    mbar_init(&bars->p_full, 4);
+    mbar_init(&bars->p_full, 8);
     mbar_init(&bars->pv_done, 1);
     fence_mbar_init();
   }
@@ -153,36 +156,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
   } else if (warp >= 4) {
     // =============================== softmax + epilogue ===============================
-    const int ew = warp - 4;
+    // 8 warps: TWO threads per query row (64 keys each), so every SM sub-partition has two warps to interleave
+    // (one warp per scheduler could not hide the TMEM-load / MUFU latencies: the softmax ran ~3x slower than its
+    // exp2 throughput bound).  The row maximum is exchanged through shared memory; the row sums stay per-thread
+    // partial sums (same running max, same rescale decisions) and are added in the epilogue.
+    const int sw = warp - 4;
+    const int ew = sw & 3;       // TMEM lane quarter
+    const int hf = sw >> 2;      // key half inside a block / output-column half in the epilogue
     const int r = ew * 32 + lane;  // query row inside the block == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>(ew * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f;
     const uint32_t aP = smem_u32(sP);
-    const uint32_t p_row = aP + r * 128;  // byte offset of this row inside a 64-key atom
+    const uint32_t p_row = aP + hf * TC_ATOM + r * 128;  // this thread's 128-byte row of key atom hf
+    float* xchg = bars->xchg;                             // [2 (block parity)][2 (half)][128 rows]
 
     for (int j = 0; j < n_kv; ++j) {
       const int sb = j & 1;
       mbar_wait(&bars->s_full[sb], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t sraw[4][32];
+      uint32_t sraw[2][32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tS0 + lane_sel + sb * 128 + c * 32, sraw[c]);
+      for (int c = 0; c < 2; ++c) tmem_ld_32x32b_x32(tS0 + lane_sel + sb * 128 + hf * 64 + c * 32, sraw[c]);
       tmem_ld_wait();
-      float mx = -INFINITY;
-      if (j == n_kv - 1) {  // diagonal block: key (j*128 + c) visible iff c <= r
+      float mx0 = -INFINITY, mx1 = -INFINITY;  // two chains
+      if (j == n_kv - 1) {  // diagonal block: key (j*128 + k) visible iff k <= r
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (c * 32 + i > r) sraw[c][i] = 0xff800000u;  // -inf
-            mx = fmaxf(mx, __uint_as_float(sraw[c][i]));
+          for (int i = 0; i < 32; i += 2) {
+            if (hf * 64 + c * 32 + i > r) sraw[c][i] = 0xff800000u;  // -inf
+            if (hf * 64 + c * 32 + i + 1 > r) sraw[c][i + 1] = 0xff800000u;
+            mx0 = fmaxf(mx0, __uint_as_float(sraw[c][i]));
+            mx1 = fmaxf(mx1, __uint_as_float(sraw[c][i + 1]));
           }
       } else {
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sraw[c][i]));
+          for (int i = 0; i < 32; i += 2) {
+            mx0 = fmaxf(mx0, __uint_as_float(sraw[c][i]));
+            mx1 = fmaxf(mx1, __uint_as_float(sraw[c][i + 1]));
+          }
       }
+      xchg[(sb * 2 + hf) * 128 + r] = fmaxf(mx0, mx1);
+      named_bar_sync_256();
+      const float mx = fmaxf(xchg[(sb * 2) * 128 + r], xchg[(sb * 2 + 1) * 128 + r]);
       // lazy rescale: keep the stale max unless the new one is more than 2^8 larger
       float alpha = 1.0f;
       bool rescale = false;
@@ -192,18 +210,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         rescale = j > 0;
       }
       const float msc = m_run * scale_log2;
-      float rs = 0.f;
+      float rs0 = 0.f, rs1 = 0.f;
       // P (bf16 pairs) is packed in place: pair i of chunk c lands in sraw[c][i / 2], which is already consumed
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           const float p0 = exp2f(fmaf(__uint_as_float(sraw[c][i]), scale_log2, -msc));
           const float p1 = exp2f(fmaf(__uint_as_float(sraw[c][i + 1]), scale_log2, -msc));
-          rs += p0 + p1;
+          rs0 += p0;
+          rs1 += p1;
           sraw[c][i >> 1] = pack_bf16(p0, p1);
         }
-      l_run = l_run * alpha + rs;
+      l_run = l_run * alpha + (rs0 + rs1);
 
       if (j > 0) {  // P buffer and O are free once P_{j-1}.V_{j-1} has completed
         mbar_wait(&bars->pv_done, (j - 1) & 1);
@@ -211,23 +230,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       // P -> shared memory, UMMA K-major SWIZZLE_128B: (row, 16-byte chunk c16) at row*128 + ((c16 ^ row%8) * 16)
 #pragma unroll
-      for (int c16 = 0; c16 < 16; ++c16) {
-        const uint32_t addr = p_row + (c16 >> 3) * TC_ATOM + (((c16 & 7) ^ (r & 7)) << 4);
-        // chunk c16 = keys [8*c16, 8*c16 + 8) = packed pairs 4*(c16 % 4) .. +3 of S chunk c16 / 4
+      for (int c16 = 0; c16 < 8; ++c16) {
+        const uint32_t addr = p_row + ((c16 ^ (r & 7)) << 4);
+        // chunk c16 = this half's keys [8*c16, 8*c16 + 8) = packed pairs 4*(c16 % 4) .. +3 of S chunk c16 / 4
         const uint32_t* pp = &sraw[c16 >> 2][(c16 & 3) * 4];
         asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pp[0]), "r"(pp[1]), "r"(pp[2]),
                      "r"(pp[3])
                      : "memory");
       }
-      if (__any_sync(0xffffffffu, rescale)) {
+      if (__any_sync(0xffffffffu, rescale)) {  // this thread's half of the O columns
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t o[32];
-          tmem_ld_32x32b_x32(tO + lane_sel + c * 32, o);
+          tmem_ld_32x32b_x32(tO + lane_sel + hf * 64 + c * 32, o);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_32x32b_x32(tO + lane_sel + c * 32, o);
+          tmem_st_32x32b_x32(tO + lane_sel + hf * 64 + c * 32, o);
         }
         tmem_st_wait();
       }
@@ -237,20 +256,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       if (lane == 0) mbar_arrive(&bars->p_full);
     }
 
-    // ---- epilogue ----
+    // ---- epilogue: this thread normalises and stores output columns [64*hf, 64*hf + 64) of its row ----
+    xchg[((n_kv & 1) * 2 + hf) * 128 + r] = l_run;   // parity slot not used by the last block's max exchange
     mbar_wait(&bars->pv_done, (n_kv - 1) & 1);
     tc_fence_after();
-    const float inv_l = 1.0f / l_run;
-    const uint32_t stage = aP + ew * 8192;  // this warp's 32 rows x 256 B (P is dead now)
+    named_bar_sync_256();
+    const float l_tot = xchg[((n_kv & 1) * 2) * 128 + r] + xchg[((n_kv & 1) * 2 + 1) * 128 + r];
+    const float inv_l = 1.0f / l_tot;
+    const uint32_t stage = aP + sw * 4096;  // this warp's 32 rows x 128 B (P is dead now)
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       uint32_t o[32];
-      tmem_ld_32x32b_x32(tO + lane_sel + c * 32, o);
+      tmem_ld_32x32b_x32(tO + lane_sel + hf * 64 + c * 32, o);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int piece = c * 4 + i;
-        const uint32_t addr = stage + lane * 256 + ((piece ^ (lane & 7)) << 4);
+        const uint32_t addr = stage + lane * 128 + ((piece ^ (lane & 7)) << 4);
         asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr),
                      "r"(pack_bf16(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l)),
                      "r"(pack_bf16(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l)),
@@ -263,18 +285,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int tok = seq0 + q0 + r;
     const int my_dst = (q0 + r < len) ? (out_row_map ? out_row_map[tok] : tok) : -1;
     // training: log2-domain log-sum-exp of the scaled scores, [heads, rows_cap] (read back by the backward kernels)
-    if (lse != nullptr && q0 + r < len)
-      lse[static_cast<int64_t>(h) * rows_cap + tok] = fmaf(m_run, scale_log2, log2f(l_run));
+    if (lse != nullptr && hf == 0 && q0 + r < len)
+      lse[static_cast<int64_t>(h) * rows_cap + tok] = fmaf(m_run, scale_log2, log2f(l_tot));
 #pragma unroll 4
-    for (int it = 0; it < 16; ++it) {  // 2 rows of 256 B per iteration, 16 lanes each
-      const int rr = it * 2 + (lane >> 4), piece = lane & 15;
+    for (int it = 0; it < 8; ++it) {  // 4 rows of 128 B per iteration, 8 lanes each
+      const int rr = it * 4 + (lane >> 3), piece = lane & 7;
       const int dst = __shfl_sync(0xffffffffu, my_dst, rr);
       if (dst >= 0) {
         uint4 v;
         asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
                      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                     : "r"(stage + rr * 256 + ((piece ^ (rr & 7)) << 4)));
-        *reinterpret_cast<uint4*>(out + static_cast<int64_t>(dst) * H + h * TC_D + piece * 8) = v;
+                     : "r"(stage + rr * 128 + ((piece ^ (rr & 7)) << 4)));
+        *reinterpret_cast<uint4*>(out + static_cast<int64_t>(dst) * H + h * TC_D + hf * 64 + piece * 8) = v;
       }
     }
   }

@@ -27,6 +27,31 @@ __global__ void __launch_bounds__(256) k7_gather_rows(const uint4* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// LoRA input dropout (PEFT lora.Linear: lora_A(dropout(x)), conf/lora.yaml lora_dropout = 0.05):
+//   out[r, c] = keep(r, c) ? bf16(x[r, c] * 1/(1-p)) : 0,  r < *n_rows, mask from dropout_hash(element index, seed)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k7_dropout_rows(const uint4* __restrict__ x, uint4* __restrict__ out, const int32_t* __restrict__ n_rows_ptr,
+                    int rows_cap, int vec_per_row, uint32_t thresh16, float scale, uint32_t seed_lo, uint32_t seed_hi) {
+  const int64_t n = static_cast<int64_t>(min(*n_rows_ptr, rows_cap)) * vec_per_row;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint4 v = ld_stream(x + i);
+    const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+    uint4 o;
+    uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // element pair 4 * i + j
+      const uint32_t hsh = dropout_hash(static_cast<uint64_t>(i) * 4 + j, seed_lo, seed_hi);
+      const float a = (hsh & 0xffffu) >= thresh16 ? bf16_lo(vv[j]) * scale : 0.f;
+      const float b = (hsh >> 16) >= thresh16 ? bf16_hi(vv[j]) * scale : 0.f;
+      op[j] = pack_bf16(a, b);
+    }
+    st_stream(out + i, o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // SwiGLU backward.  Forward (eager bf16): s = bf16(silu(g)), act = bf16(s * u).
 //   dup = bf16(dact * s);  ds = bf16(dact * u);  dgate = bf16(ds * sigma(g) * (1 + g * (1 - sigma(g))))
 // ---------------------------------------------------------------------------------------------
@@ -201,6 +226,20 @@ extern "C" int vex_gather_rows(const void* x, const int32_t* row_src, const int3
   const int grid = std::min(vex::ceil_div(rows_cap, 8), 148 * 8);
   vex::k7_gather_rows<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(x), row_src, n_rows, static_cast<uint4*>(out), rows_cap, H / 8);
+  VEX_LAUNCH_CHECK();
+  return VEX_OK;
+}
+
+extern "C" int vex_dropout_rows(const void* x, void* out, const int32_t* n_rows, int rows_cap, int K, float p,
+                                uint64_t seed, vexStream stream) {
+  if (!x || !out || !n_rows || rows_cap <= 0 || K <= 0 || !(p >= 0.f && p < 1.f)) return VEX_E_INVALID;
+  if (K % 8 != 0) return VEX_E_UNSUPPORTED;
+  const int64_t total = static_cast<int64_t>(rows_cap) * (K / 8);
+  const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 16));
+  const uint32_t thresh16 = static_cast<uint32_t>(p * 65536.0f + 0.5f);
+  vex::k7_dropout_rows<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<uint4*>(out), n_rows, rows_cap, K / 8, thresh16, 1.0f / (1.0f - p),
+      static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
   VEX_LAUNCH_CHECK();
   return VEX_OK;
 }

@@ -236,8 +236,28 @@ def _fuse_default() -> bool:
     return os.environ.get("VEX_FUSE_EPILOGUE", "1") != "0"
 
 
-def _lora_t(x_sorted: torch.Tensor, specs: Tuple[LinearSpec, LinearSpec], counts: torch.Tensor):
-    """T = scaling * x . lora_A^T for the (vision, language) pair; returns (T or None, r, [B_v, B_l])."""
+_dropout_calls = 0
+
+
+def next_dropout_seed() -> int:
+    """Base seed of one layer call's LoRA dropout masks: a function of ``torch.initial_seed()`` and a call counter,
+    so runs are reproducible under ``torch.manual_seed`` (no device sync, no generator state consumed)."""
+    global _dropout_calls
+    _dropout_calls += 1
+    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + _dropout_calls * 0xD1B54A32D192ED03) & 0x7FFFFFFFFFFFFFFF
+
+
+def dropout_stream_seed(base_seed: int, stream: int) -> int:
+    """Seed of dropout stream ``stream`` (0 qkv, 1 dense, 2 gate, 3 up, 4 down: one nn.Dropout per wrapped Linear)."""
+    return (base_seed + (stream + 1) * 0xA0761D6478BD642F) & 0x7FFFFFFFFFFFFFFF  # torch.library ints are int64
+
+
+def _lora_t(x_sorted: torch.Tensor, specs: Tuple[LinearSpec, LinearSpec], counts: torch.Tensor, *,
+            n_valid: Optional[torch.Tensor] = None, seed: Optional[int] = None, stream: int = 0,
+            keep: Optional[dict] = None, name: str = ""):
+    """T = scaling * dropout(x) . lora_A^T for the (vision, language) pair; returns (T or None, r, [B_v, B_l]).
+    With an active ``lora_dropout`` (wrapper in training mode) the LoRA branch reads a dropped copy of x
+    (PEFT: lora_B(lora_A(dropout(x))) * scaling), kept in ``keep[name + '_xd']`` for the weight gradient."""
     sv, sl = specs
     if sv.lora_A is None and sl.lora_A is None:
         return None, 0, [None, None]
@@ -248,17 +268,26 @@ def _lora_t(x_sorted: torch.Tensor, specs: Tuple[LinearSpec, LinearSpec], counts
     if r % 8 or r > 64:
         raise NotImplementedError(f"LoRA rank {r}: the fused K-extension handles multiples of 8 up to 64")
     both = sl.lora_A is not None
-    if both and (sl.r != r or sl.scaling != sv.scaling):
-        raise NotImplementedError("vision and language adapters must share rank and scaling")
+    if both and (sl.r != r or sl.scaling != sv.scaling or sl.dropout != sv.dropout):
+        raise NotImplementedError("vision and language adapters must share rank, scaling and dropout")
+    x_in = x_sorted
+    if sv.dropout > 0:
+        if seed is None or n_valid is None:
+            raise RuntimeError("LoRA dropout is active but no seed was provided")
+        x_in = torch.empty_like(x_sorted)
+        ops.dropout_rows(x_sorted, n_valid, x_in, sv.dropout, dropout_stream_seed(seed, stream))
+        if keep is not None:
+            keep[name + "_xd"] = x_in
     t = torch.empty(x_sorted.shape[0], r, dtype=torch.bfloat16, device=x_sorted.device)
-    ops.grouped_gemm(x_sorted, _bf16(sv.lora_A), _bf16(sl.lora_A) if both else None, t, counts, None,
+    ops.grouped_gemm(x_in, _bf16(sv.lora_A), _bf16(sl.lora_A) if both else None, t, counts, None,
                      float(sv.scaling))
     return t, r, [_bf16(sv.lora_B), _bf16(sl.lora_B) if both else None]
 
 
 def visual_expert_layer_forward(layer: "CogVLMDecoderLayer", hidden_states: torch.Tensor, plan: RoutingPlan,
                                 position_ids: torch.Tensor, *, use_cache: bool = False,
-                                fuse_epilogue: Optional[bool] = None, keep: Optional[dict] = None):
+                                fuse_epilogue: Optional[bool] = None, keep: Optional[dict] = None,
+                                dropout_seed: Optional[int] = None):
     """The whole layer on the device; returns (out [B, L, H], present_kv or None).  ``keep`` (training recompute):
     a dict that receives the intermediates the backward needs (gate/up are then materialised separately, the
     attention also writes its log-sum-exp, and the call returns (None, None) right before the down projection)."""
@@ -279,6 +308,10 @@ def visual_expert_layer_forward(layer: "CogVLMDecoderLayer", hidden_states: torc
     up_s = (resolve_linear(mlp.vision_mlp.up_proj), resolve_linear(mlp.language_mlp.up_proj))
     down_s = (resolve_linear(mlp.vision_mlp.down_proj), resolve_linear(mlp.language_mlp.down_proj))
     W = lambda pair: [_bf16(pair[0].weight), None, _bf16(pair[1].weight), None]
+    if dropout_seed is None and any(sp[0].dropout > 0 for sp in (qkv_s, dense_s, gate_s, up_s, down_s)):
+        dropout_seed = next_dropout_seed()  # wrappers in training mode: nn.Dropout would be active
+    lt = lambda x, sp, k, nm: _lora_t(x, sp, counts, n_valid=plan.n_valid, seed=dropout_seed, stream=k, keep=keep,
+                                      name=nm)
 
     # ---- attention block ----
     xn = new(cap, H)
@@ -286,10 +319,10 @@ def visual_expert_layer_forward(layer: "CogVLMDecoderLayer", hidden_states: torc
     cos, sin = attn.rotary_emb.tables(max(L, attn.max_position_embeddings), dev, torch.bfloat16)
     pos_flat = position_ids.reshape(-1)
     qkv = new(cap, 3 * H)  # token order: row t = [q(heads*128) | k | v], q and k rotated
-    t, r, lb = _lora_t(xn, qkv_s, counts)
+    t, r, lb = lt(xn, qkv_s, 0, "qkv")
     if keep is not None:
         keep.update(xn1=xn, t_qkv=t, specs=dict(qkv=qkv_s, dense=dense_s, gate=gate_s, up=up_s, down=down_s),
-                    ln1=ln1, ln2=ln2, cos=cos, sin=sin)
+                    ln1=ln1, ln2=ln2, cos=cos, sin=sin, dropout_seed=dropout_seed)
         xn = new(cap, H)  # the second norm gets its own buffer (xn1 is needed by the backward)
     ops.grouped_gemm_fused(keep["xn1"] if keep is not None else xn, W(qkv_s), qkv, counts, ops.EPI_ROPE, plan.sorted_to_token, None, [t, None],
                            [lb[0], None, lb[1], None], r, [cos, sin, pos_flat, s2f], 2 * H, False, 1.0)
@@ -301,7 +334,7 @@ def visual_expert_layer_forward(layer: "CogVLMDecoderLayer", hidden_states: torc
         ops.attention(qkv, plan.cu_seqlens, B, L, heads, plan.token_to_sorted, ctx, HEAD_DIM ** -0.5)
     h1 = new(B, L, H)
     ops.copy_padded_rows(hf, plan.flat_to_sorted, h1.view(cap, H))
-    t, r, lb = _lora_t(ctx, dense_s, counts)
+    t, r, lb = lt(ctx, dense_s, 1, "dense")
     if keep is not None:
         keep.update(qkv=qkv, ctx=ctx, t_dense=t)
     if fuse:
@@ -316,8 +349,8 @@ def visual_expert_layer_forward(layer: "CogVLMDecoderLayer", hidden_states: torc
     # ---- MLP block ----
     ops.rmsnorm_gather(h1.view(cap, H), ln2.weight.detach(), ln2.variance_epsilon, s2f, plan.n_valid, xn)
     act = new(cap, I)
-    tg, rg, lbg = _lora_t(xn, gate_s, counts)
-    tu, ru, lbu = _lora_t(xn, up_s, counts)
+    tg, rg, lbg = lt(xn, gate_s, 2, "gate")
+    tu, ru, lbu = lt(xn, up_s, 3, "up")
     if (tg is None) != (tu is None) or rg != ru:
         raise NotImplementedError("gate_proj and up_proj adapters must come in pairs of equal rank")
     if keep is not None:
@@ -335,7 +368,7 @@ def visual_expert_layer_forward(layer: "CogVLMDecoderLayer", hidden_states: torc
         ops.silu_mul(g, u, plan.n_valid, act)
         if keep is not None:
             keep.update(gate=g, up=u)
-    t, r, lb = _lora_t(act, down_s, counts)
+    t, r, lb = lt(act, down_s, 4, "down")
     if keep is not None:  # the recompute stops here: the down projection's output is not needed by the backward
         keep.update(act=act, t_down=t, h1=h1)
         return None, None

@@ -11,7 +11,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib, instrument
-from ._lib import EPI_PLAIN, EPI_RESIDUAL, EPI_ROPE, EPI_SWIGLU, GemmArgs  # noqa: F401
+from ._lib import EPI_DROPOUT_ACC, EPI_PLAIN, EPI_RESIDUAL, EPI_ROPE, EPI_SWIGLU, GemmArgs  # noqa: F401
 
 _BF16 = torch.bfloat16
 
@@ -141,7 +141,8 @@ def grouped_gemm_raw(a: torch.Tensor, w: Sequence[Optional[torch.Tensor]], out: 
                      lora_t: Sequence[Optional[torch.Tensor]] = (None, None),
                      lora_b: Sequence[Optional[torch.Tensor]] = (None, None, None, None), lora_r: int = 0,
                      rope: Optional[tuple] = None, rope_cols: int = 0, single_expert: bool = False,
-                     alpha: float = 1.0, n_out: Optional[int] = None, w_transposed: bool = False) -> None:
+                     alpha: float = 1.0, n_out: Optional[int] = None, w_transposed: bool = False,
+                     dropout_p: float = 0.0, dropout_seed: int = 0) -> None:
     """K3 (vex_grouped_gemm).  ``w`` = [vision_w0, vision_w1, language_w0, language_w1] ([N, K] each; the *_w1
     entries are up_proj for SWIGLU, else None).  ``lora_b`` likewise; ``lora_t`` = [T_half0, T_half1].
     ``rope`` = (cos [S,128], sin [S,128], position_ids int64 [B*L], sorted_to_flat int32).
@@ -194,7 +195,7 @@ def grouped_gemm_raw(a: torch.Tensor, w: Sequence[Optional[torch.Tensor]], out: 
         if residual.shape[-1] != out.shape[-1]:
             raise ValueError("residual/out layout mismatch")
         args.residual = residual.data_ptr()
-    elif mode == EPI_RESIDUAL:
+    elif mode in (EPI_RESIDUAL, EPI_DROPOUT_ACC):
         args.residual = out.data_ptr()  # in place: out[row] += acc (each 16-byte piece is read then written once)
     if rope is not None:
         cos, sin, pos, s2f = rope
@@ -208,7 +209,8 @@ def grouped_gemm_raw(a: torch.Tensor, w: Sequence[Optional[torch.Tensor]], out: 
     args.rows_cap, args.N, args.K, args.mode = rows_cap, (n_out or N), K, mode
     args.single_expert = int(single_expert)
     args.alpha = alpha
-    name = ("gemm_plain", "gemm_rope", "gemm_swiglu", "gemm_residual")[mode] + ("_n64" if N <= 64 else "") + \
+    args.dropout_p, args.dropout_seed = float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF
+    name = ("gemm_plain", "gemm_rope", "gemm_swiglu", "gemm_residual", "gemm_dropout_acc")[mode] + ("_n64" if N <= 64 else "") + \
         ("_dgrad" if w_transposed else "")
     with instrument.region(name):
       rc = _lib.lib().vex_grouped_gemm(C.byref(args), _stream())
@@ -238,17 +240,25 @@ def grouped_gemm_fused(a: torch.Tensor, w: List[Optional[torch.Tensor]], out: to
 @torch.library.custom_op("vex::grouped_gemm_dgrad", mutates_args=("out",))
 def grouped_gemm_dgrad(dy: torch.Tensor, w: List[Optional[torch.Tensor]], out: torch.Tensor, counts: torch.Tensor,
                        accumulate: bool, row_map: Optional[torch.Tensor], lora_dt: Optional[torch.Tensor],
-                       lora_a: List[Optional[torch.Tensor]], lora_r: int, single_expert: bool, alpha: float) -> None:
+                       lora_a: List[Optional[torch.Tensor]], lora_r: int, single_expert: bool, alpha: float,
+                       dropout_p: float = 0.0, dropout_seed: int = 0) -> None:
     """Backward of the routed Linear w.r.t. its input (what autograd computes for modeling_cogvlm.py:244-245,
     :278-279, :96-97): out[map(r)] (+)= dy[r] . W_e (+ dT[r] . A_e), with ``w`` = [vision W, language W] as STORED
     ([out_features, in_features]; read as an MN-major B operand, no transposed copy), ``lora_dt`` = scaling * dy .
     lora_B and ``lora_a`` = [vision lora_A, language lora_A] ([r, in_features]).  ``accumulate`` adds onto ``out``
-    in place (second term of d(xn) = dgate . Wg + dup . Wu)."""
+    in place (second term of d(xn) = dgate . Wg + dup . Wu).  ``dropout_p`` > 0 (with ``accumulate``): the product is
+    masked with the LoRA input-dropout mask of ``dropout_seed`` and scaled by 1 / (1 - p) before it is added --
+    out += keep * (dT . A) / (1 - p), the adjoint of lora_A(dropout(x))."""
     wv, wl = (list(w) + [None])[:2]
     av, al = (list(lora_a) + [None, None])[:2]
-    grouped_gemm_raw(dy, [wv, None, wl, None], out, counts, EPI_RESIDUAL if accumulate else EPI_PLAIN, row_map=row_map,
+    mode = EPI_RESIDUAL if accumulate else EPI_PLAIN
+    if dropout_p > 0:
+        if not accumulate:
+            raise ValueError("the dropout-masked dgrad accumulates onto `out`")
+        mode = EPI_DROPOUT_ACC
+    grouped_gemm_raw(dy, [wv, None, wl, None], out, counts, mode, row_map=row_map,
                      lora_t=[lora_dt, None], lora_b=[av, None, al, None], lora_r=lora_r, single_expert=single_expert,
-                     alpha=alpha, w_transposed=True)
+                     alpha=alpha, w_transposed=True, dropout_p=dropout_p, dropout_seed=dropout_seed)
 
 
 # ------------------------------------------------------------------------------------------ K4
@@ -349,6 +359,20 @@ def gather_rows(x: torch.Tensor, row_src: Optional[torch.Tensor], n_rows: torch.
     _lib.check(rc, "vex_gather_rows")
 
 
+@torch.library.custom_op("vex::dropout_rows", mutates_args=("out",))
+def dropout_rows(x: torch.Tensor, n_rows: torch.Tensor, out: torch.Tensor, p: float, seed: int) -> None:
+    """LoRA input dropout (vex_dropout_rows): out = keep ? x / (1 - p) : 0 on the first *n_rows rows, mask from a
+    counter-based hash of (row * K + col, seed) -- PEFT lora.Linear: lora_A(dropout(x))."""
+    _dev(x, "x", _BF16), _dev(out, "out", _BF16), _dev(n_rows, "n_rows", torch.int32)
+    if x.shape != out.shape:
+        raise ValueError("x / out shapes differ")
+    K = x.shape[-1]
+    with instrument.region("dropout_rows"):
+      rc = _lib.lib().vex_dropout_rows(x.data_ptr(), out.data_ptr(), n_rows.data_ptr(), x.numel() // K, K, float(p),
+                                       int(seed) & 0xFFFFFFFFFFFFFFFF, _stream())
+    _lib.check(rc, "vex_dropout_rows")
+
+
 @torch.library.custom_op("vex::silu_mul_backward", mutates_args=("dgate", "dup"))
 def silu_mul_backward(dact: torch.Tensor, gate: torch.Tensor, up: torch.Tensor, n_rows: torch.Tensor,
                       dgate: torch.Tensor, dup: torch.Tensor) -> None:
@@ -416,6 +440,6 @@ def lora_wgrad(x: torch.Tensor, y: torch.Tensor, out_vision: Optional[torch.Tens
     _lib.check(rc, "vex_lora_wgrad")
 
 
-for _op in (attention_train, attention_backward, lora_wgrad, gather_rows, silu_mul_backward, rmsnorm_backward, grouped_gemm_dgrad, attention_decode, partition, rmsnorm_gather, silu_mul, residual_scatter, copy_padded_rows, grouped_gemm, grouped_gemm_fused,
+for _op in (dropout_rows, attention_train, attention_backward, lora_wgrad, gather_rows, silu_mul_backward, rmsnorm_backward, grouped_gemm_dgrad, attention_decode, partition, rmsnorm_gather, silu_mul, residual_scatter, copy_padded_rows, grouped_gemm, grouped_gemm_fused,
             attention):
     _op.register_fake(lambda *a, **k: None)

@@ -29,6 +29,7 @@ class LinearSpec:
     lora_A: Optional[torch.Tensor] = None  # [r, in]
     lora_B: Optional[torch.Tensor] = None  # [out, r]
     scaling: float = 1.0
+    dropout: float = 0.0                 # p of lora_dropout when the wrapper is in training mode, else 0
 
     @property
     def r(self) -> int:
@@ -66,8 +67,9 @@ def resolve_linear(mod: nn.Module) -> LinearSpec:
             raise NotImplementedError("DoRA adapters are not supported")
         drop = mod.lora_dropout[name] if hasattr(mod, "lora_dropout") and name in mod.lora_dropout else None
         if mod.training and isinstance(drop, nn.Dropout) and drop.p > 0:
-            raise NotImplementedError("LoRA dropout (training mode) is not implemented by the fused forward; "
-                                      "call .eval() or set lora_dropout=0")
+            if drop.p >= 1:
+                raise ValueError("lora_dropout must be < 1")
+            spec.dropout = float(drop.p)  # active exactly when nn.Dropout would be (module in training mode)
         spec.lora_A = mod.lora_A[name].weight
         spec.lora_B = mod.lora_B[name].weight
         spec.scaling = float(mod.scaling[name])
@@ -149,7 +151,7 @@ class MockModulesToSave(nn.Module):
 
 
 def attach_mock_lora(layer: nn.Module, r: int = 64, lora_alpha: float = 8, b_std: float = 0.02,
-                     lora_lang: bool = True, wrap_norms: bool = True) -> nn.Module:
+                     lora_lang: bool = True, wrap_norms: bool = True, lora_dropout: float = 0.0) -> nn.Module:
     """Wraps a decoder layer's children the way ``get_peft_model`` would with the targets of
     mmmm/utils.py:19-43: all ten Linears (vision-only when ``lora_lang`` is False,
     modeling_cogvlm.py:79-85, :211-220) and both RMSNorms as modules_to_save."""
@@ -157,7 +159,8 @@ def attach_mock_lora(layer: nn.Module, r: int = 64, lora_alpha: float = 8, b_std
         p.requires_grad_(False)
 
     def wrap(parent, name):
-        setattr(parent, name, MockLoraLinear(getattr(parent, name), r=r, lora_alpha=lora_alpha, b_std=b_std))
+        setattr(parent, name, MockLoraLinear(getattr(parent, name), r=r, lora_alpha=lora_alpha, b_std=b_std,
+                                             lora_dropout=lora_dropout))
 
     wrap(layer.self_attn, "vision_expert_query_key_value")
     wrap(layer.self_attn, "vision_expert_dense")

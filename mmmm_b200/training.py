@@ -53,12 +53,16 @@ class _GradSink:
 
 def _routed_linear_backward(dy: torch.Tensor, x: torch.Tensor, t: Optional[torch.Tensor],
                             pair: Tuple[LinearSpec, LinearSpec], counts: torch.Tensor, out: torch.Tensor,
-                            sink: _GradSink, *, accumulate: bool = False, row_map: Optional[torch.Tensor] = None):
-    """Backward of the routed (vision / language) Linear + LoRA: y = x W_e^T + T B_e^T with T = s x A_e^T.
-        dx = dy W_e + dT A_e   (dT = s dy B_e)        dB_e = dy^T T        dA_e = dT^T x
-    ``dy`` / ``x`` / ``t`` are expert-sorted [cap, *]; ``out`` receives dx (through ``row_map`` / accumulated)."""
+                            sink: _GradSink, *, accumulate: bool = False, row_map: Optional[torch.Tensor] = None,
+                            x_dropped: Optional[torch.Tensor] = None, dropout_seed: int = 0):
+    """Backward of the routed (vision / language) Linear + LoRA: y = x W_e^T + T B_e^T with T = s drop(x) A_e^T.
+        dx = dy W_e + mask/(1-p) * (dT A_e)   (dT = s dy B_e)        dB_e = dy^T T        dA_e = dT^T drop(x)
+    ``dy`` / ``x`` / ``t`` are expert-sorted [cap, *]; ``out`` receives dx (through ``row_map`` / accumulated).
+    Without dropout the LoRA term rides in the main GEMM as a K-extension; with dropout (``x_dropped`` = the
+    forward's dropped copy of x) it is a second, mask-applying accumulate pass (VEX_EPI_DROPOUT_ACC)."""
     sv, sl = pair
     both = sl.lora_A is not None
+    p_drop = sv.dropout if sv.lora_A is not None else 0.0
     dt, r, lora_a = None, 0, [None, None]
     if sv.lora_A is not None:
         r = sv.r
@@ -72,14 +76,22 @@ def _routed_linear_backward(dy: torch.Tensor, x: torch.Tensor, t: Optional[torch
         if gB[0] is not None or gB[1] is not None:
             ops.lora_wgrad(dy, t, gB[0], gB[1], False, counts)
         if gA[0] is not None or gA[1] is not None:
-            ops.lora_wgrad(x, dt, gA[0], gA[1], True, counts)
-    ops.grouped_gemm_dgrad(dy, [_bf16(sv.weight), _bf16(sl.weight)], out, counts, accumulate, row_map, dt, lora_a, r,
-                           False, 1.0)
+            ops.lora_wgrad(x_dropped if p_drop > 0 else x, dt, gA[0], gA[1], True, counts)
+    if p_drop > 0:
+        ops.grouped_gemm_dgrad(dy, [_bf16(sv.weight), _bf16(sl.weight)], out, counts, accumulate, row_map, None,
+                               [None, None], 0, False, 1.0)
+        ops.grouped_gemm_dgrad(dt, lora_a, out, counts, True, row_map, None, [None, None], 0, not both, 1.0,
+                               p_drop, dropout_seed)
+    else:
+        ops.grouped_gemm_dgrad(dy, [_bf16(sv.weight), _bf16(sl.weight)], out, counts, accumulate, row_map, dt, lora_a,
+                               r, False, 1.0)
 
 
-def layer_backward(layer, plan, position_ids: torch.Tensor, hidden_states: torch.Tensor, d_out: torch.Tensor):
-    """Returns (d_hidden [B, L, H], [(param, grad), ...]) -- see the module docstring."""
-    from .modeling_cogvlm import visual_expert_layer_forward
+def layer_backward(layer, plan, position_ids: torch.Tensor, hidden_states: torch.Tensor, d_out: torch.Tensor,
+                   dropout_seed: Optional[int] = None):
+    """Returns (d_hidden [B, L, H], [(param, grad), ...]) -- see the module docstring.  ``dropout_seed``: the seed the
+    forward used for the LoRA dropout masks (the recompute and the dgrad epilogues regenerate them from it)."""
+    from .modeling_cogvlm import dropout_stream_seed, visual_expert_layer_forward
     B, L, H = hidden_states.shape
     cap = B * L
     attn, mlp = layer.self_attn, layer.mlp
@@ -88,8 +100,10 @@ def layer_backward(layer, plan, position_ids: torch.Tensor, hidden_states: torch
     dev = hidden_states.device
     keep: Dict = {}
     with torch.no_grad():
-        visual_expert_layer_forward(layer, hidden_states, plan, position_ids, keep=keep)
+        visual_expert_layer_forward(layer, hidden_states, plan, position_ids, keep=keep, dropout_seed=dropout_seed)
     specs = keep["specs"]
+    seed = keep.get("dropout_seed") or 0
+    drop = lambda nm, k: dict(x_dropped=keep.get(nm + "_xd"), dropout_seed=dropout_stream_seed(seed, k))
     counts, s2f, n_valid = plan.counts, plan.sorted_to_flat, plan.n_valid
     new = lambda *shape: torch.empty(*shape, dtype=torch.bfloat16, device=dev)
     sink = _GradSink()
@@ -100,13 +114,14 @@ def layer_backward(layer, plan, position_ids: torch.Tensor, hidden_states: torch
     ops.gather_rows(dof, s2f, n_valid, dy)
     # ---- MLP block ----
     dact = new(cap, I)
-    _routed_linear_backward(dy, keep["act"], keep["t_down"], specs["down"], counts, dact, sink)
+    _routed_linear_backward(dy, keep["act"], keep["t_down"], specs["down"], counts, dact, sink, **drop("down", 4))
     dg, du = new(cap, I), new(cap, I)
     ops.silu_mul_backward(dact, keep["gate"], keep["up"], n_valid, dg, du)
     del dact
     dxn2 = new(cap, H)
-    _routed_linear_backward(dg, keep["xn2"], keep["t_gate"], specs["gate"], counts, dxn2, sink)
-    _routed_linear_backward(du, keep["xn2"], keep["t_up"], specs["up"], counts, dxn2, sink, accumulate=True)
+    _routed_linear_backward(dg, keep["xn2"], keep["t_gate"], specs["gate"], counts, dxn2, sink, **drop("gate", 2))
+    _routed_linear_backward(du, keep["xn2"], keep["t_up"], specs["up"], counts, dxn2, sink, accumulate=True,
+                            **drop("up", 3))
     del dg, du
     ln1, ln2 = keep["ln1"], keep["ln2"]
     dh1 = new(cap, H)                                                  # grad w.r.t. h1 rows (sorted): dy + norm branch
@@ -115,14 +130,14 @@ def layer_backward(layer, plan, position_ids: torch.Tensor, hidden_states: torch
     # ---- attention block ----
     dctx_tok = new(cap, H)                                             # token order (K9 zeroes its tail rows)
     _routed_linear_backward(dh1, keep["ctx"], keep["t_dense"], specs["dense"], counts, dctx_tok, sink,
-                            row_map=plan.sorted_to_token)
+                            row_map=plan.sorted_to_token, **drop("dense", 1))
     dqkv = new(cap, 3 * H)                                             # d(pre-rotary q | k | v), sorted order
     delta = torch.empty(heads, cap, dtype=torch.float32, device=dev)
     ops.attention_backward(keep["qkv"], keep["ctx"], dctx_tok, keep["lse"], delta, plan.cu_seqlens,
                            plan.token_to_sorted, plan.token_to_flat, position_ids.reshape(-1), keep["cos"], keep["sin"],
                            B, L, heads, dqkv, HEAD_DIM ** -0.5)
     dxn1 = dxn2                                                        # reuse
-    _routed_linear_backward(dqkv, keep["xn1"], keep["t_qkv"], specs["qkv"], counts, dxn1, sink)
+    _routed_linear_backward(dqkv, keep["xn1"], keep["t_qkv"], specs["qkv"], counts, dxn1, sink, **drop("qkv", 0))
     d_hidden = torch.empty_like(d_out)
     ops.copy_padded_rows(dof, plan.flat_to_sorted, d_hidden.view(cap, H))   # padded rows: identity path only
     ops.rmsnorm_backward(dxn1, hf, s2f, ln1.weight.detach(), ln1.variance_epsilon, dh1, None, d_hidden.view(cap, H), s2f,
@@ -141,9 +156,11 @@ def trainable_tensors(layer) -> List[torch.Tensor]:
 class _LayerFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, layer, plan, position_ids, hidden_states, *trainables):
-        from .modeling_cogvlm import visual_expert_layer_forward
+        from .modeling_cogvlm import next_dropout_seed, visual_expert_layer_forward
+        ctx.dropout_seed = next_dropout_seed()  # the backward's recompute must regenerate the same LoRA dropout masks
         with torch.no_grad():
-            out, _ = visual_expert_layer_forward(layer, hidden_states, plan, position_ids)
+            out, _ = visual_expert_layer_forward(layer, hidden_states, plan, position_ids,
+                                                 dropout_seed=ctx.dropout_seed)
         ctx.layer, ctx.plan, ctx.position_ids = layer, plan, position_ids
         ctx.trainables = trainables
         ctx.save_for_backward(hidden_states)
@@ -153,7 +170,8 @@ class _LayerFunction(torch.autograd.Function):
     def backward(ctx, d_out):
         (hidden_states,) = ctx.saved_tensors
         with torch.no_grad():
-            d_hidden, pg = layer_backward(ctx.layer, ctx.plan, ctx.position_ids, hidden_states, d_out.contiguous())
+            d_hidden, pg = layer_backward(ctx.layer, ctx.plan, ctx.position_ids, hidden_states, d_out.contiguous(),
+                                          ctx.dropout_seed)
         by_id = {id(p): g for p, g in pg}
         tr = tuple(by_id.get(id(p)) for p in ctx.trainables)
         return (None, None, None, d_hidden if ctx.needs_input_grad[3] else None, *tr)

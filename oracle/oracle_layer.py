@@ -103,12 +103,19 @@ class LoRA:
     A: torch.Tensor  # [r, in]
     B: torch.Tensor  # [out, r]
     scaling: float = 1.0
+    # training mode: PEFT computes lora_B(lora_A(lora_dropout(x))) (conf/lora.yaml: lora_dropout 0.05).  The mask is an
+    # explicit input here -- entries 0 or 1 / (1 - p), same shape as the rows this Linear sees -- so a test can hand the
+    # oracle the very mask the CUDA path generated (PyTorch's own Philox stream is not reproducible across devices).
+    drop_mask: Optional[torch.Tensor] = None
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, lora: Optional[LoRA] = None) -> torch.Tensor:
     y = F.linear(x, w)
     if lora is not None:
-        delta = F.linear(F.linear(x.to(lora.A.dtype), lora.A), lora.B) * lora.scaling
+        xl = x.to(lora.A.dtype)
+        if lora.drop_mask is not None:
+            xl = (xl * lora.drop_mask.to(xl.dtype)).to(xl.dtype)
+        delta = F.linear(F.linear(xl, lora.A), lora.B) * lora.scaling
         y = (y + delta).to(y.dtype)
     return y
 

@@ -139,6 +139,59 @@ def test_k7_gather_rows():
     assert (out[61:] == 5.0).all()
 
 
+def test_k7_dropout_rows_mask_properties():
+    """LoRA input dropout: Bernoulli(1 - p) keep mask from a counter-based hash -- reproducible per seed, different
+    across seeds, kept values scaled by 1 / (1 - p) with one bf16 rounding, rows past the live count untouched."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(13)
+    rows, n, K, p = 700, 650, 4096, 0.05
+    x = torch.randn(rows, K, generator=g).bfloat16().cuda()
+    nr = torch.tensor([n], dtype=torch.int32).cuda()
+    out = torch.full_like(x, 9.0)
+    ops.dropout_rows(x, nr, out, p, 1234567890123)
+    keep = out[:n] != 0
+    frac = float(keep.float().mean())
+    assert abs(frac - (1 - p)) < 2e-3, frac
+    want = (x[:n].float() * (1.0 / (1.0 - p))).bfloat16()
+    assert torch.equal(out[:n][keep], want[keep])
+    assert (out[n:] == 9.0).all()
+    # per-row and per-column keep rates stay close to 1 - p (no stripes)
+    assert float((keep.float().mean(0) - (1 - p)).abs().max()) < 0.05
+    assert float((keep.float().mean(1) - (1 - p)).abs().max()) < 0.03
+    out2 = torch.empty_like(x)
+    ops.dropout_rows(x, nr, out2, p, 1234567890123)
+    assert torch.equal(out2[:n], out[:n])
+    ops.dropout_rows(x, nr, out2, p, 1234567890124)
+    agree = float(((out2[:n] != 0) == keep).float().mean())
+    assert abs(agree - ((1 - p) ** 2 + p ** 2)) < 5e-3, agree        # independent masks
+    ops.dropout_rows(x, nr, out2, 0.0, 5)
+    assert torch.equal(out2[:n], x[:n])
+
+
+@pytest.mark.parametrize("single", [False, True])
+def test_k3_dgrad_dropout_accumulate_epilogue(single, gemm_kernel):
+    """out += mask / (1 - p) * (dT . A): the mask the epilogue regenerates must be the one vex_dropout_rows drew."""
+    ops = _ops()
+    Tv, Tl, N, r, p, seed = 300, 0 if single else 170, 768, 64, 0.25, 987654321987
+    g = torch.Generator().manual_seed(14)
+    T = Tv + Tl
+    cap = T + 6
+    dt = torch.randn(cap, r, generator=g).bfloat16().cuda()
+    Av = (torch.randn(r, N, generator=g) * 0.2).bfloat16().cuda()
+    Al = (torch.randn(r, N, generator=g) * 0.2).bfloat16().cuda()
+    base = torch.randn(cap, N, generator=g).bfloat16().cuda()
+    counts = torch.tensor([Tv, Tl, T, 0], dtype=torch.int32).cuda()
+    ones = torch.ones(cap, N, dtype=torch.bfloat16).cuda()
+    mask = torch.zeros_like(ones)
+    ops.dropout_rows(ones, counts[2:3], mask, p, seed)                 # 0 or 1 / (1 - p)
+    out = base.clone()
+    ops.grouped_gemm_dgrad(dt, [Av, None if single else Al], out, counts, True, None, None, [None, None], 0, single,
+                           1.0, p, seed)
+    want = base.float().clone()
+    want[:T] += (mask[:T].float() * _ref_dgrad(dt, Av, Al, Tv, Tl)[:T]).bfloat16().float()
+    torch.testing.assert_close(out.float(), want, rtol=1e-2, atol=3e-2)
+
+
 def test_k7_silu_mul_backward_vs_autograd():
     """Adjoint of the eager bf16 act_fn(gate) * up (modeling_cogvlm.py:55) against torch.autograd on CPU."""
     ops = _ops()

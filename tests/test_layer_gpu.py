@@ -364,3 +364,78 @@ def test_training_step_gradients_vs_oracle_autograd(lora_lang):
           wf["post_attention_layernorm.weight"].grad, "ln2")
     if not lora_lang:   # language adapters do not exist: nothing else received a gradient
         assert all(p.grad is None for n, p in layer.named_parameters() if not p.requires_grad)
+
+
+def test_training_step_with_lora_dropout_vs_oracle_autograd(monkeypatch):
+    """The reference trains with lora_dropout = 0.05 (conf/lora.yaml): PEFT applies nn.Dropout to the LoRA branch's
+    input of every wrapped Linear.  The fused path draws its own counter-based masks (K7) -- extracted here by running
+    the same kernel over ones -- and the oracle gets exactly those masks: forward output and all gradients must agree."""
+    from mmmm_b200 import modeling_cogvlm as M, ops
+    from mmmm_b200.inputs import make_inputs
+    from mmmm_b200.peft_compat import attach_mock_lora
+    from mmmm_b200.plan import build_plan
+    H, I, heads, r, p_drop, base_seed = 512, 768, 4, 32, 0.2, 0x1234ABCD5678
+    w = O.random_weights(H, I, heads, seed=41, dtype=torch.bfloat16)
+    ad = O.random_lora(H, I, r=r, seed=42, dtype=torch.bfloat16, b_std=0.05)
+    layer = M.CogVLMDecoderLayer(M.VexConfig(hidden_size=H, intermediate_size=I, num_attention_heads=heads))
+    layer.load_state_dict(w)
+    layer = layer.to(torch.bfloat16).cuda()
+    attach_mock_lora(layer, r=r, lora_dropout=p_drop)
+    for path, a in ad.items():
+        m = layer.get_submodule(path)
+        m.lora_A["default"].weight.data.copy_(a.A)
+        m.lora_B["default"].weight.data.copy_(a.B)
+        m.scaling["default"] = a.scaling
+    layer.train()
+    monkeypatch.setattr(M, "next_dropout_seed", lambda: base_seed)
+    inp = make_inputs(2, 90, 30, H, ragged=True, seed=43)
+    pm = inp.padding_mask
+    proj = torch.randn(inp.hidden_states.shape, generator=torch.Generator().manual_seed(44)).bfloat16() * pm[..., None]
+    x = inp.hidden_states.cuda().requires_grad_(True)
+    (out,) = layer(x, token_type_ids=inp.token_type_ids.cuda(), position_ids=inp.position_ids.cuda(),
+                   padding_mask=pm.cuda())
+    (out.float() * proj.cuda().float()).sum().backward()
+    # eval mode: dropout off, output differs from the training-mode one
+    layer.eval()
+    with torch.no_grad():
+        (out_eval,) = layer(x.detach(), token_type_ids=inp.token_type_ids.cuda(), position_ids=inp.position_ids.cuda(),
+                            padding_mask=pm.cuda())
+    assert not torch.equal(out_eval, out.detach())
+
+    # masks of the five dropout streams, in sorted row order, split per expert
+    plan = build_plan(inp.token_type_ids.cuda(), pm.cuda())
+    Tv, Tl, T = plan.counts.cpu().tolist()[:3]
+    cap = pm.numel()
+    masks = {}
+    for stream, (name, width) in enumerate((("qkv", H), ("dense", H), ("gate", H), ("up", H), ("down", I))):
+        ones = torch.ones(cap, width, dtype=torch.bfloat16).cuda()
+        m = torch.zeros_like(ones)
+        ops.dropout_rows(ones, plan.n_valid, m, p_drop, M.dropout_stream_seed(base_seed, stream))
+        masks[name] = m.cpu().float()
+    which = {"query_key_value": "qkv", "dense": "dense", "gate_proj": "gate", "up_proj": "up", "down_proj": "down"}
+    wf = {k: v.float() for k, v in w.items()}
+    adf = {}
+    for path, a in ad.items():
+        mk = masks[next(v for k, v in which.items() if k in path)]
+        sl = mk[:Tv] if "vision" in path else mk[Tv:T]
+        adf[path] = O.LoRA(a.A.float().requires_grad_(True), a.B.float().requires_grad_(True), a.scaling, drop_mask=sl)
+    for k in ("input_layernorm.weight", "post_attention_layernorm.weight"):
+        wf[k].requires_grad_(True)
+    xr = inp.hidden_states.float().requires_grad_(True)
+    (ref,) = O.decoder_layer(wf, xr, inp.token_type_ids, inp.position_ids, pm, num_heads=heads, lora=adf)
+    (ref * proj.float()).sum().backward()
+
+    def close(got, want, name, tol=4e-2):
+        e = float((got.float().cpu() - want).norm() / want.norm().clamp_min(1e-12))
+        assert e <= tol, (name, e)
+
+    mx, fro = _errs(out.detach().cpu()[pm], ref.detach()[pm])
+    assert mx <= MAX_REL and fro <= FRO_REL, (mx, fro)
+    close(x.grad[pm.cuda()], xr.grad[pm], "d_hidden")
+    for path, a in adf.items():
+        m = layer.get_submodule(path)
+        close(m.lora_A["default"].weight.grad, a.A.grad, path + ".lora_A")
+        close(m.lora_B["default"].weight.grad, a.B.grad, path + ".lora_B")
+    close(layer.input_layernorm.modules_to_save["default"].weight.grad, wf["input_layernorm.weight"].grad, "ln1")
+    close(layer.post_attention_layernorm.modules_to_save["default"].weight.grad,
+          wf["post_attention_layernorm.weight"].grad, "ln2")
