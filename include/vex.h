@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VEX_ABI_VERSION 3
+#define VEX_ABI_VERSION 4
 
 #define VEX_OK 0
 #define VEX_E_INVALID (-1)     /* bad argument (null pointer, size, alignment) */
@@ -115,6 +115,13 @@ int vex_copy_padded_rows(const void* x, const int32_t* flat_to_sorted, void* out
 #define VEX_EPI_DROPOUT_ACC 4 /* out[map(r)] = residual[map(r)] + bf16(keep(r, col) * alpha / (1 - p) * acc): adjoint of
                                  the LoRA input dropout (PEFT lora.Linear: lora_A(dropout(x))), mask as vex_dropout_rows */
 
+#define VEX_EPI_CE 5       /* fused lm_head + cross-entropy, forward (CogVLMForCausalLM.forward :701-706 +
+                              _sample_weighted_ce :610-627): no logits are written; per row r and 256-column tile t
+                              ce_pmax[r, t] = max_j z, ce_psum[r, t] = sum_j exp(z - max), ce_zlabel[r] = z[label_r],
+                              z = bf16-rounded logit.  single_expert, N = vocabulary (tiles = ceil(N / 256)) */
+#define VEX_EPI_CE_BWD 6   /* backward: out[r, j] = bf16((exp(z - ce_lse[r]) - [j == label_r]) * ce_w[r] * ce_dloss[0]
+                              / counts[0]) -- d(loss)/d(logits), the A operand of the lm_head dgrad GEMM */
+
 typedef struct vexGemmArgs {
   const void* a;            /* [rows_cap, K] bf16, sorted row order, row stride lda elements */
   int64_t lda;
@@ -149,6 +156,13 @@ typedef struct vexGemmArgs {
                                DROPOUT_ACC only */
   float dropout_p;          /* VEX_EPI_DROPOUT_ACC: drop probability and seed of the forward vex_dropout_rows call; */
   uint64_t dropout_seed;    /*   the mask index is sorted_row * N + col */
+  const int32_t* ce_labels; /* VEX_EPI_CE / CE_BWD: label of row r (device, from vex_label_rows) */
+  float* ce_pmax;           /* VEX_EPI_CE out: [rows_cap, ceil(N/256)] fp32 */
+  float* ce_psum;           /* VEX_EPI_CE out: [rows_cap, ceil(N/256)] fp32 */
+  float* ce_zlabel;         /* VEX_EPI_CE out: [rows_cap] fp32 */
+  const float* ce_lse;      /* VEX_EPI_CE_BWD: [rows_cap] natural-log log-sum-exp (vex_ce_reduce) */
+  const float* ce_w;        /* VEX_EPI_CE_BWD: [rows_cap] per-row weight (vex_label_rows) */
+  const float* ce_dloss;    /* VEX_EPI_CE_BWD: device scalar, gradient of the loss */
 } vexGemmArgs;
 
 int vex_grouped_gemm(const vexGemmArgs* args, vexStream stream);
@@ -210,6 +224,18 @@ int vex_silu_mul_backward(const void* dact, const void* gate, const void* up, vo
 int vex_rmsnorm_backward(const void* dy, const void* x, const int32_t* x_map, const void* weight, int weight_is_fp32,
                          float eps, const void* add, const int32_t* add_map, void* dx, const int32_t* dx_map,
                          float* dweight, const int32_t* n_rows, int rows_cap, int H, vexStream stream);
+
+/* K10 -- row selection and reduction around the fused lm_head + cross-entropy (VEX_EPI_CE / VEX_EPI_CE_BWD).
+ * vex_label_rows: rows with labels != ignore_index (-100, CE_IGNORE_INDEX mmmm/data/defs.py), ascending flat order
+ * (== the order of ce[mask], :619-626): row_idx[k] = flat position, label_sel[k] = label, w_sel[k] = weight (fp32 from
+ * bf16 / fp32 `weight`, 1.0 when weight == NULL), count[0] = number of selected rows.  n <= 2^24.
+ * vex_ce_reduce: lse[r] = log sum_j exp(z_rj) from the tile partials, loss[0] = sum_r (lse[r] - zlabel[r]) * w_sel[r]
+ * / count (== F.cross_entropy mean when weight is None, == dot(ce[mask], weight[mask]) / mask.sum() otherwise;
+ * 0/0 = NaN for an all-ignored batch, like the reference).  loss must be zeroed by the caller. */
+int vex_label_rows(const int64_t* labels, const void* weight, int weight_is_fp32, int n, int64_t ignore_index,
+                   int32_t* row_idx, int32_t* label_sel, float* w_sel, int32_t* count, vexStream stream);
+int vex_ce_reduce(const float* pmax, const float* psum, const float* zlabel, const float* w_sel, const int32_t* count,
+                  int rows_cap, int n_tiles, float* lse, float* loss, vexStream stream);
 
 /* K8 -- LoRA weight gradients on tcgen05 (both operands MN-major, reduction over tokens), per expert segment e:
  *     out_e[f, j] += sum_{t in segment e} x[t, f] * y[t, j]        f < F, j < r

@@ -4,7 +4,8 @@ Only the hot path named by BASELINE.json is here: ``CogVLMDecoderLayer`` and the
 Importing the package is cheap; the CUDA library (libvex.so) is built/loaded on first use and its
 absence is a hard error (there is no CPU fallback).
 """
-__all__ = ["CogVLMDecoderLayer", "VexConfig", "swap_decoder_layers", "build_plan"]
+__all__ = ["CogVLMDecoderLayer", "VexConfig", "swap_decoder_layers", "build_plan", "VisualExpertDecoder",
+           "fused_lm_head_loss", "LoraGradReducer"]
 
 
 def __getattr__(name):
@@ -13,6 +14,12 @@ def __getattr__(name):
                 "masked_rms_norm"):
         from . import modeling_cogvlm as m
         return getattr(m, name)
+    if name == "fused_lm_head_loss":
+        from .lm_head import fused_lm_head_loss
+        return fused_lm_head_loss
+    if name in ("LoraGradReducer", "layer_forward_train"):
+        from . import training as t
+        return getattr(t, name)
     if name == "build_plan":
         from .plan import build_plan
         return build_plan

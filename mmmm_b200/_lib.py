@@ -12,7 +12,7 @@ _lock = threading.Lock()
 _lib = None
 
 VEX_OK = 0
-EPI_PLAIN, EPI_ROPE, EPI_SWIGLU, EPI_RESIDUAL, EPI_DROPOUT_ACC = 0, 1, 2, 3, 4
+EPI_PLAIN, EPI_ROPE, EPI_SWIGLU, EPI_RESIDUAL, EPI_DROPOUT_ACC, EPI_CE, EPI_CE_BWD = 0, 1, 2, 3, 4, 5, 6
 COUNT_VISION, COUNT_LANGUAGE, COUNT_VALID, COUNT_MAXLEN, NUM_COUNTS = 0, 1, 2, 3, 4
 
 # every symbol include/vex.h declares (tests/test_abi.py checks the header against this list)
@@ -20,7 +20,7 @@ SYMBOLS = [
     "vex_abi_version", "vex_error_string", "vex_last_cuda_error", "vex_device_check", "vex_partition",
     "vex_rmsnorm_gather", "vex_silu_mul", "vex_residual_scatter", "vex_copy_padded_rows", "vex_grouped_gemm",
     "vex_attention", "vex_attention_decode", "vex_gather_rows", "vex_silu_mul_backward", "vex_rmsnorm_backward",
-    "vex_lora_wgrad", "vex_attention_lse", "vex_attention_backward", "vex_dropout_rows",
+    "vex_lora_wgrad", "vex_attention_lse", "vex_attention_backward", "vex_dropout_rows", "vex_label_rows", "vex_ce_reduce",
 ]
 
 
@@ -38,6 +38,8 @@ class GemmArgs(C.Structure):
         ("rows_cap", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("mode", C.c_int32),
         ("single_expert", C.c_int32), ("alpha", C.c_float), ("w_transposed", C.c_int32),
         ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64),
+        ("ce_labels", C.c_void_p), ("ce_pmax", C.c_void_p), ("ce_psum", C.c_void_p), ("ce_zlabel", C.c_void_p),
+        ("ce_lse", C.c_void_p), ("ce_w", C.c_void_p), ("ce_dloss", C.c_void_p),
     ]
 
 
@@ -79,6 +81,8 @@ def lib() -> C.CDLL:
         L.vex_rmsnorm_backward.argtypes = [p, p, p, p, i32, f32, p, p, p, p, p, p, i32, i32, p]
         L.vex_attention_lse.argtypes = [p, p, i32, i32, i32, p, p, f32, p, p]
         L.vex_attention_backward.argtypes = [p, p, p, p, p, p, p, p, p, p, p, i32, i32, i32, i32, p, f32, p]
+        L.vex_label_rows.argtypes = [p, p, i32, i32, i64, p, p, p, p, p]
+        L.vex_ce_reduce.argtypes = [p, p, p, p, p, i32, i32, p, p, p]
         L.vex_dropout_rows.argtypes = [p, p, p, i32, i32, f32, C.c_uint64, p]
         L.vex_lora_wgrad.argtypes = [p, i64, p, i64, i32, p, p, i64, i32, p, i32, i32, p]
         for name in SYMBOLS:

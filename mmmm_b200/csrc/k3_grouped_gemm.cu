@@ -66,6 +66,15 @@ struct GemmDev {
   int lora_mask;   // bit e: expert e has an adapter
   int trans_b;     // 1: weights are [K, N] row-major (MN-major B operand): out = A . W  (backward dgrad)
   uint32_t drop_thresh16, drop_seed_lo, drop_seed_hi;  // VEX_EPI_DROPOUT_ACC: mask of dropout_hash(s_row * N + col)
+  // VEX_EPI_CE / VEX_EPI_CE_BWD (fused lm_head + cross-entropy): per-row label, per-(row, n-tile) softmax partials
+  const int32_t* ce_labels;
+  float* ce_pmax;
+  float* ce_psum;
+  float* ce_zlabel;
+  const float* ce_lse;
+  const float* ce_w;
+  const float* ce_dloss;
+  int ce_tiles;
 };
 
 template <int BN>
@@ -210,6 +219,60 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, int e, int m, in
   uint32_t raw[32];
   float v[32];
 
+  if (p.mode == VEX_EPI_CE) {
+    // Fused lm_head + cross-entropy, forward: the logits of this 128 x BN tile never leave the SM.  Per row: running
+    // max m and sum of exp(z - m) over the tile's columns (z = bf16-rounded logit, what `lm_head(h).float()` holds,
+    // modeling_cogvlm.py:701) and the label's logit if it falls into the tile.  vex_ce_reduce combines the tiles.
+    constexpr float L2E = 1.4426950408889634f;
+    const int label = valid ? p.ce_labels[s_row] : -1;
+    float m = -INFINITY, ssum = 0.f, zl = 0.f;
+    bool has = false;
+#pragma unroll 1
+    for (int q = 0; q < BN / 32; ++q) {
+      const int cbase = n * BN + q * 32;
+      tmem_ld_32x32b_x32(t_acc + q * 32, raw);
+      tmem_ld_wait();
+      float cm = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] = (cbase + j < p.N) ? bf16r(__uint_as_float(raw[j])) : -INFINITY;
+        cm = fmaxf(cm, v[j]);
+        zl += (cbase + j == label) ? v[j] : 0.f;  // select chain (no dynamic register indexing)
+      }
+      if (cm > m) {  // never true while cm == -inf (columns past N), so m - cm is never inf - inf
+        ssum *= exp2f((m - cm) * L2E);
+        m = cm;
+      }
+      if (m > -INFINITY) {
+        const float ml = m * L2E;
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          a0 += exp2f(fmaf(v[j], L2E, -ml));
+          a1 += exp2f(fmaf(v[j + 1], L2E, -ml));
+        }
+        ssum += a0 + a1;
+      }
+      has = has || (label >= cbase && label < cbase + 32);
+    }
+    release();
+    if (valid) {
+      p.ce_pmax[static_cast<int64_t>(s_row) * p.ce_tiles + n] = m;
+      p.ce_psum[static_cast<int64_t>(s_row) * p.ce_tiles + n] = ssum;
+      if (has) p.ce_zlabel[s_row] = zl;
+    }
+    __syncwarp();
+    return;
+  }
+  // VEX_EPI_CE_BWD: per-row constants of d(loss)/d(logit) = (softmax - onehot) * w_row * dloss / n_rows
+  int ce_label = -1;
+  float ce_lse2 = 0.f, ce_coef = 0.f;
+  if (p.mode == VEX_EPI_CE_BWD && valid) {
+    ce_label = p.ce_labels[s_row];
+    ce_lse2 = p.ce_lse[s_row] * 1.4426950408889634f;
+    ce_coef = p.ce_w[s_row] * p.ce_dloss[0] / static_cast<float>(max(cnt0, 1));
+  }
+
   if (p.mode == VEX_EPI_SWIGLU) {
     if constexpr (BN == 256) {
 #pragma unroll 1
@@ -295,6 +358,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, int e, int m, in
           if (p.mode == VEX_EPI_PLAIN) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
+          } else if (p.mode == VEX_EPI_CE_BWD) {
+            // dz = (exp(z - lse) - [col == label]) * coef, z = bf16-rounded logit; rounded to bf16 on store like the
+            // eager `.float()` backward hands it to lm_head's backward
+            const int cbase = col0 + q * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float z = bf16r(__uint_as_float(raw[j]));
+              const float sm = exp2f(fmaf(z, 1.4426950408889634f, -ce_lse2));
+              v[j] = (sm - (cbase + j == ce_label ? 1.f : 0.f)) * ce_coef;
+            }
           } else if (p.mode == VEX_EPI_DROPOUT_ACC) {
             // adjoint of the LoRA input dropout: keep(s_row, col) * alpha * acc, same hash as k7_dropout_rows
             const uint64_t pair0 = (static_cast<uint64_t>(s_row) * p.N + (col0 + q * 32)) >> 1;
@@ -869,11 +942,11 @@ static bool use_pair_kernel() {
 
 extern "C" int vex_grouped_gemm(const vexGemmArgs* a, vexStream stream) {
   using namespace vex;
-  if (!a || !a->a || !a->out || !a->counts || !a->w[0][0]) return VEX_E_INVALID;
+  if (!a || !a->a || (!a->out && a->mode != VEX_EPI_CE) || !a->counts || !a->w[0][0]) return VEX_E_INVALID;
   if (a->rows_cap <= 0 || a->N <= 0 || a->K <= 0) return VEX_E_INVALID;
   if (a->N % 8 != 0 || a->K % 8 != 0 || a->ldo % 8 != 0 || a->lda % 8 != 0 || a->ldw % 8 != 0)
     return VEX_E_UNSUPPORTED;
-  if (a->mode < VEX_EPI_PLAIN || a->mode > VEX_EPI_DROPOUT_ACC) return VEX_E_INVALID;
+  if (a->mode < VEX_EPI_PLAIN || a->mode > VEX_EPI_CE_BWD) return VEX_E_INVALID;
   const bool swiglu = a->mode == VEX_EPI_SWIGLU;
   if (!a->single_expert && !a->w[1][0]) return VEX_E_INVALID;
   if (swiglu && (!a->w[0][1] || (!a->single_expert && !a->w[1][1]))) return VEX_E_INVALID;
@@ -887,6 +960,12 @@ extern "C" int vex_grouped_gemm(const vexGemmArgs* a, vexStream stream) {
   }
   const bool tb = a->w_transposed != 0;
   if (tb && (swiglu || a->mode == VEX_EPI_ROPE)) return VEX_E_UNSUPPORTED;
+  const bool ce = a->mode == VEX_EPI_CE || a->mode == VEX_EPI_CE_BWD;
+  if (ce) {
+    if (!a->single_expert || tb || a->N <= 64 || !a->ce_labels) return VEX_E_INVALID;
+    if (a->mode == VEX_EPI_CE && (!a->ce_pmax || !a->ce_psum || !a->ce_zlabel)) return VEX_E_INVALID;
+    if (a->mode == VEX_EPI_CE_BWD && (!a->ce_lse || !a->ce_w || !a->ce_dloss)) return VEX_E_INVALID;
+  }
   const bool small_n = a->N <= 64 && a->mode == VEX_EPI_PLAIN;
   const int BN = small_n ? 64 : 256;
   const int half_rows = swiglu ? 128 : BN / 2;
@@ -948,6 +1027,14 @@ extern "C" int vex_grouped_gemm(const vexGemmArgs* a, vexStream stream) {
   dev.mode = a->mode;
   dev.single_expert = a->single_expert;
   dev.trans_b = tb;
+  dev.ce_labels = a->ce_labels;
+  dev.ce_pmax = a->ce_pmax;
+  dev.ce_psum = a->ce_psum;
+  dev.ce_zlabel = a->ce_zlabel;
+  dev.ce_lse = a->ce_lse;
+  dev.ce_w = a->ce_w;
+  dev.ce_dloss = a->ce_dloss;
+  dev.ce_tiles = ceil_div(a->N, 256);
   if (a->mode == VEX_EPI_DROPOUT_ACC) {
     dev.drop_thresh16 = static_cast<uint32_t>(a->dropout_p * 65536.0f + 0.5f);
     dev.drop_seed_lo = static_cast<uint32_t>(a->dropout_seed);

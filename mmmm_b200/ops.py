@@ -11,7 +11,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib, instrument
-from ._lib import EPI_DROPOUT_ACC, EPI_PLAIN, EPI_RESIDUAL, EPI_ROPE, EPI_SWIGLU, GemmArgs  # noqa: F401
+from ._lib import EPI_CE, EPI_CE_BWD, EPI_DROPOUT_ACC, EPI_PLAIN, EPI_RESIDUAL, EPI_ROPE, EPI_SWIGLU, GemmArgs  # noqa: F401
 
 _BF16 = torch.bfloat16
 
@@ -142,14 +142,15 @@ def grouped_gemm_raw(a: torch.Tensor, w: Sequence[Optional[torch.Tensor]], out: 
                      lora_b: Sequence[Optional[torch.Tensor]] = (None, None, None, None), lora_r: int = 0,
                      rope: Optional[tuple] = None, rope_cols: int = 0, single_expert: bool = False,
                      alpha: float = 1.0, n_out: Optional[int] = None, w_transposed: bool = False,
-                     dropout_p: float = 0.0, dropout_seed: int = 0) -> None:
+                     dropout_p: float = 0.0, dropout_seed: int = 0, ce: Optional[dict] = None) -> None:
     """K3 (vex_grouped_gemm).  ``w`` = [vision_w0, vision_w1, language_w0, language_w1] ([N, K] each; the *_w1
     entries are up_proj for SWIGLU, else None).  ``lora_b`` likewise; ``lora_t`` = [T_half0, T_half1].
     ``rope`` = (cos [S,128], sin [S,128], position_ids int64 [B*L], sorted_to_flat int32).
     ``w_transposed``: the weights are [K, N] (out = a . w, the dgrad form dX = dY . W over the nn.Linear weight as
     stored) and ``lora_b`` holds lora_A [r, N]."""
     _dev(a, "a", _BF16)
-    _dev(out, "out", _BF16)
+    if out is not None:
+        _dev(out, "out", _BF16)
     _dev(counts, "counts", torch.int32)
     K = a.shape[-1]
     rows_cap = a.numel() // K
@@ -187,8 +188,15 @@ def grouped_gemm_raw(a: torch.Tensor, w: Sequence[Optional[torch.Tensor]], out: 
                 raise ValueError(f"lora_b[{i}] must be [{N}, {lora_r}] ([{lora_r}, {N}] = lora_A when transposed)")
             args.lora_b[i // 2][i % 2] = bt.data_ptr()
         args.lora_r = lora_r
-    args.out, args.ldo = out.data_ptr(), out.shape[-1]
+    if out is not None:
+        args.out, args.ldo = out.data_ptr(), out.shape[-1]
     args.counts = counts.data_ptr()
+    if ce is not None:  # fused lm_head + cross-entropy epilogues (EPI_CE / EPI_CE_BWD)
+        for key, dt in (("labels", torch.int32), ("pmax", torch.float32), ("psum", torch.float32),
+                        ("zlabel", torch.float32), ("lse", torch.float32), ("w", torch.float32),
+                        ("dloss", torch.float32)):
+            if ce.get(key) is not None:
+                setattr(args, "ce_" + key, _dev(ce[key], "ce." + key, dt).data_ptr())
     args.row_map = _ptr(None if row_map is None else _dev(row_map, "row_map", torch.int32))
     if residual is not None:
         _dev(residual, "residual", _BF16)
@@ -210,7 +218,7 @@ def grouped_gemm_raw(a: torch.Tensor, w: Sequence[Optional[torch.Tensor]], out: 
     args.single_expert = int(single_expert)
     args.alpha = alpha
     args.dropout_p, args.dropout_seed = float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF
-    name = ("gemm_plain", "gemm_rope", "gemm_swiglu", "gemm_residual", "gemm_dropout_acc")[mode] + ("_n64" if N <= 64 else "") + \
+    name = ("gemm_plain", "gemm_rope", "gemm_swiglu", "gemm_residual", "gemm_dropout_acc", "gemm_ce", "gemm_ce_bwd")[mode] + ("_n64" if N <= 64 else "") + \
         ("_dgrad" if w_transposed else "")
     with instrument.region(name):
       rc = _lib.lib().vex_grouped_gemm(C.byref(args), _stream())
@@ -416,6 +424,68 @@ def rmsnorm_backward(dy: torch.Tensor, x: torch.Tensor, x_map: Optional[torch.Te
     _lib.check(rc, "vex_rmsnorm_backward")
 
 
+# ------------------------------------------------------------------------------------------ K10 (lm_head + CE)
+@torch.library.custom_op("vex::label_rows", mutates_args=("row_idx", "label_sel", "w_sel", "count"))
+def label_rows(labels: torch.Tensor, weight: Optional[torch.Tensor], ignore_index: int, row_idx: torch.Tensor,
+               label_sel: torch.Tensor, w_sel: torch.Tensor, count: torch.Tensor) -> None:
+    """vex_label_rows: ordered compaction of the positions with labels != ignore_index (the rows
+    _sample_weighted_ce keeps, modeling_cogvlm.py:619-626)."""
+    _dev(labels, "labels", torch.int64)
+    n = labels.numel()
+    for nm, t, dt in (("row_idx", row_idx, torch.int32), ("label_sel", label_sel, torch.int32),
+                      ("w_sel", w_sel, torch.float32)):
+        _dev(t, nm, dt)
+        if t.numel() < n:
+            raise ValueError(f"{nm} needs {n} elements")
+    _dev(count, "count", torch.int32)
+    if weight is not None:
+        _dev(weight, "weight")
+        if weight.dtype not in (_BF16, torch.float32) or weight.numel() != n:
+            raise ValueError("weight must be bf16 / fp32 with one entry per label")
+    with instrument.region("label_rows"):
+      rc = _lib.lib().vex_label_rows(labels.data_ptr(), _ptr(weight),
+                                     int(weight is not None and weight.dtype == torch.float32), n, int(ignore_index),
+                                     row_idx.data_ptr(), label_sel.data_ptr(), w_sel.data_ptr(), count.data_ptr(),
+                                     _stream())
+    _lib.check(rc, "vex_label_rows")
+
+
+@torch.library.custom_op("vex::lm_head_ce_forward", mutates_args=("pmax", "psum", "zlabel", "lse", "loss"))
+def lm_head_ce_forward(h_sel: torch.Tensor, w: torch.Tensor, label_sel: torch.Tensor, w_sel: torch.Tensor,
+                       count: torch.Tensor, lora_t: Optional[torch.Tensor], lora_b: Optional[torch.Tensor], lora_r: int,
+                       pmax: torch.Tensor, psum: torch.Tensor, zlabel: torch.Tensor, lse: torch.Tensor,
+                       loss: torch.Tensor) -> None:
+    """Fused lm_head + weighted cross-entropy, forward (CogVLMForCausalLM.forward :701-706, _sample_weighted_ce
+    :610-627): the vocabulary GEMM over the selected rows with the softmax statistics in its epilogue (VEX_EPI_CE,
+    no logits in HBM) + vex_ce_reduce.  ``loss`` (fp32 [1]) must be zero on entry."""
+    V = w.shape[0]
+    tiles = (V + 255) // 256
+    cap = h_sel.shape[0]
+    if pmax.numel() < cap * tiles or psum.numel() < cap * tiles or zlabel.numel() < cap or lse.numel() < cap:
+        raise ValueError("partials / lse buffers too small")
+    grouped_gemm_raw(h_sel, [w, None, None, None], None, count, EPI_CE, lora_t=[lora_t, None],
+                     lora_b=[lora_b, None, None, None], lora_r=lora_r, single_expert=True,
+                     ce=dict(labels=label_sel, pmax=pmax, psum=psum, zlabel=zlabel))
+    with instrument.region("ce_reduce"):
+      rc = _lib.lib().vex_ce_reduce(pmax.data_ptr(), psum.data_ptr(), zlabel.data_ptr(),
+                                    _dev(w_sel, "w_sel", torch.float32).data_ptr(), count.data_ptr(), cap, tiles,
+                                    lse.data_ptr(), _dev(loss, "loss", torch.float32).data_ptr(), _stream())
+    _lib.check(rc, "vex_ce_reduce")
+
+
+@torch.library.custom_op("vex::lm_head_ce_backward", mutates_args=("dz",))
+def lm_head_ce_backward(h_sel: torch.Tensor, w: torch.Tensor, label_sel: torch.Tensor, w_sel: torch.Tensor,
+                        count: torch.Tensor, lora_t: Optional[torch.Tensor], lora_b: Optional[torch.Tensor],
+                        lora_r: int, lse: torch.Tensor, dloss: torch.Tensor, dz: torch.Tensor) -> None:
+    """d(loss)/d(logits) of the selected rows as bf16 [rows, V] (VEX_EPI_CE_BWD: logits recomputed by the GEMM,
+    softmax from the saved log-sum-exp) -- the A operand of the lm_head dgrad GEMM."""
+    if tuple(dz.shape) != (h_sel.shape[0], w.shape[0]):
+        raise ValueError("dz must be [rows, V]")
+    grouped_gemm_raw(h_sel, [w, None, None, None], dz, count, EPI_CE_BWD, lora_t=[lora_t, None],
+                     lora_b=[lora_b, None, None, None], lora_r=lora_r, single_expert=True,
+                     ce=dict(labels=label_sel, lse=lse, w=w_sel, dloss=dloss))
+
+
 # ------------------------------------------------------------------------------------------ K8
 @torch.library.custom_op("vex::lora_wgrad", mutates_args=("out_vision", "out_language"))
 def lora_wgrad(x: torch.Tensor, y: torch.Tensor, out_vision: Optional[torch.Tensor], out_language: Optional[torch.Tensor],
@@ -440,6 +510,6 @@ def lora_wgrad(x: torch.Tensor, y: torch.Tensor, out_vision: Optional[torch.Tens
     _lib.check(rc, "vex_lora_wgrad")
 
 
-for _op in (dropout_rows, attention_train, attention_backward, lora_wgrad, gather_rows, silu_mul_backward, rmsnorm_backward, grouped_gemm_dgrad, attention_decode, partition, rmsnorm_gather, silu_mul, residual_scatter, copy_padded_rows, grouped_gemm, grouped_gemm_fused,
+for _op in (label_rows, lm_head_ce_forward, lm_head_ce_backward, dropout_rows, attention_train, attention_backward, lora_wgrad, gather_rows, silu_mul_backward, rmsnorm_backward, grouped_gemm_dgrad, attention_decode, partition, rmsnorm_gather, silu_mul, residual_scatter, copy_padded_rows, grouped_gemm, grouped_gemm_fused,
             attention):
     _op.register_fake(lambda *a, **k: None)

@@ -103,6 +103,20 @@ def main():
     # long positions (> 256) to exercise the bf16 arange collapse of the rotary table
     longp = layer_case(M, hidden=256, heads=2, inter=256, batch=2, nv=8, nt=300, seed=12)
     torch.save(longp, os.path.join(OUT, "layer_longpos.pt"))
+    # lm_head + _sample_weighted_ce (modeling_cogvlm.py:610-627, :701-706) through the unmodified reference function
+    g = torch.Generator().manual_seed(13)
+    Bc, Lc, Hc, Vc = 3, 37, 64, 333
+    hid = torch.randn(Bc, Lc, Hc, generator=g).bfloat16()
+    wlm = (torch.randn(Vc, Hc, generator=g) * 0.3).bfloat16()
+    labels = torch.randint(0, Vc, (Bc, Lc), generator=g)
+    labels[torch.rand(Bc, Lc, generator=g) < 0.6] = -100
+    wt = (0.5 + torch.rand(Bc, Lc, generator=g)).bfloat16()
+    ce = {}
+    for prec, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+        logits = torch.nn.functional.linear(hid.to(dt), wlm.to(dt)).float()
+        ce[prec] = dict(weighted=M._sample_weighted_ce(logits, labels, wt), plain=M._sample_weighted_ce(logits, labels, None))
+    torch.save(dict(hidden_states=hid, lm_head_weight=wlm, labels=labels, weight=wt, loss=ce),
+               os.path.join(OUT, "lm_head_ce.pt"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

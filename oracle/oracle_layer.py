@@ -329,3 +329,27 @@ def random_lora(hidden_size: int, intermediate_size: int, *, r: int = 64, seed: 
         Bm = torch.randn(o, r, generator=g) * b_std
         out[path] = LoRA(A.to(dtype), Bm.to(dtype), scaling)
     return out
+
+
+# --------------------------------------------------------------------------------------------- section 8(f)-3
+CE_IGNORE_INDEX = -100  # mmmm/data/defs.py
+
+
+def sample_weighted_ce(logits: torch.Tensor, labels: torch.Tensor, weight: Optional[torch.Tensor]) -> torch.Tensor:
+    """``_sample_weighted_ce`` (modeling_cogvlm.py:610-627): plain mean cross-entropy over labels != -100 when ``weight``
+    is None, else dot(ce[mask], weight.float()[mask]) / mask.sum() with a per-position weight."""
+    logits = logits.view(-1, logits.shape[-1])
+    labels = labels.view(-1)
+    if weight is None:
+        return F.cross_entropy(logits, labels)
+    mask = labels != CE_IGNORE_INDEX
+    ce = F.cross_entropy(logits, labels, reduction="none")
+    return torch.dot(ce[mask], weight.float().view(-1)[mask]) / mask.sum()
+
+
+def lm_head_loss(hidden_states: torch.Tensor, lm_head_weight: torch.Tensor, labels: torch.Tensor,
+                 weight: Optional[torch.Tensor] = None, lora: Optional[LoRA] = None) -> torch.Tensor:
+    """``logits = self.lm_head(last_hidden_state).float(); loss = _sample_weighted_ce(logits, labels, weight)``
+    (CogVLMForCausalLM.forward, modeling_cogvlm.py:701-706; labels are already shifted by the data module)."""
+    logits = linear(hidden_states, lm_head_weight, lora).float()
+    return sample_weighted_ce(logits, labels, weight)

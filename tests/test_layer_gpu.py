@@ -439,3 +439,102 @@ def test_training_step_with_lora_dropout_vs_oracle_autograd(monkeypatch):
     close(layer.input_layernorm.modules_to_save["default"].weight.grad, wf["input_layernorm.weight"].grad, "ln1")
     close(layer.post_attention_layernorm.modules_to_save["default"].weight.grad,
           wf["post_attention_layernorm.weight"].grad, "ln2")
+
+
+# ------------------------------------------------------------------------------------------ section 8(f)-3
+def _lm_case(B, L, H, V, frac, seed, r=0):
+    g = torch.Generator().manual_seed(seed)
+    h = torch.randn(B, L, H, generator=g).bfloat16()
+    w = (torch.randn(V, H, generator=g) * (2.0 / H ** 0.5)).bfloat16()
+    labels = torch.randint(0, V, (B, L), generator=g)
+    labels[torch.rand(B, L, generator=g) >= frac] = -100
+    wt = (0.5 + torch.rand(B, L, generator=g)).bfloat16()
+    lora = None
+    if r:
+        lora = O.LoRA((torch.randn(r, H, generator=g) * 0.05).bfloat16(), (torch.randn(V, r, generator=g) * 0.05).bfloat16(), 0.5)
+    return h, w, labels, wt, lora
+
+
+def _lm_module(w, lora):
+    from mmmm_b200.peft_compat import MockLoraLinear
+    V, H = w.shape
+    lin = torch.nn.Linear(H, V, bias=False).to(torch.bfloat16)
+    lin.weight.data.copy_(w)
+    lin.weight.requires_grad_(False)
+    if lora is None:
+        return lin.cuda()
+    m = MockLoraLinear(lin, r=lora.A.shape[0])
+    m.lora_A["default"].weight.data.copy_(lora.A)
+    m.lora_B["default"].weight.data.copy_(lora.B)
+    m.scaling["default"] = lora.scaling
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize("weighted", [True, False])
+@pytest.mark.parametrize("r", [0, 16])
+def test_fused_lm_head_loss_vs_oracle(weighted, r):
+    """lm_head + _sample_weighted_ce (modeling_cogvlm.py:610-627, :701-706) without logits in HBM: loss against the
+    oracle in bf16 (the reference's precision) and fp32, gradients against torch.autograd over the oracle."""
+    from mmmm_b200.lm_head import fused_lm_head_loss
+    h, w, labels, wt, lora = _lm_case(3, 211, 256, 1000, 0.35, seed=51 + r, r=r)
+    wt_ = wt if weighted else None
+    mod = _lm_module(w, lora)
+    x = h.cuda().requires_grad_(True)
+    loss = fused_lm_head_loss(x, mod, labels.cuda(), None if wt_ is None else wt_.cuda())
+    assert loss.dtype == torch.float32 and loss.dim() == 0
+    (loss * 3.0).backward()
+    ref16 = O.lm_head_loss(h, w, labels, wt_, lora)
+    hf = h.float().requires_grad_(True)
+    lf = None if lora is None else O.LoRA(lora.A.float().requires_grad_(True), lora.B.float().requires_grad_(True), lora.scaling)
+    ref32 = O.lm_head_loss(hf, w.float(), labels, wt_, lf)
+    (ref32 * 3.0).backward()
+    assert abs(float(loss) - float(ref16)) <= 3e-3 * abs(float(ref16)), (float(loss), float(ref16))
+    assert abs(float(loss) - float(ref32)) <= 5e-3 * abs(float(ref32)), (float(loss), float(ref32))
+    rel = lambda a, b: float((a.float().cpu() - b).norm() / b.norm().clamp_min(1e-12))
+    assert rel(x.grad, hf.grad) <= 2e-2, rel(x.grad, hf.grad)
+    assert (x.grad.cpu()[labels == -100] == 0).all()             # rows without a label get no gradient
+    if lora is not None:
+        assert rel(mod.lora_A["default"].weight.grad, lf.A.grad) <= 4e-2
+        assert rel(mod.lora_B["default"].weight.grad, lf.B.grad) <= 4e-2
+
+
+def test_fused_lm_head_loss_edge_cases(golden_dir):
+    from mmmm_b200.lm_head import fused_lm_head_loss
+    # the committed fixture of the unmodified reference function (tests/golden/lm_head_ce.pt, V = 333 is not a
+    # multiple of 8: pad the vocabulary with rows that can never win -- a large negative logit -- is NOT done by the
+    # op; it requires V % 8 == 0, so the fixture is checked on a padded copy whose extra logits are exactly 0 weight)
+    g = torch.load(os.path.join(golden_dir, "lm_head_ce.pt"), weights_only=False)
+    h, w, labels, wt = g["hidden_states"], g["lm_head_weight"], g["labels"], g["weight"]
+    Vp = 336
+    wp = torch.zeros(Vp, w.shape[1], dtype=torch.bfloat16)
+    wp[:333] = w
+    ref = O.lm_head_loss(h, wp, labels, wt)                       # same padding on the oracle side
+    got = fused_lm_head_loss(h.cuda(), _lm_module(wp, None), labels.cuda(), wt.cuda())
+    assert abs(float(got) - float(ref)) <= 3e-3 * abs(float(ref))
+    # nothing labelled: 0 / 0 = NaN like the reference; exactly one labelled row; errors
+    lab = torch.full_like(labels, -100)
+    assert torch.isnan(fused_lm_head_loss(h.cuda(), _lm_module(wp, None), lab.cuda(), wt.cuda()))
+    lab[1, 5] = 7
+    one = fused_lm_head_loss(h.cuda(), _lm_module(wp, None), lab.cuda(), None)
+    assert abs(float(one) - float(O.lm_head_loss(h, wp, lab, None))) <= 3e-3 * abs(float(one))
+    with pytest.raises(ValueError):
+        fused_lm_head_loss(h, _lm_module(wp, None), labels, wt)   # CPU tensors: no fallback
+    with pytest.raises(TypeError):
+        fused_lm_head_loss(h.cuda().float(), _lm_module(wp, None), labels.cuda(), None)
+
+
+def test_fused_lm_head_loss_full_vocabulary():
+    """Vocabulary 32 008 (not a multiple of the 256-column tile), hidden 4096, 8 x 1485 positions with ~17 % labelled
+    (config-2 shape): loss and input gradient against the oracle evaluated on the GPU in bf16."""
+    from mmmm_b200.lm_head import fused_lm_head_loss
+    h, w, labels, wt, _ = _lm_case(8, 1485, 4096, 32008, 0.17, seed=77)
+    mod = _lm_module(w, None)
+    x = h.cuda().requires_grad_(True)
+    loss = fused_lm_head_loss(x, mod, labels.cuda(), wt.cuda())
+    loss.backward()
+    xr = h.cuda().requires_grad_(True)
+    ref = O.lm_head_loss(xr, w.cuda(), labels.cuda(), wt.cuda())
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= 2e-3 * abs(float(ref)), (float(loss), float(ref))
+    e = float((x.grad.float() - xr.grad.float()).norm() / xr.grad.float().norm())
+    assert e <= 2e-2, e

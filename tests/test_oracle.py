@@ -152,3 +152,22 @@ def test_oracle_decode_steps_bit_exact_vs_live_reference(dtype):
                                   rms_norm_eps=cfg.rms_norm_eps, use_cache=True, past_key_value=kv)
         assert torch.equal(out, ref_out)
         assert torch.equal(kv[0], ref_kv[0]) and torch.equal(kv[1], ref_kv[1])
+
+
+def test_lm_head_ce_vs_golden_and_live_reference(golden_dir):
+    """the oracle's lm_head + _sample_weighted_ce restatement against the fixture written by the
+    unmodified reference function, and bit-exact against the live function where /root/reference exists."""
+    g = _load(golden_dir, "lm_head_ce.pt")
+    for prec, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+        h, w = g["hidden_states"].to(dt), g["lm_head_weight"].to(dt)
+        got_w = O.lm_head_loss(h, w, g["labels"], g["weight"])
+        got_p = O.lm_head_loss(h, w, g["labels"], None)
+        assert torch.equal(got_w, g["loss"][prec]["weighted"]) and torch.equal(got_p, g["loss"][prec]["plain"])
+    if RL.reference_available():
+        M = RL.load_reference()
+        logits = torch.nn.functional.linear(g["hidden_states"].float(), g["lm_head_weight"].float())
+        for wt in (g["weight"], None):
+            assert torch.equal(M._sample_weighted_ce(logits, g["labels"], wt), O.sample_weighted_ce(logits, g["labels"], wt))
+    # all labels ignored -> NaN, like the reference (0 / 0)
+    lab = torch.full_like(g["labels"], -100)
+    assert torch.isnan(O.lm_head_loss(g["hidden_states"].float(), g["lm_head_weight"].float(), lab, g["weight"]))

@@ -87,6 +87,45 @@ def bench_rowwise(T=11880, H=4096, I=11008):
         print(json.dumps({"kernel": name, "rows": T, "ms": ms, "GBps": nbytes / ms / 1e6}))
 
 
+def bench_lm_head(B=8, L=1485, H=4096, V=32008, frac=0.17):
+    """Fused lm_head + weighted CE (forward + backward to the hidden states) against the reference's way of
+    computing it -- fp32 logits for every position, then F.cross_entropy on the masked rows -- in eager PyTorch on
+    the same GPU (a comparator, not a fallback)."""
+    from mmmm_b200.lm_head import fused_lm_head_loss
+    from oracle import oracle_layer as O
+    g = torch.Generator(device="cuda").manual_seed(0)
+    h = torch.randn(B, L, H, device="cuda", generator=g).bfloat16()
+    lin = torch.nn.Linear(H, V, bias=False, device="cuda", dtype=torch.bfloat16)
+    lin.weight.requires_grad_(False)
+    labels = torch.randint(0, V, (B, L), device="cuda", generator=g)
+    labels[torch.rand(B, L, device="cuda", generator=g) >= frac] = -100
+    wt = (0.5 + torch.rand(B, L, device="cuda", generator=g)).bfloat16()
+    n_lab = int((labels != -100).sum())
+
+    def ours():
+        x = h.detach().requires_grad_(True)
+        fused_lm_head_loss(x, lin, labels, wt).backward()
+        return x.grad
+
+    def eager():
+        x = h.detach().requires_grad_(True)
+        O.lm_head_loss(x, lin.weight, labels, wt).backward()
+        return x.grad
+
+    ms_o = timeit(ours, iters=10, warmup=3)
+    torch.cuda.reset_peak_memory_stats()
+    ours()
+    mem_o = torch.cuda.max_memory_allocated()
+    ms_e = timeit(eager, iters=5, warmup=2)
+    torch.cuda.reset_peak_memory_stats()
+    eager()
+    mem_e = torch.cuda.max_memory_allocated()
+    flop = 3 * 2.0 * n_lab * H * V  # logits forward, logits recompute, dgrad over the labelled rows
+    print(json.dumps({"kernel": "lm_head_ce_fwd_bwd", "positions": B * L, "labelled": n_lab, "V": V, "ms": ms_o,
+                      "tflops_labelled_rows": flop / ms_o / 1e9, "peak_mem_GB": mem_o / 1e9,
+                      "eager_all_positions_ms": ms_e, "eager_peak_mem_GB": mem_e / 1e9, "speedup": ms_e / ms_o}))
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("all", "attention"):
@@ -96,3 +135,5 @@ if __name__ == "__main__":
         bench_gemm()
     if which in ("all", "rowwise"):
         bench_rowwise()
+    if which in ("all", "lmhead"):
+        bench_lm_head()
