@@ -471,6 +471,120 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+def run_vision(args):
+    """the EVA2-CLIP-E vision encoder in front of the decoder (63 layers of 1792 = 16 x 112, MLP 15360,
+    GLU projector to 4096 / 11008) over a batch of 490 x 490 images (35 x 35 patches of 14 + class token = 1226
+    tokens per image, the BASELINE vision-token count), one step = EVA2CLIPModel.forward over the batch."""
+    import torch.distributed as dist
+    from types import SimpleNamespace
+    from mmmm_b200 import instrument
+    from mmmm_b200.sharding import max_over_ranks
+    from mmmm_b200.visual import EVA2CLIPModel
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    C, heads, Iv, nl, side, patch = 1792, 16, 15360, args.vision_layers, 490, 14
+    b = WORKLOADS[args.workload][0]
+    vc = dict(hidden_size=C, num_heads=heads, intermediate_size=Iv, num_hidden_layers=nl, layer_norm_eps=1e-6,
+              in_channels=3, patch_size=(1, patch, patch), pos_embed_shape=(1, side // patch, side // patch),
+              hidden_act="gelu")
+    with torch.device("meta"):
+        model = EVA2CLIPModel(SimpleNamespace(hidden_size=H, intermediate_size=I, vision_config=vc))
+    model = model.to_empty(device=dev).to(torch.bfloat16).eval()
+    g = torch.Generator(device=dev).manual_seed(0)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("layernorm.weight") or n.endswith("norm1.weight"):
+                p.copy_(1 + 0.1 * torch.randn(p.shape, generator=g, device=dev))
+            else:
+                p.copy_(0.02 * torch.randn(p.shape, generator=g, device=dev))
+    images = [torch.randn(3, 1, side, side, generator=g, device=dev).to(torch.bfloat16) for _ in range(b)]
+    ps, pool = [(1, patch, patch)] * b, [(1, 1, 1)] * b
+    host_images = [im.cpu().pin_memory() for im in images]
+
+    def step():
+        return model(images, ps, pool)
+
+    def step_e2e():
+        out = model([h.to(dev, non_blocking=True) for h in host_images], ps, pool)
+        return [o.cpu() for o in out]
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            step()
+        kernels = instrument.profile(step, iters=3) if rank == 0 else None
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        instrument.reset()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        launches = instrument.launches()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if rank == 0 else None
+        ms_step = max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+        step_e2e()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_e2e = max(2, args.steps // 4)
+        for _ in range(n_e2e):
+            step_e2e()
+        torch.cuda.synchronize()
+        ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3, dev) / n_e2e
+    if rank == 0:
+        L = 1 + (side // patch) ** 2
+        tokens = b * L
+        hd = C // heads
+        flop_layer = tokens * 2 * (C * 3 * C + C * C + 2 * C * Iv) + b * 4 * heads * hd * L * L
+        flop_glu = b * (L - 1) * 2 * (C * H + 3 * H * I)
+        flop_patch = b * (L - 1) * 2 * 3 * patch * patch * C
+        flop = nl * flop_layer + flop_glu + flop_patch
+        pk = peaks()
+        tf = flop / (ms_step / 1e3) / 1e12
+        roof = None
+        if kernels and "gemm_plain_gelu" in kernels:
+            k = kernels["gemm_plain_gelu"]
+            ms_launch = k["ms"] / max(k["calls_per_step"], 1)
+            ach = 2.0 * tokens * C * Iv / (ms_launch / 1e3) / 1e12
+            roof = {"kernel": "k3_grouped_gemm_pair (fc1 + bias + GELU epilogue)", "bound": "tensor", "achieved": ach,
+                    "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": None,
+                    "peak_source": pk["source"] + " (burst figure)", "ms_per_launch": ms_launch}
+        total = tokens * world
+        print(json.dumps({
+            "metric": "vision-encoder prefill tokens/s", "value": total / (ms_step / 1e3), "unit": "tokens/s",
+            "images_per_s": b * world / (ms_step / 1e3), "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"EVA2-CLIP-E vision encoder ({nl} layers, hidden {C} = {heads} x {hd}, MLP {Iv}) + GLU "
+                                   f"projector ({H} / {I}), batch {b} x {side}x{side} image ({L} tokens) per GPU",
+                       "vision_layers": nl, "images_per_gpu": b, "tokens_per_gpu": tokens,
+                       "parallelism": f"dp{world} (images sharded, no collective)",
+                       "l2": "per-step weights (136 MB per layer) and activations exceed the 126 MB L2; no flush needed"},
+            "encoder_tflops_per_gpu": tf, "encoder_frac_of_bf16_peak": tf / pk["bf16_tflops"],
+            "roofline": roof, "kernels": kernels,
+            "e2e": {"value": total / (ms_e2e / 1e3), "unit": "tokens/s",
+                    "h2d_bytes_per_step": sum(h.numel() * 2 for h in host_images),
+                    "d2h_bytes_per_step": b * (L + 1) * H * 2, "ms_per_step": ms_e2e,
+                    "how": "model(images) with pinned host images, features copied back to the host"},
+            "gpu_launches": launches, "clocks": clocks, "peaks": pk,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -484,11 +598,15 @@ def main():
     ap.add_argument("--train", action="store_true", help="config 5: LoRA fwd+bwd training step + grad all-reduce")
     ap.add_argument("--lora-dropout", type=float, default=0.0, help="--train: lora_dropout (the reference uses 0.05)")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the forward as one CUDA graph (default), 0: eager")
+    ap.add_argument("--vision", action="store_true", help="SURVEY 8(f)-4: time the EVA2-CLIP-E vision encoder instead")
+    ap.add_argument("--vision-layers", type=int, default=63)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.vision:
+        run_vision(args)
     elif args.train:
         run_train(args)
     else:

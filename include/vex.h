@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VEX_ABI_VERSION 4
+#define VEX_ABI_VERSION 5
 
 #define VEX_OK 0
 #define VEX_E_INVALID (-1)     /* bad argument (null pointer, size, alignment) */
@@ -122,6 +122,9 @@ int vex_copy_padded_rows(const void* x, const int32_t* flat_to_sorted, void* out
 #define VEX_EPI_CE_BWD 6   /* backward: out[r, j] = bf16((exp(z - ce_lse[r]) - [j == label_r]) * ce_w[r] * ce_dloss[0]
                               / counts[0]) -- d(loss)/d(logits), the A operand of the lm_head dgrad GEMM */
 
+#define VEX_ACT_NONE 0
+#define VEX_ACT_GELU 1     /* exact (erf) GELU: ACT2FN['gelu'] of the vision MLP (visual.py:108, :115) */
+
 typedef struct vexGemmArgs {
   const void* a;            /* [rows_cap, K] bf16, sorted row order, row stride lda elements */
   int64_t lda;
@@ -163,6 +166,10 @@ typedef struct vexGemmArgs {
   const float* ce_lse;      /* VEX_EPI_CE_BWD: [rows_cap] natural-log log-sum-exp (vex_ce_reduce) */
   const float* ce_w;        /* VEX_EPI_CE_BWD: [rows_cap] per-row weight (vex_label_rows) */
   const float* ce_dloss;    /* VEX_EPI_CE_BWD: device scalar, gradient of the loss */
+  const void* bias;         /* VEX_EPI_PLAIN / VEX_EPI_RESIDUAL: bf16 [N] bias of an nn.Linear WITH bias (the vision
+                               encoder's Linears, visual.py:84-85, :110-111, and the patch convolution), added to the fp32
+                               accumulator before the single bf16 rounding; NULL = none.  N % 32 == 0, forward form only */
+  int32_t act;              /* VEX_EPI_PLAIN: activation applied to the bf16-rounded output (VEX_ACT_*) */
 } vexGemmArgs;
 
 int vex_grouped_gemm(const vexGemmArgs* args, vexStream stream);
@@ -263,6 +270,45 @@ int vex_attention_backward(const void* qkv, const void* out_sorted, void* d_out_
                            const int32_t* token_to_flat, const int64_t* position_ids, const void* rope_cos,
                            const void* rope_sin, int rope_len, int B, int max_len_cap, int heads, void* dqkv,
                            float scale, vexStream stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Vision encoder in front of the decoder: EVA2CLIPModel.forward, mmmm/models/cogvlm/
+ * visual.py:24-208.  Its Linears run on vex_grouped_gemm (single_expert, `bias` / `act`), its attention on
+ * vex_attention_blockdiag; the entry points below are the row-wise pieces.
+ * --------------------------------------------------------------------------------------------------- */
+
+/* K4 (non-causal): xformers memory_efficient_attention under a BlockDiagonalMask (visual.py:96-98) -- every token
+ * attends to all tokens of its own image.  Same buffers and layout as vex_attention (head slots of 128; a head_dim
+ * below 128 is zero-padded by the caller, `scale` = head_dim^-0.5 of the real head_dim). */
+int vex_attention_blockdiag(const void* qkv, const int32_t* cu_seqlens, int B, int max_len_cap, int heads,
+                            const int32_t* out_row_map, void* out, float scale, vexStream stream);
+
+/* K11 -- nn.LayerNorm over rows r < *n_rows of x [rows_cap, H] (bf16; weight / bias bf16 [H], bias may be NULL):
+ *   t = bf16((x - mean) * rsqrt(var + eps) * weight + bias)      fp32 statistics, biased variance
+ *   act == VEX_ACT_GELU: t = bf16(gelu(t))                       GLU projector, visual.py:173-174
+ *   residual != NULL:    y = bf16(residual + t)  else  y = t     TransformerLayer.forward visual.py:128-135
+ * y may alias residual (in-place residual stream).  H % 256 == 0, H <= 2048 or H == 4096. */
+int vex_layernorm(const void* x, const void* weight, const void* bias, float eps, const void* residual, int act,
+                  const int32_t* n_rows, void* y, int rows_cap, int H, vexStream stream);
+
+/* K11 -- im2col of the patch convolution (PatchEmbedding.forward visual.py:65 -> Downsample.forward
+ * mmmm/models/resample.py:56-63, conv3d with stride == kernel): image [C, D, H, W] bf16 ->
+ * out[(gz*gh + gy)*gw + gx][((c*pd + kz)*ph + ky)*pw + kx], row stride ldo elements (columns past C*pd*ph*pw are left
+ * untouched).  The convolution is then vex_grouped_gemm against weight.reshape(C_out, -1) with `bias`. */
+int vex_patchify(const void* image, int C, int D, int H, int W, int pd, int ph, int pw, void* out, int64_t ldo,
+                 vexStream stream);
+
+/* K11 -- F.max_pool3d over the patch grid in token-major layout (EVA2CLIPModel.forward visual.py:197-202):
+ * x rows (z*gh + y)*gw + x_ of C bf16 (row stride ldx) -> out rows (oz*oh + oy)*ow + ox, windows (pz, py, px), floor
+ * semantics.  (1, 1, 1) copies the rows (the class-token drop of visual.py:198 when x points behind it). */
+int vex_maxpool_tokens(const void* x, int64_t ldx, int gd, int gh, int gw, int pz, int py, int px, void* out,
+                       int64_t ldo, int C, vexStream stream);
+
+/* K11 -- out[row_dst[r]] = x[row_src ? row_src[r] : r] for r < n (rows of H bf16, H % 8 == 0; row_dst[r] < 0 skips):
+ * the boi / eoi rows around each image's features (visual.py:204-206) and the feature scatter into the text
+ * embeddings (CogVLMModel.forward modeling_cogvlm.py:450-453). */
+int vex_scatter_rows(const void* x, const int32_t* row_src, const int32_t* row_dst, int n, void* out, int H,
+                     vexStream stream);
 
 #ifdef __cplusplus
 }

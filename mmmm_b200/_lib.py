@@ -13,6 +13,7 @@ _lib = None
 
 VEX_OK = 0
 EPI_PLAIN, EPI_ROPE, EPI_SWIGLU, EPI_RESIDUAL, EPI_DROPOUT_ACC, EPI_CE, EPI_CE_BWD = 0, 1, 2, 3, 4, 5, 6
+ACT_NONE, ACT_GELU = 0, 1
 COUNT_VISION, COUNT_LANGUAGE, COUNT_VALID, COUNT_MAXLEN, NUM_COUNTS = 0, 1, 2, 3, 4
 
 # every symbol include/vex.h declares (tests/test_abi.py checks the header against this list)
@@ -21,6 +22,7 @@ SYMBOLS = [
     "vex_rmsnorm_gather", "vex_silu_mul", "vex_residual_scatter", "vex_copy_padded_rows", "vex_grouped_gemm",
     "vex_attention", "vex_attention_decode", "vex_gather_rows", "vex_silu_mul_backward", "vex_rmsnorm_backward",
     "vex_lora_wgrad", "vex_attention_lse", "vex_attention_backward", "vex_dropout_rows", "vex_label_rows", "vex_ce_reduce",
+    "vex_attention_blockdiag", "vex_layernorm", "vex_patchify", "vex_maxpool_tokens", "vex_scatter_rows",
 ]
 
 
@@ -40,6 +42,7 @@ class GemmArgs(C.Structure):
         ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64),
         ("ce_labels", C.c_void_p), ("ce_pmax", C.c_void_p), ("ce_psum", C.c_void_p), ("ce_zlabel", C.c_void_p),
         ("ce_lse", C.c_void_p), ("ce_w", C.c_void_p), ("ce_dloss", C.c_void_p),
+        ("bias", C.c_void_p), ("act", C.c_int32),
     ]
 
 
@@ -85,6 +88,11 @@ def lib() -> C.CDLL:
         L.vex_ce_reduce.argtypes = [p, p, p, p, p, i32, i32, p, p, p]
         L.vex_dropout_rows.argtypes = [p, p, p, i32, i32, f32, C.c_uint64, p]
         L.vex_lora_wgrad.argtypes = [p, i64, p, i64, i32, p, p, i64, i32, p, i32, i32, p]
+        L.vex_attention_blockdiag.argtypes = [p, p, i32, i32, i32, p, p, f32, p]
+        L.vex_layernorm.argtypes = [p, p, p, f32, p, i32, p, p, i32, i32, p]
+        L.vex_patchify.argtypes = [p, i32, i32, i32, i32, i32, i32, i32, p, i64, p]
+        L.vex_maxpool_tokens.argtypes = [p, i64, i32, i32, i32, i32, i32, i32, p, i64, i32, p]
+        L.vex_scatter_rows.argtypes = [p, p, p, i32, p, i32, p]
         for name in SYMBOLS:
             fn = getattr(L, name)
             if name not in ("vex_error_string",):

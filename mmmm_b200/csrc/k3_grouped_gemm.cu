@@ -75,6 +75,9 @@ struct GemmDev {
   const float* ce_w;
   const float* ce_dloss;
   int ce_tiles;
+  // vision-encoder Linears (visual.py:84-85, :110-111: nn.Linear WITH bias; MLP activation ACT2FN['gelu'])
+  const __nv_bfloat16* bias;  // [N] or nullptr: added to the fp32 accumulator before the bf16 rounding
+  int act;                    // VEX_ACT_NONE / VEX_ACT_GELU (exact erf form, on the bf16-rounded Linear output)
 };
 
 template <int BN>
@@ -380,6 +383,22 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, int e, int m, in
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          }
+          if (p.bias != nullptr && col0 + q * 32 < p.N) {
+            // nn.Linear with bias: the bias joins the fp32 accumulator, one rounding (cuBLASLt bias epilogue);
+            // every thread of the warp reads the same 32 bias values (broadcast)
+            float bv[32];
+            load_bf16x32(p.bias + col0 + q * 32, bv);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += bv[j];
+          }
+          if (p.act == VEX_ACT_GELU) {
+            // eager bf16: y = bf16(Linear), then gelu(y) = 0.5 y (1 + erf(y / sqrt 2)) rounded on store
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float y = bf16r(v[j]);
+              v[j] = 0.5f * y * (1.0f + erff(y * 0.70710678118654752f));
+            }
           }
           stage_piece32(stage_row, q * 4, lane, v);
         }
@@ -960,6 +979,11 @@ extern "C" int vex_grouped_gemm(const vexGemmArgs* a, vexStream stream) {
   }
   const bool tb = a->w_transposed != 0;
   if (tb && (swiglu || a->mode == VEX_EPI_ROPE)) return VEX_E_UNSUPPORTED;
+  if (a->bias || a->act != VEX_ACT_NONE) {
+    if (a->mode != VEX_EPI_PLAIN && a->mode != VEX_EPI_RESIDUAL) return VEX_E_UNSUPPORTED;
+    if (a->act != VEX_ACT_NONE && (a->act != VEX_ACT_GELU || a->mode != VEX_EPI_PLAIN)) return VEX_E_UNSUPPORTED;
+    if (a->N % 32 != 0 || tb || (reinterpret_cast<uintptr_t>(a->bias) & 15)) return VEX_E_UNSUPPORTED;
+  }
   const bool ce = a->mode == VEX_EPI_CE || a->mode == VEX_EPI_CE_BWD;
   if (ce) {
     if (!a->single_expert || tb || a->N <= 64 || !a->ce_labels) return VEX_E_INVALID;
@@ -1035,6 +1059,8 @@ extern "C" int vex_grouped_gemm(const vexGemmArgs* a, vexStream stream) {
   dev.ce_w = a->ce_w;
   dev.ce_dloss = a->ce_dloss;
   dev.ce_tiles = ceil_div(a->N, 256);
+  dev.bias = static_cast<const __nv_bfloat16*>(a->bias);
+  dev.act = a->act;
   if (a->mode == VEX_EPI_DROPOUT_ACC) {
     dev.drop_thresh16 = static_cast<uint32_t>(a->dropout_p * 65536.0f + 0.5f);
     dev.drop_seed_lo = static_cast<uint32_t>(a->dropout_seed);

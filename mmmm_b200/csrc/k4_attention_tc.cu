@@ -57,13 +57,14 @@ __global__ void zero_tail_rows(__nv_bfloat16* buf, const int32_t* __restrict__ c
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k4_attention_tc(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* __restrict__ cu_seqlens, int heads,
                     const int32_t* __restrict__ out_row_map, __nv_bfloat16* __restrict__ out, float scale_log2,
-                    float* __restrict__ lse, int rows_cap) {
+                    float* __restrict__ lse, int rows_cap, int causal) {
   const int b = blockIdx.z, h = blockIdx.y;
   const int seq0 = cu_seqlens[b], len = cu_seqlens[b + 1] - seq0;
   const int qb = gridDim.x - 1 - blockIdx.x;  // heaviest query blocks first
   const int q0 = qb * TC_BQ;
   if (q0 >= len) return;
-  const int n_kv = qb + 1;
+  // causal: key blocks up to the diagonal; non-causal (vision encoder, visual.py:96-98): every key block of the sample
+  const int n_kv = causal ? qb + 1 : (len + TC_BK - 1) / TC_BK;
   const int H = heads * TC_D;
 
   extern __shared__ uint8_t tc_smem_raw[];
@@ -179,13 +180,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       for (int c = 0; c < 2; ++c) tmem_ld_32x32b_x32(tS0 + lane_sel + sb * 128 + hf * 64 + c * 32, sraw[c]);
       tmem_ld_wait();
       float mx0 = -INFINITY, mx1 = -INFINITY;  // two chains
-      if (j == n_kv - 1) {  // diagonal block: key (j*128 + k) visible iff k <= r
+      if (j == n_kv - 1) {
+        // last block.  causal: it is the diagonal block, key (j*128 + k) visible iff k <= r.  non-causal: keys past the
+        // end of the sample (the next sample's tokens / the zeroed tail) are masked, k <= len - 1 - j*128
+        const int kmax = causal ? r : len - 1 - j * TC_BK;
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            if (hf * 64 + c * 32 + i > r) sraw[c][i] = 0xff800000u;  // -inf
-            if (hf * 64 + c * 32 + i + 1 > r) sraw[c][i + 1] = 0xff800000u;
+            if (hf * 64 + c * 32 + i > kmax) sraw[c][i] = 0xff800000u;  // -inf
+            if (hf * 64 + c * 32 + i + 1 > kmax) sraw[c][i + 1] = 0xff800000u;
             mx0 = fmaxf(mx0, __uint_as_float(sraw[c][i]));
             mx1 = fmaxf(mx1, __uint_as_float(sraw[c][i + 1]));
           }
@@ -310,7 +314,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 }
 
 int launch_attention_tc(const void* qkv, const int32_t* cu_seqlens, int B, int max_len_cap, int heads,
-                        const int32_t* out_row_map, void* out, float scale, int rows_cap, float* lse, cudaStream_t s) {
+                        const int32_t* out_row_map, void* out, float scale, int rows_cap, float* lse, int causal,
+                        cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
     VEX_CUDA_TRY(cudaFuncSetAttribute(k4_attention_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
@@ -327,7 +332,7 @@ int launch_attention_tc(const void* qkv, const int32_t* cu_seqlens, int B, int m
   dim3 grid(ceil_div(max_len_cap, TC_BQ), heads, B);
   k4_attention_tc<<<grid, TC_THREADS, TC_SMEM, s>>>(tm, cu_seqlens, heads, out_row_map,
                                                     static_cast<__nv_bfloat16*>(out),
-                                                    scale * 1.4426950408889634f, lse, rows_cap);
+                                                    scale * 1.4426950408889634f, lse, rows_cap, causal);
   VEX_LAUNCH_CHECK();
   return VEX_OK;
 }

@@ -11,7 +11,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib, instrument
-from ._lib import EPI_CE, EPI_CE_BWD, EPI_DROPOUT_ACC, EPI_PLAIN, EPI_RESIDUAL, EPI_ROPE, EPI_SWIGLU, GemmArgs  # noqa: F401
+from ._lib import ACT_GELU, ACT_NONE, EPI_CE, EPI_CE_BWD, EPI_DROPOUT_ACC, EPI_PLAIN, EPI_RESIDUAL, EPI_ROPE, EPI_SWIGLU, GemmArgs  # noqa: F401
 
 _BF16 = torch.bfloat16
 
@@ -142,12 +142,15 @@ def grouped_gemm_raw(a: torch.Tensor, w: Sequence[Optional[torch.Tensor]], out: 
                      lora_b: Sequence[Optional[torch.Tensor]] = (None, None, None, None), lora_r: int = 0,
                      rope: Optional[tuple] = None, rope_cols: int = 0, single_expert: bool = False,
                      alpha: float = 1.0, n_out: Optional[int] = None, w_transposed: bool = False,
-                     dropout_p: float = 0.0, dropout_seed: int = 0, ce: Optional[dict] = None) -> None:
+                     dropout_p: float = 0.0, dropout_seed: int = 0, ce: Optional[dict] = None,
+                     bias: Optional[torch.Tensor] = None, act: int = ACT_NONE) -> None:
     """K3 (vex_grouped_gemm).  ``w`` = [vision_w0, vision_w1, language_w0, language_w1] ([N, K] each; the *_w1
     entries are up_proj for SWIGLU, else None).  ``lora_b`` likewise; ``lora_t`` = [T_half0, T_half1].
     ``rope`` = (cos [S,128], sin [S,128], position_ids int64 [B*L], sorted_to_flat int32).
     ``w_transposed``: the weights are [K, N] (out = a . w, the dgrad form dX = dY . W over the nn.Linear weight as
-    stored) and ``lora_b`` holds lora_A [r, N]."""
+    stored) and ``lora_b`` holds lora_A [r, N].
+    ``bias`` (bf16 [N]) / ``act`` (ACT_GELU): nn.Linear with bias and the erf-GELU of the vision encoder's Linears
+    (visual.py:84-85, :110-117), PLAIN / RESIDUAL epilogues only."""
     _dev(a, "a", _BF16)
     if out is not None:
         _dev(out, "out", _BF16)
@@ -218,8 +221,14 @@ def grouped_gemm_raw(a: torch.Tensor, w: Sequence[Optional[torch.Tensor]], out: 
     args.single_expert = int(single_expert)
     args.alpha = alpha
     args.dropout_p, args.dropout_seed = float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF
+    if bias is not None:
+        _dev(bias, "bias", _BF16)
+        if bias.numel() != (n_out or N):
+            raise ValueError("bias must have one entry per output feature")
+        args.bias = bias.data_ptr()
+    args.act = int(act)
     name = ("gemm_plain", "gemm_rope", "gemm_swiglu", "gemm_residual", "gemm_dropout_acc", "gemm_ce", "gemm_ce_bwd")[mode] + ("_n64" if N <= 64 else "") + \
-        ("_dgrad" if w_transposed else "")
+        ("_dgrad" if w_transposed else "") + ("_gelu" if act == ACT_GELU else "")
     with instrument.region(name):
       rc = _lib.lib().vex_grouped_gemm(C.byref(args), _stream())
     _lib.check(rc, "vex_grouped_gemm")
@@ -486,6 +495,104 @@ def lm_head_ce_backward(h_sel: torch.Tensor, w: torch.Tensor, label_sel: torch.T
                      ce=dict(labels=label_sel, lse=lse, w=w_sel, dloss=dloss))
 
 
+# ------------------------------------------------------------------------------------------ vision encoder (8(f)-4)
+@torch.library.custom_op("vex::linear_bias_act", mutates_args=("out",))
+def linear_bias_act(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor,
+                    n_rows: torch.Tensor, row_map: Optional[torch.Tensor], accumulate: bool, gelu: bool) -> None:
+    """K3 as a single-expert Linear with bias / GELU / accumulate epilogue, rows r < n_rows[0]:
+    out[map(r)] = act(bf16(a[r] . w^T + bias))   or, with ``accumulate``,   out[map(r)] += bf16(a[r] . w^T + bias)
+    -- the vision encoder's nn.Linear calls (visual.py:92, :99, :114-116) and the patch convolution as a GEMM added
+    onto the position-embedding rows (visual.py:65-72)."""
+    grouped_gemm_raw(a, [w, None, None, None], out, n_rows, EPI_RESIDUAL if accumulate else EPI_PLAIN,
+                     row_map=row_map, single_expert=True, bias=bias, act=ACT_GELU if gelu else ACT_NONE)
+
+
+@torch.library.custom_op("vex::attention_blockdiag", mutates_args=("out",))
+def attention_blockdiag(qkv: torch.Tensor, cu_seqlens: torch.Tensor, batch: int, max_len_cap: int, heads: int,
+                        out: torch.Tensor, scale: float) -> None:
+    """K4 non-causal (vex_attention_blockdiag): memory_efficient_attention under a BlockDiagonalMask
+    (visual.py:96-98) over packed QKV [B * max_len_cap, 3, heads, 128]."""
+    _dev(qkv, "qkv", _BF16), _dev(out, "out", _BF16), _dev(cu_seqlens, "cu_seqlens", torch.int32)
+    if qkv.shape[-1] != 3 * heads * 128 or out.shape[-1] != heads * 128:
+        raise ValueError("qkv rows must be [3 * heads * 128] and out rows [heads * 128] wide (head slots of 128)")
+    cap = batch * max_len_cap
+    if qkv.numel() < cap * 3 * heads * 128 or out.numel() < cap * heads * 128 or cu_seqlens.numel() < batch + 1:
+        raise ValueError("qkv / out must have B * max_len_cap rows")
+    with instrument.region("attention_blockdiag", 2):
+      rc = _lib.lib().vex_attention_blockdiag(qkv.data_ptr(), cu_seqlens.data_ptr(), batch, max_len_cap, heads, None,
+                                              out.data_ptr(), float(scale), _stream())
+    _lib.check(rc, "vex_attention_blockdiag")
+
+
+@torch.library.custom_op("vex::layernorm", mutates_args=("out",))
+def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], eps: float, accumulate: bool,
+              gelu: bool, n_rows: torch.Tensor, out: torch.Tensor) -> None:
+    """K11 (vex_layernorm) over the first n_rows[0] rows: out = [gelu] LayerNorm(x), or with ``accumulate``
+    out += LayerNorm(x) -- the post-branch LayerNorm + residual of TransformerLayer.forward (visual.py:128-135) and
+    LayerNorm + GELU of the GLU projector (:173-174)."""
+    _dev(x, "x", _BF16), _dev(out, "out", _BF16), _dev(weight, "weight", _BF16), _dev(n_rows, "n_rows", torch.int32)
+    H = x.shape[-1]
+    if weight.numel() != H or out.shape != x.shape:
+        raise ValueError("hidden size mismatch")
+    if bias is not None and _dev(bias, "bias", _BF16).numel() != H:
+        raise ValueError("bias size mismatch")
+    with instrument.region("layernorm"):
+      rc = _lib.lib().vex_layernorm(x.data_ptr(), weight.data_ptr(), _ptr(bias), float(eps),
+                                    out.data_ptr() if accumulate else None, ACT_GELU if gelu else ACT_NONE,
+                                    n_rows.data_ptr(), out.data_ptr(), x.numel() // H, H, _stream())
+    _lib.check(rc, "vex_layernorm")
+
+
+@torch.library.custom_op("vex::patchify", mutates_args=("out",))
+def patchify(image: torch.Tensor, pd: int, ph: int, pw: int, out: torch.Tensor) -> None:
+    """K11 (vex_patchify): im2col of the kernel == stride patch convolution (visual.py:65, resample.py:56-63):
+    image [C, D, H, W] -> out [(D/pd)(H/ph)(W/pw), >= C*pd*ph*pw] (a row-strided 2-D view is fine)."""
+    _dev(image, "image", _BF16)
+    if not out.is_cuda or out.dtype != _BF16 or out.dim() != 2 or out.stride(1) != 1:
+        raise ValueError("out must be a 2-D CUDA bf16 tensor with unit inner stride")
+    C, D, H, W = image.shape
+    n = (D // pd) * (H // ph) * (W // pw)
+    if out.shape[0] != n or out.shape[1] < C * pd * ph * pw:
+        raise ValueError(f"out must be [{n}, >= {C * pd * ph * pw}]")
+    with instrument.region("patchify"):
+      rc = _lib.lib().vex_patchify(image.data_ptr(), C, D, H, W, pd, ph, pw, out.data_ptr(), out.stride(0), _stream())
+    _lib.check(rc, "vex_patchify")
+
+
+@torch.library.custom_op("vex::maxpool_tokens", mutates_args=("out",))
+def maxpool_tokens(x: torch.Tensor, grid: List[int], pool: List[int], out: torch.Tensor) -> None:
+    """K11 (vex_maxpool_tokens): F.max_pool3d over the (d, h, w) patch grid in token-major layout
+    (visual.py:199-202); x [d*h*w, C] and out [(d/pz)(h/py)(w/px), C] may be row-strided views."""
+    for n, t in (("x", x), ("out", out)):
+        if not t.is_cuda or t.dtype != _BF16 or t.dim() != 2 or t.stride(1) != 1:
+            raise ValueError(f"{n} must be a 2-D CUDA bf16 tensor with unit inner stride")
+    gd, gh, gw = grid
+    pz, py, px = pool
+    C = x.shape[1]
+    if x.shape[0] != gd * gh * gw or out.shape != ((gd // pz) * (gh // py) * (gw // px), C):
+        raise ValueError("grid / pool / tensor shapes disagree")
+    with instrument.region("maxpool_tokens"):
+      rc = _lib.lib().vex_maxpool_tokens(x.data_ptr(), x.stride(0), gd, gh, gw, pz, py, px, out.data_ptr(),
+                                         out.stride(0), C, _stream())
+    _lib.check(rc, "vex_maxpool_tokens")
+
+
+@torch.library.custom_op("vex::scatter_rows", mutates_args=("out",))
+def scatter_rows(x: torch.Tensor, row_src: Optional[torch.Tensor], row_dst: torch.Tensor, out: torch.Tensor) -> None:
+    """K11 (vex_scatter_rows): out[row_dst[r]] = x[row_src[r]] (boi / eoi rows visual.py:204-206, feature scatter
+    modeling_cogvlm.py:450-453)."""
+    _dev(x, "x", _BF16), _dev(out, "out", _BF16), _dev(row_dst, "row_dst", torch.int32)
+    H = x.shape[-1]
+    if out.shape[-1] != H:
+        raise ValueError("row width mismatch")
+    if row_src is not None and _dev(row_src, "row_src", torch.int32).numel() != row_dst.numel():
+        raise ValueError("row_src / row_dst lengths differ")
+    with instrument.region("scatter_rows"):
+      rc = _lib.lib().vex_scatter_rows(x.data_ptr(), _ptr(row_src), row_dst.data_ptr(), row_dst.numel(),
+                                       out.data_ptr(), H, _stream())
+    _lib.check(rc, "vex_scatter_rows")
+
+
 # ------------------------------------------------------------------------------------------ K8
 @torch.library.custom_op("vex::lora_wgrad", mutates_args=("out_vision", "out_language"))
 def lora_wgrad(x: torch.Tensor, y: torch.Tensor, out_vision: Optional[torch.Tensor], out_language: Optional[torch.Tensor],
@@ -510,6 +617,6 @@ def lora_wgrad(x: torch.Tensor, y: torch.Tensor, out_vision: Optional[torch.Tens
     _lib.check(rc, "vex_lora_wgrad")
 
 
-for _op in (label_rows, lm_head_ce_forward, lm_head_ce_backward, dropout_rows, attention_train, attention_backward, lora_wgrad, gather_rows, silu_mul_backward, rmsnorm_backward, grouped_gemm_dgrad, attention_decode, partition, rmsnorm_gather, silu_mul, residual_scatter, copy_padded_rows, grouped_gemm, grouped_gemm_fused,
+for _op in (linear_bias_act, attention_blockdiag, layernorm, patchify, maxpool_tokens, scatter_rows, label_rows, lm_head_ce_forward, lm_head_ce_backward, dropout_rows, attention_train, attention_backward, lora_wgrad, gather_rows, silu_mul_backward, rmsnorm_backward, grouped_gemm_dgrad, attention_decode, partition, rmsnorm_gather, silu_mul, residual_scatter, copy_padded_rows, grouped_gemm, grouped_gemm_fused,
             attention):
     _op.register_fake(lambda *a, **k: None)

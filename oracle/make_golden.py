@@ -82,6 +82,33 @@ def layer_case(M, *, hidden, heads, inter, batch, nv, nt, seed, with_lora=False)
     )
 
 
+VISION_TINY = dict(hidden_size=256, num_heads=2, intermediate_size=256, num_hidden_layers=2, patch_size=(4, 8, 8),
+                   pos_embed_shape=(2, 4, 4), lm_hidden_size=256, lm_intermediate_size=256)
+VISION_TINY_IMAGES = dict(shapes=[(4, 32, 32), (1, 24, 40), (8, 32, 32), (8, 64, 32)],
+                          patch=[(4, 8, 8), (1, 8, 8), (4, 8, 8), (2, 8, 8)],
+                          pool=[(1, 1, 1), (1, 1, 1), (2, 2, 2), (2, 2, 1)])
+
+
+def vision_case():
+    """EVA2CLIPModel.forward (visual.py:191-208) of the UNMODIFIED reference on a tiny config: four images with
+    different depths / patch depths (depth-reduced kernels, resampled position embeddings) and pool sizes."""
+    from oracle import oracle_vision as OV
+    cfg = OV.VisionConfig(**VISION_TINY)
+    w = OV.random_vision_weights(cfg, seed=21)
+    imgs = OV.random_images(VISION_TINY_IMAGES["shapes"], seed=22)
+    model = RL.make_reference_vision(cfg, w)
+    res = {}
+    for prec, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+        m = model.to(dt)
+        with torch.no_grad():
+            x, mask, shapes = m.patch_embedding([i.to(dt) for i in imgs], VISION_TINY_IMAGES["patch"])
+            feats = m([i.to(dt) for i in imgs], VISION_TINY_IMAGES["patch"], VISION_TINY_IMAGES["pool"])
+        res[prec] = dict(patch_embedding=x.clone(), seqlens=list(mask.seqlens), grids=[tuple(s) for s in shapes],
+                         features=[f.clone() for f in feats])
+    return dict(config=VISION_TINY, weights={k: v.to(torch.bfloat16) for k, v in w.items()},
+                images=[i.to(torch.bfloat16) for i in imgs], **VISION_TINY_IMAGES, **res)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     M = RL.load_reference()
@@ -117,6 +144,7 @@ def main():
         ce[prec] = dict(weighted=M._sample_weighted_ce(logits, labels, wt), plain=M._sample_weighted_ce(logits, labels, None))
     torch.save(dict(hidden_states=hid, lm_head_weight=wlm, labels=labels, weight=wt, loss=ce),
                os.path.join(OUT, "lm_head_ce.pt"))
+    torch.save(vision_case(), os.path.join(OUT, "vision_tiny.pt"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -150,3 +150,110 @@ def make_reference_layer(hidden_size=4096, intermediate_size=11008, num_heads=32
     # the cos/sin cache is grow-only and keeps its creation dtype (modeling_cogvlm.py:172-180)
     layer.self_attn.rotary_emb.max_seq_len_cached = 0
     return layer, cfg
+
+
+# ---------------------------------------------------------------------------------------------
+# vision encoder
+# ---------------------------------------------------------------------------------------------
+class BlockDiagonalMask:
+    """Stand-in for ``xformers.ops.fmha.BlockDiagonalMask`` (xformers 0.0.27, absent here): per-image lengths;
+    ``from_tensor_list`` packs [1, n_i, C] tensors along dim 1 and ``split`` undoes it, as documented."""
+
+    def __init__(self, seqlens):
+        self.seqlens = list(seqlens)
+
+    @classmethod
+    def from_tensor_list(cls, tensors):
+        return cls([t.shape[1] for t in tensors]), torch.cat(tensors, dim=1)
+
+    def split(self, x):
+        return list(torch.split(x, self.seqlens, dim=1))
+
+
+def memory_efficient_attention_any(q, k, v, attn_bias=None, p: float = 0.0, scale=None):
+    """``xformers.ops.memory_efficient_attention`` stand-in for both masks the reference uses: the causal one of the
+    decoder layer (delegates to ``memory_efficient_attention`` above) and the non-causal ``BlockDiagonalMask`` of the
+    vision encoder (visual.py:96-98): q, k, v [1, T, H, D]; every token sees all tokens of its own block."""
+    if isinstance(attn_bias, BlockDiagonalCausalMask):
+        assert scale is None
+        return memory_efficient_attention(q, k, v, attn_bias, p)
+    assert p == 0.0 and isinstance(attn_bias, BlockDiagonalMask)
+    scale = q.shape[-1] ** -0.5 if scale is None else scale
+    out = torch.empty_like(q)
+    start = 0
+    for n in attn_bias.seqlens:
+        sl = slice(start, start + n)
+        qb = q[0, sl].permute(1, 0, 2).float()
+        kb = k[0, sl].permute(1, 0, 2).float()
+        vb = v[0, sl].permute(1, 0, 2)
+        pr = torch.softmax(torch.matmul(qb, kb.transpose(-1, -2)) * scale, dim=-1)
+        out[0, sl] = torch.matmul(pr.to(vb.dtype).float(), vb.float()).permute(1, 0, 2).to(q.dtype)
+        start += n
+    return out
+
+
+_LOADED_VISUAL = None
+
+
+def load_reference_visual():
+    """Returns the executed reference module ``mmmm.models.cogvlm.visual`` (visual.py UNMODIFIED), with the real
+    ``mmmm/models/resample.py``, ``mmmm/utils.py`` and the vendored luolib helpers it calls
+    (``luolib/models/spadop/resample.py``, ``luolib/utils/einops.py``) executed from where they lie.  Stubs only for
+    packages absent from the image: monai (``StrEnum``), cytoolz (``compose``), xformers."""
+    global _LOADED_VISUAL
+    if _LOADED_VISUAL is not None:
+        return _LOADED_VISUAL
+    load_reference()
+    import enum
+
+    ref = os.path.join(REFERENCE_ROOT, "mmmm")
+    luo = os.path.join(REFERENCE_ROOT, "luolib")
+
+    def _load(name, path):
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+
+    sys.modules["luolib.types"].__dict__.update(param3_t=tuple)
+    _stub("monai")
+    _stub("monai.utils", StrEnum=enum.StrEnum)
+
+    def compose(*fs):  # cytoolz.compose: right-to-left function composition
+        def run(x):
+            for f in reversed(fs):
+                x = f(x)
+            return x
+        return run
+
+    _stub("cytoolz", compose=compose)
+    rs = _load("luolib.models.spadop.resample", luo + "/models/spadop/resample.py")
+    sys.modules["luolib.models"].spadop = _stub("luolib.models.spadop", resample=rs.resample)
+    ein = _load("luolib.utils.einops", luo + "/utils/einops.py")
+    _stub("luolib.utils", flatten=ein.flatten, spatialize=ein.spatialize)
+    _load("mmmm.utils", ref + "/utils.py")
+    sys.modules["mmmm.models"].resample = _load("mmmm.models.resample", ref + "/models/resample.py")
+    sys.modules["xformers.ops"].memory_efficient_attention = memory_efficient_attention_any
+    sys.modules["xformers.ops"].fmha = sys.modules["xformers.ops.fmha"]
+    sys.modules["xformers.ops.fmha"].BlockDiagonalMask = BlockDiagonalMask
+    sys.modules["xformers"].ops = sys.modules["xformers.ops"]
+    _LOADED_VISUAL = _load("mmmm.models.cogvlm.visual", ref + "/models/cogvlm/visual.py")
+    return _LOADED_VISUAL
+
+
+def make_reference_vision(cfg, weights, dtype=torch.float32):
+    """A reference ``EVA2CLIPModel`` holding ``weights`` (oracle/oracle_vision.py key layout == its state dict).
+    ``cfg`` is an ``oracle_vision.VisionConfig``."""
+    V = load_reference_visual()
+    config = types.SimpleNamespace(
+        hidden_size=cfg.lm_hidden_size, intermediate_size=cfg.lm_intermediate_size,
+        vision_config=dict(hidden_size=cfg.hidden_size, num_heads=cfg.num_heads, intermediate_size=cfg.intermediate_size,
+                           num_hidden_layers=cfg.num_hidden_layers, layer_norm_eps=cfg.layer_norm_eps,
+                           in_channels=cfg.in_channels, patch_size=tuple(cfg.patch_size),
+                           pos_embed_shape=tuple(cfg.pos_embed_shape), pt_pos_embed_shape=tuple(cfg.pos_embed_shape[1:]),
+                           hidden_act=cfg.hidden_act, dropout_prob=0.0))
+    model = V.EVA2CLIPModel(config)
+    missing, unexpected = model.load_state_dict({k: v.clone() for k, v in weights.items()}, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    return model.to(dtype).eval()

@@ -1,0 +1,263 @@
+"""GPU parity tests of the vision-encoder path: the new kernels through the C ABI against
+plain fp32 / ATen restatements of the same op, and the drop-in ``EVA2CLIPModel`` against the oracle
+(oracle/oracle_vision.py, pinned bit-exact to the unmodified reference) and the committed reference fixture.
+Row moves and max-pooling are bit-exact; floating point within the tolerance written in each test
+(bf16: max-abs error / max-abs reference <= 2e-2 and relative Frobenius <= 1e-2, BASELINE.json north_star)."""
+import os
+from types import SimpleNamespace
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle_vision as OV  # noqa: E402
+
+BF = torch.bfloat16
+
+
+def _ops():
+    from mmmm_b200 import ops
+    return ops
+
+
+def _err(got, want):
+    got, want = got.float().cpu(), want.float().cpu()
+    return (float((got - want).abs().max() / want.abs().max().clamp_min(1e-6)),
+            float((got - want).norm() / want.norm().clamp_min(1e-6)))
+
+
+def _counts(n):
+    return torch.tensor([n, 0, 0, 0], dtype=torch.int32, device="cuda")
+
+
+# ------------------------------------------------------------------------------------------ K3 bias / GELU epilogue
+@pytest.mark.parametrize("pair", ["1", "0"])
+@pytest.mark.parametrize("rows,K,N,gelu", [(300, 256, 512, False), (1226, 1792, 1536, True), (77, 1792, 6144, False),
+                                           (515, 2048, 1792, False), (130, 768, 1792, True)])
+def test_linear_bias_act(rows, K, N, gelu, pair, monkeypatch):
+    monkeypatch.setenv("VEX_GEMM_PAIR", pair)
+    g = torch.Generator().manual_seed(rows + N)
+    a = torch.randn(rows + 40, K, generator=g).to(BF)
+    w = (torch.randn(N, K, generator=g) * 0.05).to(BF)
+    b = torch.randn(N, generator=g).to(BF)
+    out = torch.full((rows + 40, N), 7.0, dtype=BF, device="cuda")
+    _ops().linear_bias_act(a.cuda(), w.cuda(), b.cuda(), out, _counts(rows), None, False, gelu)
+    want = F.linear(a[:rows].float(), w.float(), b.float()).to(BF)  # one rounding after the bias (cuBLASLt epilogue)
+    if gelu:
+        want = F.gelu(want.float()).to(BF)
+    mx, fro = _err(out[:rows], want)
+    assert mx <= 8e-3 and fro <= 4e-3, (mx, fro)
+    assert (out[rows:] == 7.0).all()  # rows past the live count are not written
+
+
+def test_linear_bias_accumulate_row_map():
+    """The patch-convolution form: out[map(r)] += bf16(a[r] . w^T + bias), rows the map skips stay untouched."""
+    g = torch.Generator().manual_seed(5)
+    rows, K, N = 200, 192, 256
+    a = torch.randn(rows, K, generator=g).to(BF)
+    w = (torch.randn(N, K, generator=g) * 0.05).to(BF)
+    b = torch.randn(N, generator=g).to(BF)
+    base = torch.randn(rows + 10, N, generator=g).to(BF)
+    perm = torch.randperm(rows + 10, generator=g)[:rows].int()
+    out = base.clone().cuda()
+    _ops().linear_bias_act(a.cuda(), w.cuda(), b.cuda(), out, _counts(rows), perm.cuda(), True, False)
+    want = base.clone()
+    want[perm.long()] = (F.linear(a.float(), w.float(), b.float()).to(BF).float() + base[perm.long()].float()).to(BF)
+    mx, fro = _err(out, want)
+    assert mx <= 8e-3 and fro <= 4e-3, (mx, fro)
+    untouched = torch.ones(rows + 10, dtype=torch.bool)
+    untouched[perm.long()] = False
+    assert torch.equal(out.cpu()[untouched], base[untouched])
+
+
+# ------------------------------------------------------------------------------------------ K11 row-wise kernels
+@pytest.mark.parametrize("H", [256, 1792, 2048, 4096])
+@pytest.mark.parametrize("mode", ["plain", "residual", "gelu"])
+def test_layernorm(H, mode):
+    g = torch.Generator().manual_seed(H)
+    rows = 333
+    x = (torch.randn(rows + 5, H, generator=g) * 2 + 0.3).to(BF)
+    w = (1 + 0.1 * torch.randn(H, generator=g)).to(BF)
+    b = (0.1 * torch.randn(H, generator=g)).to(BF)
+    res = torch.randn(rows + 5, H, generator=g).to(BF)
+    eps = 1e-6 if mode != "gelu" else 1e-5
+    out = res.clone().cuda() if mode == "residual" else torch.zeros(rows + 5, H, dtype=BF, device="cuda")
+    _ops().layernorm(x.cuda(), w.cuda(), b.cuda(), eps, mode == "residual", mode == "gelu", _counts(rows), out)
+    t = F.layer_norm(x[:rows].float(), (H,), w.float(), b.float(), eps).to(BF)
+    if mode == "gelu":
+        t = F.gelu(t.float()).to(BF)
+    if mode == "residual":
+        t = (res[:rows].float() + t.float()).to(BF)
+    # fp32 statistics in a different summation order: at most one bf16 ulp on isolated elements
+    mx, fro = _err(out[:rows], t)
+    assert mx <= 8e-3 and fro <= 2e-3, (mx, fro)
+    tail = res[rows:] if mode == "residual" else torch.zeros(5, H, dtype=BF)
+    assert torch.equal(out[rows:].cpu(), tail)
+
+
+@pytest.mark.parametrize("shape,ps", [((3, 4, 32, 48), (4, 8, 8)), ((3, 1, 42, 56), (1, 14, 14)),
+                                      ((3, 8, 64, 64), (2, 16, 16)), ((1, 3, 20, 24), (1, 4, 8))])
+def test_patchify_bit_exact(shape, ps):
+    g = torch.Generator().manual_seed(sum(shape))
+    img = torch.randn(*shape, generator=g).to(BF)
+    C, D, H, W = shape
+    gd, gh, gw = D // ps[0], H // ps[1], W // ps[2]
+    K = C * ps[0] * ps[1] * ps[2]
+    kpad = (K + 63) // 64 * 64
+    out = torch.zeros(gd * gh * gw, kpad, dtype=BF, device="cuda")
+    _ops().patchify(img.cuda(), ps[0], ps[1], ps[2], out)
+    want = img[:, :gd * ps[0], :gh * ps[1], :gw * ps[2]].reshape(C, gd, ps[0], gh, ps[1], gw, ps[2])
+    want = want.permute(1, 3, 5, 0, 2, 4, 6).reshape(gd * gh * gw, K)
+    assert torch.equal(out[:, :K].cpu(), want) and (out[:, K:] == 0).all()
+    # and the convolution it stands for: conv3d(stride == kernel) == patches . weight.reshape(C_out, -1)^T
+    w = torch.randn(16, C, *ps, generator=g)
+    conv = F.conv3d(img.float()[None], w, None, ps)[0].flatten(1).t()
+    torch.testing.assert_close(want.float() @ w.reshape(16, -1).t(), conv, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("grid,pool", [((4, 8, 8), (2, 2, 2)), ((3, 7, 5), (1, 2, 2)), ((1, 35, 35), (1, 1, 1)),
+                                       ((8, 4, 4), (4, 1, 2))])
+def test_maxpool_tokens_bit_exact(grid, pool):
+    g = torch.Generator().manual_seed(sum(grid))
+    C = 256
+    n = grid[0] * grid[1] * grid[2]
+    x = torch.randn(n + 1, C, generator=g).to(BF)  # row 0 plays the class token that is dropped
+    og = tuple(a // b for a, b in zip(grid, pool))
+    out = torch.zeros(og[0] * og[1] * og[2], C, dtype=BF, device="cuda")
+    _ops().maxpool_tokens(x.cuda()[1:], list(grid), list(pool), out)
+    want = F.max_pool3d(x[1:].float().t().reshape(1, C, *grid), pool).flatten(2)[0].t().to(BF)
+    assert torch.equal(out.cpu(), want)
+
+
+def test_scatter_rows_bit_exact():
+    g = torch.Generator().manual_seed(1)
+    table = torch.randn(2, 512, generator=g).to(BF)
+    out = torch.zeros(20, 512, dtype=BF, device="cuda")
+    src = torch.tensor([0, 1, 0, 1, 0], dtype=torch.int32)
+    dst = torch.tensor([3, 9, 10, 19, -1], dtype=torch.int32)
+    _ops().scatter_rows(table.cuda(), src.cuda(), dst.cuda(), out)
+    want = torch.zeros(20, 512, dtype=BF)
+    want[dst[:4].long()] = table[src[:4].long()]
+    assert torch.equal(out.cpu(), want)
+
+
+# ------------------------------------------------------------------------------------------ K4 non-causal
+@pytest.mark.parametrize("lens,heads", [([129, 17, 256, 300], 2), ([1226, 1226], 16), ([1, 128, 127], 3)])
+def test_attention_blockdiag(lens, heads):
+    g = torch.Generator().manual_seed(sum(lens))
+    B, max_len = len(lens), max(lens)
+    T = sum(lens)
+    cap = B * max_len
+    qkv = torch.randn(cap, 3, heads, 128, generator=g).to(BF)
+    qkv[T:] = float("nan")  # the kernel must never let rows past the live tokens leak in
+    cu = torch.tensor([0] + torch.tensor(lens).cumsum(0).tolist(), dtype=torch.int32)
+    out = torch.zeros(cap, heads * 128, dtype=BF, device="cuda")
+    scale = 112 ** -0.5  # the vision heads are 112 wide inside their 128 slot
+    _ops().attention_blockdiag(qkv.reshape(cap, -1).cuda(), cu.cuda(), B, max_len, heads, out, scale)
+    q, k, v = (qkv[:T, i][None] for i in range(3))
+    want = OV.blockdiag_attention(q, k, v, lens, scale)[0].reshape(T, -1)
+    mx, fro = _err(out[:T], want)
+    assert mx <= 2e-2 and fro <= 1e-2, (mx, fro)
+    assert torch.isfinite(out[:T].float()).all()
+
+
+# ------------------------------------------------------------------------------------------ the drop-in module
+def _build(cfg: OV.VisionConfig, w):
+    from mmmm_b200.visual import EVA2CLIPModel
+    vc = dict(hidden_size=cfg.hidden_size, num_heads=cfg.num_heads, intermediate_size=cfg.intermediate_size,
+              num_hidden_layers=cfg.num_hidden_layers, layer_norm_eps=cfg.layer_norm_eps, in_channels=cfg.in_channels,
+              patch_size=tuple(cfg.patch_size), pos_embed_shape=tuple(cfg.pos_embed_shape), hidden_act="gelu")
+    model = EVA2CLIPModel(SimpleNamespace(hidden_size=cfg.lm_hidden_size, intermediate_size=cfg.lm_intermediate_size,
+                                          vision_config=vc))
+    model.load_state_dict(w)
+    return model.to(BF).cuda().eval()
+
+
+def _check_features(got, want, tol=(2e-2, 1e-2)):
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert tuple(a.shape) == tuple(b.shape)
+        mx, fro = _err(a, b)
+        assert mx <= tol[0] and fro <= tol[1], (mx, fro)
+
+
+def test_module_matches_reference_fixture(golden_dir):
+    """Drop-in EVA2CLIPModel vs the outputs of the UNMODIFIED reference (bf16 run) stored in the fixture: four images,
+    three patch sizes (depth-reduced kernels), resampled position embeddings, two pooled images."""
+    c = torch.load(os.path.join(golden_dir, "vision_tiny.pt"), weights_only=False)
+    cfg = OV.VisionConfig(**c["config"])
+    model = _build(cfg, c["weights"])
+    with torch.no_grad():
+        got = model([i.cuda() for i in c["images"]], c["patch"], c["pool"])
+    _check_features(got, c["bf16"]["features"])
+    # ... and no further from the fp32 reference than the reference's own bf16 run is (x1.5)
+    for a, r16, r32 in zip(got, c["bf16"]["features"], c["fp32"]["features"]):
+        assert _err(a, r32)[1] <= 1.5 * _err(r16, r32)[1] + 1e-3
+
+
+@pytest.mark.parametrize("layers", [1, 3])
+def test_module_head_dim_112_vs_oracle(layers):
+    """EVA2-CLIP-E geometry (1792 = 16 heads x 112, zero-padded head slots), upstream 14 x 14 patches (K = 588 is
+    not a multiple of 64: zero-padded im2col), ragged image sizes."""
+    cfg = OV.VisionConfig(hidden_size=1792, num_heads=16, intermediate_size=1024, num_hidden_layers=layers,
+                          patch_size=(1, 14, 14), pos_embed_shape=(1, 6, 6), lm_hidden_size=512,
+                          lm_intermediate_size=768)
+    w = OV.random_vision_weights(cfg, seed=31, dtype=BF)
+    imgs = OV.random_images([(1, 84, 84), (1, 140, 70), (1, 56, 210)], seed=32, dtype=BF)
+    ps, pool = [(1, 14, 14)] * 3, [(1, 1, 1), (1, 2, 1), (1, 1, 1)]
+    want = OV.eva2clip(w, imgs, ps, pool, cfg)
+    model = _build(cfg, w)
+    with torch.no_grad():
+        got = model([i.cuda() for i in imgs], ps, pool)
+    _check_features(got, want)
+
+
+def test_encode_into_matches_scatter():
+    """encode_into == CogVLMModel.forward's feature scatter (modeling_cogvlm.py:450-453) over the oracle's features;
+    text rows stay bit-identical; a second call with new weights sees them (derived-copy cache keyed on versions)."""
+    cfg = OV.VisionConfig(hidden_size=256, num_heads=2, intermediate_size=512, num_hidden_layers=2,
+                          patch_size=(2, 8, 8), pos_embed_shape=(2, 4, 4), lm_hidden_size=256, lm_intermediate_size=512)
+    w = OV.random_vision_weights(cfg, seed=41, dtype=BF)
+    imgs = OV.random_images([(2, 32, 32), (4, 32, 32)], seed=42, dtype=BF)
+    ps, pool = [(2, 8, 8), (2, 8, 8)], [(1, 1, 1), (2, 2, 2)]
+    g = torch.Generator().manual_seed(43)
+    emb = torch.randn(2, 40, 256, generator=g).to(BF)
+    model = _build(cfg, w)
+    for round_ in range(2):
+        feats = OV.eva2clip(w, imgs, ps, pool, cfg)
+        want = OV.scatter_image_features(emb, feats)
+        got = emb.clone().cuda()
+        with torch.no_grad():
+            assert model.encode_into(got, [i.cuda() for i in imgs], ps, pool) is got
+        touched = torch.zeros(2, 40, dtype=torch.bool)
+        for i, f in enumerate(feats):
+            touched[i, 1:1 + f.shape[1]] = True
+        assert torch.equal(got.cpu()[~touched], emb[~touched])
+        mx, fro = _err(got.cpu()[touched], want[touched])
+        assert mx <= 2e-2 and fro <= 1e-2, (mx, fro)
+        # boi / eoi rows are copies
+        assert torch.equal(got.cpu()[0, 1], w["boi"].reshape(-1)) and torch.equal(got.cpu()[1, feats[1].shape[1]], w["eoi"].reshape(-1))
+        # perturb the weights in place for the second round
+        w = {k: (v * 1.5).to(BF) if k.endswith("query_key_value.weight") or k.endswith("position_embedding.weight") else v
+             for k, v in w.items()}
+        with torch.no_grad():
+            for k, v in model.state_dict().items():
+                v.copy_(w[k])
+
+
+def test_full_width_layer_vs_oracle():
+    """One full-width EVA2-CLIP-E layer (1792 / 15360, 16 x 112) + the full-width GLU projector (4096 / 11008) on two
+    490 x 490 images (1226 tokens each, the BASELINE vision-token count)."""
+    cfg = OV.VisionConfig(hidden_size=1792, num_heads=16, intermediate_size=15360, num_hidden_layers=1,
+                          patch_size=(1, 14, 14), pos_embed_shape=(1, 35, 35))
+    w = OV.random_vision_weights(cfg, seed=51, dtype=BF)
+    imgs = OV.random_images([(1, 490, 490)] * 2, seed=52, dtype=BF)
+    ps, pool = [(1, 14, 14)] * 2, [(1, 1, 1)] * 2
+    want = OV.eva2clip(w, imgs, ps, pool, cfg)
+    model = _build(cfg, w)
+    with torch.no_grad():
+        got = model([i.cuda() for i in imgs], ps, pool)
+    assert got[0].shape == (1, 1227, 4096)
+    _check_features(got, want)
