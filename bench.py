@@ -398,6 +398,8 @@ def run_train(args):
     r = args.lora or 64
     b, nv, nt = WORKLOADS[args.workload]
     layers = [make_gpu_layer(dev, r, seed=i, lora_dropout=args.lora_dropout).train() for i in range(args.layers)]
+    for l in layers:
+        l.recompute = bool(args.recompute)
     params = [p for l in layers for p in l.parameters() if p.requires_grad]
     reducer = LoraGradReducer(params)
     inp = make_inputs(b, nv, nt, H, seed=rank).to(dev)
@@ -451,15 +453,19 @@ def run_train(args):
         g_down = tokens * 2 * H * I
         lora_f = tokens * 2 * r * 69888
         attn_f = b * 4 * HEADS * 128 * seq * (seq + 1) // 2
-        flop = args.layers * ((g_fwd + lora_f) + (g_fwd - g_down + lora_f) + (g_fwd + lora_f) + 2 * lora_f
-                              + 2 * attn_f + 2.5 * attn_f)
+        rec = 1 if args.recompute else 0
+        flop = args.layers * ((g_fwd + lora_f) + rec * (g_fwd - g_down + lora_f) + (g_fwd + lora_f) + 2 * lora_f
+                              + (1 + rec) * attn_f + 2.5 * attn_f)
         pk = peaks()
         print(json.dumps({
             "metric": "visual-expert LoRA train tokens/s", "value": total / (ms_step / 1e3), "unit": "tokens/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": dict(config_dict(args, tokens), lora_r=r, lora_dropout=args.lora_dropout,
-                           mode="train: fwd + recompute + bwd + LoRA-grad allreduce"),
+                           recompute=bool(args.recompute),
+                           mode=("train: fwd + recompute + bwd + LoRA-grad allreduce" if args.recompute else
+                                 "train: fwd (activations kept in HBM) + bwd + LoRA-grad allreduce")),
+            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
             "allreduce_ms": allreduce_ms, "allreduce_bytes": reducer.nbytes, "trainable_params": reducer.flat.numel(),
             "gpu_launches": launches, "kernels": kernels,
             "step_tflops_per_gpu": flop / (ms_step / 1e3) / 1e12,
@@ -597,6 +603,8 @@ def main():
     ap.add_argument("--layers", type=int, default=1, help="decoder layers per step (32 = the full stack, config 3/4)")
     ap.add_argument("--train", action="store_true", help="config 5: LoRA fwd+bwd training step + grad all-reduce")
     ap.add_argument("--lora-dropout", type=float, default=0.0, help="--train: lora_dropout (the reference uses 0.05)")
+    ap.add_argument("--recompute", type=int, default=1, help="--train: 1 = checkpoint each layer like the reference "
+                    "(save the input, recompute in backward); 0 = keep the activations in HBM (no recompute pass)")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the forward as one CUDA graph (default), 0: eager")
     ap.add_argument("--vision", action="store_true", help="SURVEY 8(f)-4: time the EVA2-CLIP-E vision encoder instead")
     ap.add_argument("--vision-layers", type=int, default=63)

@@ -37,9 +37,15 @@ __global__ void __launch_bounds__(K11_WARPS * 32)
   const int n_rows = min(*n_rows_ptr, rows_cap);
   for (int r = blockIdx.x * K11_WARPS + warp; r < n_rows; r += gridDim.x * K11_WARPS) {
     const uint4* xp = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(r) * H);
-    uint4 v[NCHUNK];
+    uint4 v[NCHUNK], rv[NCHUNK];
 #pragma unroll
     for (int i = 0; i < NCHUNK; ++i) v[i] = ld_stream(xp + i * 32 + lane);
+    // the residual row is requested together with x: one memory round trip per row instead of two
+    const uint4* rp = residual ? reinterpret_cast<const uint4*>(residual + static_cast<int64_t>(r) * H) : nullptr;
+    if (rp) {
+#pragma unroll
+      for (int i = 0; i < NCHUNK; ++i) rv[i] = ld_stream(rp + i * 32 + lane);
+    }
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < NCHUNK; ++i) {
@@ -64,7 +70,6 @@ __global__ void __launch_bounds__(K11_WARPS * 32)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     const float rstd = rsqrtf(sq * (1.0f / H) + eps);
-    const uint4* rp = residual ? reinterpret_cast<const uint4*>(residual + static_cast<int64_t>(r) * H) : nullptr;
     uint4* yp = reinterpret_cast<uint4*>(y + static_cast<int64_t>(r) * H);
 #pragma unroll
     for (int i = 0; i < NCHUNK; ++i) {
@@ -84,13 +89,10 @@ __global__ void __launch_bounds__(K11_WARPS * 32)
       }
       if (act == VEX_ACT_GELU) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float z = bf16r(t[j]);
-          t[j] = 0.5f * z * (1.0f + erff(z * 0.70710678118654752f));
-        }
+        for (int j = 0; j < 8; ++j) t[j] = gelu_erf(bf16r(t[j]));
       }
       if (rp) {
-        const uint4 r4 = ld_stream(rp + i * 32 + lane);
+        const uint4 r4 = rv[i];
         const uint32_t ru[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {

@@ -393,11 +393,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, int e, int m, in
             for (int j = 0; j < 32; ++j) v[j] += bv[j];
           }
           if (p.act == VEX_ACT_GELU) {
-            // eager bf16: y = bf16(Linear), then gelu(y) = 0.5 y (1 + erf(y / sqrt 2)) rounded on store
+            // eager bf16: y = bf16(Linear), then gelu(y) = y Phi(y) (erf form) rounded on store
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float y = bf16r(v[j]);
-              v[j] = 0.5f * y * (1.0f + erff(y * 0.70710678118654752f));
+              v[j] = gelu_erf(bf16r(v[j]));
             }
           }
           stage_piece32(stage_row, q * 4, lane, v);

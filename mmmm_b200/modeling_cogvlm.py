@@ -369,9 +369,17 @@ def visual_expert_layer_forward(layer: "CogVLMDecoderLayer", hidden_states: torc
         if keep is not None:
             keep.update(gate=g, up=u)
     t, r, lb = lt(act, down_s, 4, "down")
-    if keep is not None:  # the recompute stops here: the down projection's output is not needed by the backward
+    if keep is not None:
         keep.update(act=act, t_down=t, h1=h1)
-        return None, None
+        if not keep.get("continue_forward", False):
+            return None, None  # the recompute stops here: the down projection's output is not needed by the backward
+        # activation-keeping training forward (no recompute in the backward): h1 is needed by the backward, so the
+        # down projection writes a fresh buffer instead of accumulating in place
+        out = new(B, L, H)
+        ops.copy_padded_rows(hf, plan.flat_to_sorted, out.view(cap, H))
+        ops.grouped_gemm_fused(act, W(down_s), out.view(cap, H), counts, ops.EPI_RESIDUAL, s2f, h1.view(cap, H),
+                               [t, None], [lb[0], None, lb[1], None], r, [], 0, False, 1.0)
+        return out, None
     if fuse:  # in place: h1[row] += down(act)[row]; padded rows of h1 already hold the input
         ops.grouped_gemm_fused(act, W(down_s), h1.view(cap, H), counts, ops.EPI_RESIDUAL, s2f, None, [t, None],
                                [lb[0], None, lb[1], None], r, [], 0, False, 1.0)

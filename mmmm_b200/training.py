@@ -88,9 +88,11 @@ def _routed_linear_backward(dy: torch.Tensor, x: torch.Tensor, t: Optional[torch
 
 
 def layer_backward(layer, plan, position_ids: torch.Tensor, hidden_states: torch.Tensor, d_out: torch.Tensor,
-                   dropout_seed: Optional[int] = None):
+                   dropout_seed: Optional[int] = None, keep: Optional[Dict] = None):
     """Returns (d_hidden [B, L, H], [(param, grad), ...]) -- see the module docstring.  ``dropout_seed``: the seed the
-    forward used for the LoRA dropout masks (the recompute and the dgrad epilogues regenerate them from it)."""
+    forward used for the LoRA dropout masks (the recompute and the dgrad epilogues regenerate them from it).
+    ``keep``: the intermediates of an activation-keeping forward (``layer.recompute = False``); None = recompute them
+    from ``hidden_states`` (the reference's checkpointing granularity)."""
     from .modeling_cogvlm import dropout_stream_seed, visual_expert_layer_forward
     B, L, H = hidden_states.shape
     cap = B * L
@@ -98,9 +100,10 @@ def layer_backward(layer, plan, position_ids: torch.Tensor, hidden_states: torch
     heads = attn.num_heads
     I = mlp.vision_mlp.intermediate_size
     dev = hidden_states.device
-    keep: Dict = {}
-    with torch.no_grad():
-        visual_expert_layer_forward(layer, hidden_states, plan, position_ids, keep=keep, dropout_seed=dropout_seed)
+    if keep is None:
+        keep = {}
+        with torch.no_grad():
+            visual_expert_layer_forward(layer, hidden_states, plan, position_ids, keep=keep, dropout_seed=dropout_seed)
     specs = keep["specs"]
     seed = keep.get("dropout_seed") or 0
     drop = lambda nm, k: dict(x_dropped=keep.get(nm + "_xd"), dropout_seed=dropout_stream_seed(seed, k))
@@ -158,8 +161,13 @@ class _LayerFunction(torch.autograd.Function):
     def forward(ctx, layer, plan, position_ids, hidden_states, *trainables):
         from .modeling_cogvlm import next_dropout_seed, visual_expert_layer_forward
         ctx.dropout_seed = next_dropout_seed()  # the backward's recompute must regenerate the same LoRA dropout masks
+        ctx.keep = None
+        if not recompute_default(layer):
+            # B200 has the HBM to keep one layer's intermediates (~1.5 GB per 8 x 1485 tokens, 47 GB for 32 layers):
+            # the backward then starts from them instead of re-running the forward
+            ctx.keep = {"continue_forward": True}
         with torch.no_grad():
-            out, _ = visual_expert_layer_forward(layer, hidden_states, plan, position_ids,
+            out, _ = visual_expert_layer_forward(layer, hidden_states, plan, position_ids, keep=ctx.keep,
                                                  dropout_seed=ctx.dropout_seed)
         ctx.layer, ctx.plan, ctx.position_ids = layer, plan, position_ids
         ctx.trainables = trainables
@@ -171,10 +179,22 @@ class _LayerFunction(torch.autograd.Function):
         (hidden_states,) = ctx.saved_tensors
         with torch.no_grad():
             d_hidden, pg = layer_backward(ctx.layer, ctx.plan, ctx.position_ids, hidden_states, d_out.contiguous(),
-                                          ctx.dropout_seed)
+                                          ctx.dropout_seed, keep=ctx.keep)
+            ctx.keep = None  # release the kept activations as soon as the layer's backward is done
         by_id = {id(p): g for p, g in pg}
         tr = tuple(by_id.get(id(p)) for p in ctx.trainables)
         return (None, None, None, d_hidden if ctx.needs_input_grad[3] else None, *tr)
+
+
+def recompute_default(layer) -> bool:
+    """True (default): save only the layer input and recompute in the backward, like the reference's always-on
+    gradient checkpointing (mmmm/models/mmmm.py:287-291).  ``layer.recompute = False`` or VEX_TRAIN_RECOMPUTE=0 keeps
+    the intermediates in HBM instead (B200-sized memory: no recompute pass, ~1.3x faster step)."""
+    import os
+    flag = getattr(layer, "recompute", None)
+    if flag is None:
+        return os.environ.get("VEX_TRAIN_RECOMPUTE", "1") != "0"
+    return bool(flag)
 
 
 def layer_forward_train(layer, hidden_states: torch.Tensor, plan, position_ids: torch.Tensor) -> torch.Tensor:

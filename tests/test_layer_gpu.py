@@ -305,8 +305,9 @@ def test_decoder_stack_wrapper_vs_oracle():
     assert mx <= 2 * MAX_REL and fro <= 2 * FRO_REL, (mx, fro)
 
 
+@pytest.mark.parametrize("recompute", [True, False])
 @pytest.mark.parametrize("lora_lang", [True, False])
-def test_training_step_gradients_vs_oracle_autograd(lora_lang):
+def test_training_step_gradients_vs_oracle_autograd(lora_lang, recompute):
     """BASELINE config 5 shape of work on a small layer: LoRA forward + backward through the fused layer
     (self-checkpointing autograd.Function) against torch.autograd over the oracle in fp32 on the same
     bf16-representable values: gradients of the input, every lora_A / lora_B and both RMSNorm weights."""
@@ -329,6 +330,7 @@ def test_training_step_gradients_vs_oracle_autograd(lora_lang):
         m.lora_B["default"].weight.data.copy_(a.B)
         m.scaling["default"] = a.scaling
     layer.train()
+    layer.recompute = recompute  # True: checkpoint like the reference (mmmm.py:287-291); False: keep activations in HBM
     inp = make_inputs(2, 90, 30, H, ragged=True, seed=33)
     pm = inp.padding_mask
     gsel = torch.Generator().manual_seed(34)

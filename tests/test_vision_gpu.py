@@ -208,10 +208,17 @@ def test_module_head_dim_112_vs_oracle(layers):
     imgs = OV.random_images([(1, 84, 84), (1, 140, 70), (1, 56, 210)], seed=32, dtype=BF)
     ps, pool = [(1, 14, 14)] * 3, [(1, 1, 1), (1, 2, 1), (1, 1, 1)]
     want = OV.eva2clip(w, imgs, ps, pool, cfg)
+    want32 = OV.eva2clip({k: v.float() for k, v in w.items()}, [i.float() for i in imgs], ps, pool, cfg)
     model = _build(cfg, w)
     with torch.no_grad():
         got = model([i.cuda() for i in imgs], ps, pool)
-    _check_features(got, want)
+    # With these narrow random weights the reference's OWN bf16 run sits 0.9-1.1e-2 (relative Frobenius) away from its
+    # fp32 run, so two bf16 realisations differ by up to ~1.4e-2: the bars are max-abs error <= 2e-2 of the reference
+    # maximum (north_star), Frobenius <= 2e-2, and no further from the fp32 reference than 1.5x the reference's own
+    # bf16 run (SURVEY section 7 tolerance definition).
+    _check_features(got, want, tol=(2e-2, 2e-2))
+    for a, r16, r32 in zip(got, want, want32):
+        assert _err(a, r32)[1] <= 1.5 * _err(r16, r32)[1], (_err(a, r32), _err(r16, r32))
 
 
 def test_encode_into_matches_scatter():
