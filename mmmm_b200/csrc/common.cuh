@@ -73,10 +73,21 @@ __device__ __forceinline__ uint32_t dropout_hash(uint64_t pair_index, uint32_t s
 // Abramowitz-Stegun 7.1.26 form erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2), t = 1 / (1 + p z), z >= 0
 // (absolute error 1.5e-7, far below the bf16 rounding that follows).  Branch-free, two MUFU ops (rcp, ex2) -- erff()
 // costs 2-3x as many issue slots and diverges, which made the fc1 epilogue of the vision MLP the bottleneck of its GEMM.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float gelu_erf(float y) {
-  const float z = fabsf(y) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  const float e = exp2f(-z * z * 1.4426950408889634f);
+  // single MUFU.RCP / MUFU.EX2 (approx, ~1e-7 relative): __frcp_rn / exp2f expand to guarded multi-instruction
+  // sequences that made this 3x slower than the polynomial itself
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, fabsf(y), 1.0f));
+  const float e = ex2_approx(y * y * (-0.5f * 1.4426950408889634f));
   float q = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
   q = fmaf(t, q, 0.5f * 1.421413741f);
   q = fmaf(t, q, 0.5f * -0.284496736f);
