@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VEX_ABI_VERSION 5
+#define VEX_ABI_VERSION 6
 
 #define VEX_OK 0
 #define VEX_E_INVALID (-1)     /* bad argument (null pointer, size, alignment) */
@@ -116,9 +116,10 @@ int vex_copy_padded_rows(const void* x, const int32_t* flat_to_sorted, void* out
                                  the LoRA input dropout (PEFT lora.Linear: lora_A(dropout(x))), mask as vex_dropout_rows */
 
 #define VEX_EPI_CE 5       /* fused lm_head + cross-entropy, forward (CogVLMForCausalLM.forward :701-706 +
-                              _sample_weighted_ce :610-627): no logits are written; per row r and 256-column tile t
+                              _sample_weighted_ce :610-627): no logits are written; per row r and 128-column half tile t
                               ce_pmax[r, t] = max_j z, ce_psum[r, t] = sum_j exp(z - max), ce_zlabel[r] = z[label_r],
-                              z = bf16-rounded logit.  single_expert, N = vocabulary (tiles = ceil(N / 256)) */
+                              z = bf16-rounded logit.  single_expert, N = vocabulary, slots per row = 2 * ceil(N / 256)
+                              (an empty slot holds max = -inf, sum = 0) */
 #define VEX_EPI_CE_BWD 6   /* backward: out[r, j] = bf16((exp(z - ce_lse[r]) - [j == label_r]) * ce_w[r] * ce_dloss[0]
                               / counts[0]) -- d(loss)/d(logits), the A operand of the lm_head dgrad GEMM */
 
@@ -160,8 +161,8 @@ typedef struct vexGemmArgs {
   float dropout_p;          /* VEX_EPI_DROPOUT_ACC: drop probability and seed of the forward vex_dropout_rows call; */
   uint64_t dropout_seed;    /*   the mask index is sorted_row * N + col */
   const int32_t* ce_labels; /* VEX_EPI_CE / CE_BWD: label of row r (device, from vex_label_rows) */
-  float* ce_pmax;           /* VEX_EPI_CE out: [rows_cap, ceil(N/256)] fp32 */
-  float* ce_psum;           /* VEX_EPI_CE out: [rows_cap, ceil(N/256)] fp32 */
+  float* ce_pmax;           /* VEX_EPI_CE out: [rows_cap, 2 * ceil(N/256)] fp32 */
+  float* ce_psum;           /* VEX_EPI_CE out: [rows_cap, 2 * ceil(N/256)] fp32 */
   float* ce_zlabel;         /* VEX_EPI_CE out: [rows_cap] fp32 */
   const float* ce_lse;      /* VEX_EPI_CE_BWD: [rows_cap] natural-log log-sum-exp (vex_ce_reduce) */
   const float* ce_w;        /* VEX_EPI_CE_BWD: [rows_cap] per-row weight (vex_label_rows) */

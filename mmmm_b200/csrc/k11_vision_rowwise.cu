@@ -20,7 +20,7 @@ constexpr int K11_WARPS = 8;
 // one warp per row, the row stays in registers (NCHUNK x 16 B per lane), two-pass variance
 // ---------------------------------------------------------------------------------------------
 template <int NCHUNK>  // H = NCHUNK * 256
-__global__ void __launch_bounds__(K11_WARPS * 32)
+__global__ void __launch_bounds__(K11_WARPS * 32, NCHUNK <= 8 ? 2 : 1)  // <= 128 registers: 16 warps per SM
     k11_layernorm(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ weight,
                   const __nv_bfloat16* __restrict__ bias, float eps, const __nv_bfloat16* residual, int act,
                   const int32_t* __restrict__ n_rows_ptr, __nv_bfloat16* y, int rows_cap) {

@@ -260,8 +260,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, int e, int m, in
     }
     release();
     if (valid) {
-      p.ce_pmax[static_cast<int64_t>(s_row) * p.ce_tiles + n] = m;
-      p.ce_psum[static_cast<int64_t>(s_row) * p.ce_tiles + n] = ssum;
+      const int64_t slot = static_cast<int64_t>(s_row) * p.ce_tiles + 2 * n;
+      p.ce_pmax[slot] = m;
+      p.ce_psum[slot] = ssum;
+      p.ce_pmax[slot + 1] = -INFINITY;  // the half-tile slot the CTA-pair kernel would fill: contributes exp(-inf) * 0
+      p.ce_psum[slot + 1] = 0.f;
       if (has) p.ce_zlabel[s_row] = zl;
     }
     __syncwarp();
@@ -410,6 +413,261 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, int e, int m, in
       write_panel(g_row, col0, p.mode == VEX_EPI_RESIDUAL || p.mode == VEX_EPI_DROPOUT_ACC);
       __syncwarp();
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair kernel epilogue: EIGHT epilogue warps, two per SM sub-partition.  Warps w and w + 4 share TMEM lane
+// quarter w % 4 and split the 256 accumulator columns (half = 0 / 1 -> columns [128 half, 128 half + 128)); each warp
+// stages 64 output columns at a time (32 rows x 128 B = 4 KB per warp, the same 32 KB in total as the 4-warp layout).
+// Why: with one warp per sub-partition the epilogue issues at IPC ~0.3 (nothing to switch to while a TMEM load, a
+// MUFU result or a bias load is outstanding); for short-K GEMMs (the vision encoder's K = 1792: 14 k cycles of
+// mainloop per tile) that made the EPILOGUE the bound -- tensor pipe 62 % active, profiles/r1_vision_fc1_gelu_v1.md.
+// ---------------------------------------------------------------------------------------------
+struct CeRow {
+  int label;
+  float lse2, coef;
+};
+
+// one 32-column chunk of the PLAIN / RESIDUAL / DROPOUT_ACC / CE_BWD epilogues (+ bias, + GELU): raw fp32 accumulator
+// bits -> v (fp32 values that the bf16 pack rounds)
+__device__ __forceinline__ void chunk_math(const GemmDev& p, const uint32_t (&raw)[32], float (&v)[32], int cbase,
+                                           int s_row, const CeRow& ce) {
+  if (p.mode == VEX_EPI_PLAIN) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
+  } else if (p.mode == VEX_EPI_CE_BWD) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float z = bf16r(__uint_as_float(raw[j]));
+      const float sm = exp2f(fmaf(z, 1.4426950408889634f, -ce.lse2));
+      v[j] = (sm - (cbase + j == ce.label ? 1.f : 0.f)) * ce.coef;
+    }
+  } else if (p.mode == VEX_EPI_DROPOUT_ACC) {
+    const uint64_t pair0 = (static_cast<uint64_t>(s_row) * p.N + cbase) >> 1;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      const uint32_t hsh = dropout_hash(pair0 + (j >> 1), p.drop_seed_lo, p.drop_seed_hi);
+      v[j] = (hsh & 0xffffu) >= p.drop_thresh16 ? __uint_as_float(raw[j]) * p.alpha : 0.f;
+      v[j + 1] = (hsh >> 16) >= p.drop_thresh16 ? __uint_as_float(raw[j + 1]) * p.alpha : 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+  }
+  if (p.bias != nullptr && cbase < p.N) {
+    float bv[32];
+    load_bf16x32(p.bias + cbase, bv);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += bv[j];
+  }
+  if (p.act == VEX_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(bf16r(v[j]));
+  }
+}
+
+// rotary on 32 (j, j + 64) column pairs of one head: lo / hi = bf16-rounded q[j], q[j + 64]; first = columns j,
+// second = columns j + 64 (apply_rotary_pos_emb_index_bhs, modeling_cogvlm.py:188-193, eager-bf16 rounding points)
+__device__ __forceinline__ void rope_math(const GemmDev& p, int pos, int q, uint32_t (&lo)[32], uint32_t (&hi)[32],
+                                          float (&first)[32], float (&second)[32]) {
+  const __nv_bfloat16* cr = p.rope_cos + static_cast<int64_t>(pos) * 128 + q * 32;
+  const __nv_bfloat16* sr = p.rope_sin + static_cast<int64_t>(pos) * 128 + q * 32;
+  uint4 ct[4], st[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    ct[i] = __ldg(reinterpret_cast<const uint4*>(cr) + i);
+    st[i] = __ldg(reinterpret_cast<const uint4*>(sr) + i);
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    lo[j] = __float_as_uint(bf16r(__uint_as_float(lo[j])));
+    hi[j] = __float_as_uint(bf16r(__uint_as_float(hi[j])));
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const uint32_t cw = reinterpret_cast<const uint32_t*>(ct)[j >> 1];
+    const uint32_t sw = reinterpret_cast<const uint32_t*>(st)[j >> 1];
+    const float cj = (j & 1) ? bf16_hi(cw) : bf16_lo(cw);
+    const float sj = (j & 1) ? bf16_hi(sw) : bf16_lo(sw);
+    first[j] = bf16r(__uint_as_float(lo[j]) * cj) - bf16r(__uint_as_float(hi[j]) * sj);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    ct[i] = __ldg(reinterpret_cast<const uint4*>(cr + 64) + i);
+    st[i] = __ldg(reinterpret_cast<const uint4*>(sr + 64) + i);
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const uint32_t cw = reinterpret_cast<const uint32_t*>(ct)[j >> 1];
+    const uint32_t sw = reinterpret_cast<const uint32_t*>(st)[j >> 1];
+    const float cj = (j & 1) ? bf16_hi(cw) : bf16_lo(cw);
+    const float sj = (j & 1) ? bf16_hi(sw) : bf16_lo(sw);
+    second[j] = bf16r(__uint_as_float(hi[j]) * cj) + bf16r(__uint_as_float(lo[j]) * sj);
+  }
+}
+
+//   t_acc      : TMEM address of this warp's lane quarter at the accumulator's first column
+//   stage_base : this warp's 4 KB staging area (32 rows x 128 B)
+//   half       : which 128 accumulator columns this warp owns
+//   release()  : called exactly once by every warp, after its last TMEM read of the tile
+template <class Release>
+__device__ __forceinline__ void epilogue_tile_half(const GemmDev& p, int e, int m, int n, int cnt0, int cnt1,
+                                                   uint32_t t_acc, uint32_t stage_base, int lane, int ew, int half,
+                                                   Release release) {
+  constexpr int BN = 256;
+  constexpr int PITCH = 128;  // bytes per staged row: 64 bf16 columns
+  const uint32_t stage_row = stage_base + static_cast<uint32_t>(lane * PITCH);
+
+  // coalesced write-out of one staged 64-column piece: staged columns [0, 32) go to global columns [colA, colA + 32),
+  // staged columns [32, 64) to [colB, colB + 32) (colB = colA + 32 except for the rotary halves)
+  auto write_piece = [&](int g_row, int colA, int colB, bool add_residual) {
+#pragma unroll 4
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + (lane >> 3);
+      const int piece = lane & 7;
+      const int g = __shfl_sync(0xffffffffu, g_row, rr);
+      const int col = piece < 4 ? colA + piece * 8 : colB + (piece - 4) * 8;
+      if (g >= 0 && col < p.N) {
+        uint4 v = ld_shared_v4(stage_base + static_cast<uint32_t>(rr * PITCH + ((piece ^ (rr & 7)) << 4)));
+        const int64_t off = static_cast<int64_t>(g) * p.ldo + col;
+        if (add_residual) {
+          const uint4 r4 = ld_stream(p.residual + off);
+          const uint32_t a[4] = {v.x, v.y, v.z, v.w}, b[4] = {r4.x, r4.y, r4.z, r4.w};
+          uint32_t* vp = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            vp[j] = pack_bf16(bf16_lo(a[j]) + bf16_lo(b[j]), bf16_hi(a[j]) + bf16_hi(b[j]));
+        }
+        *reinterpret_cast<uint4*>(p.out + off) = v;
+      }
+    }
+  };
+
+  const int r_local = m * BM + ew * 32 + lane;
+  const bool valid = r_local < (e ? cnt1 : cnt0);
+  const int s_row = (e ? cnt0 : 0) + r_local;
+  int g_row = -1;
+  int pos = 0;
+  if (valid) {
+    g_row = p.row_map ? p.row_map[s_row] : s_row;
+    if (p.mode == VEX_EPI_ROPE) {
+      const int64_t pz = p.position_ids[p.sorted_to_flat[s_row]];
+      pos = static_cast<int>(min(max(pz, int64_t(0)), int64_t(p.rope_len - 1)));
+    }
+  }
+  uint32_t raw[32];
+  float v[32];
+
+  if (p.mode == VEX_EPI_CE) {
+    // per-row softmax statistics over this warp's 128 columns; the two halves of a tile write separate partial slots
+    // (ce_tiles counts 128-column half tiles for the pair kernel)
+    constexpr float L2E = 1.4426950408889634f;
+    const int label = valid ? p.ce_labels[s_row] : -1;
+    float mx = -INFINITY, ssum = 0.f, zl = 0.f;
+    bool has = false;
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+      const int cbase = n * BN + half * 128 + q * 32;
+      tmem_ld_32x32b_x32(t_acc + half * 128 + q * 32, raw);
+      tmem_ld_wait();
+      float cm = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] = (cbase + j < p.N) ? bf16r(__uint_as_float(raw[j])) : -INFINITY;
+        cm = fmaxf(cm, v[j]);
+        zl += (cbase + j == label) ? v[j] : 0.f;
+      }
+      if (cm > mx) {
+        ssum *= exp2f((mx - cm) * L2E);
+        mx = cm;
+      }
+      if (mx > -INFINITY) {
+        const float ml = mx * L2E;
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          a0 += exp2f(fmaf(v[j], L2E, -ml));
+          a1 += exp2f(fmaf(v[j + 1], L2E, -ml));
+        }
+        ssum += a0 + a1;
+      }
+      has = has || (label >= cbase && label < cbase + 32);
+    }
+    release();
+    if (valid) {
+      const int64_t slot = static_cast<int64_t>(s_row) * p.ce_tiles + 2 * n + half;
+      p.ce_pmax[slot] = mx;
+      p.ce_psum[slot] = ssum;
+      if (has) p.ce_zlabel[s_row] = zl;
+    }
+    __syncwarp();
+    return;
+  }
+  CeRow ce{-1, 0.f, 0.f};
+  if (p.mode == VEX_EPI_CE_BWD && valid) {
+    ce.label = p.ce_labels[s_row];
+    ce.lse2 = p.ce_lse[s_row] * 1.4426950408889634f;
+    ce.coef = p.ce_w[s_row] * p.ce_dloss[0] / static_cast<float>(max(cnt0, 1));
+  }
+
+  if (p.mode == VEX_EPI_SWIGLU) {
+    // output columns [64 half, 64 half + 64) of the tile's 128: gate accumulator columns q*32.., up columns 128 + q*32..
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      const int q = 2 * half + c;
+      uint32_t raw_u[32];
+      tmem_ld_32x32b_x32(t_acc + q * 32, raw);
+      tmem_ld_32x32b_x32(t_acc + 128 + q * 32, raw_u);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float g = bf16r(__uint_as_float(raw[j]));
+        const float u = bf16r(__uint_as_float(raw_u[j]));
+        v[j] = bf16r(silu_acc(g)) * u;
+      }
+      stage_piece32(stage_row, c * 4, lane, v);
+    }
+    release();
+    write_piece(g_row, n * 128 + half * 64, n * 128 + half * 64 + 32, false);
+    __syncwarp();
+    return;
+  }
+
+  const int col0 = n * BN + half * 128;
+  const uint32_t t_panel = t_acc + half * 128;
+  if (p.mode == VEX_EPI_ROPE && col0 < p.rope_cols) {
+    // this warp's panel is one head: pairs (j, j + 64)
+#pragma unroll 1
+    for (int q = 0; q < 2; ++q) {
+      uint32_t raw_hi[32];
+      float v2[32];
+      tmem_ld_32x32b_x32(t_panel + q * 32, raw);
+      tmem_ld_32x32b_x32(t_panel + 64 + q * 32, raw_hi);
+      tmem_ld_wait();
+      rope_math(p, pos, q, raw, raw_hi, v, v2);
+      stage_piece32(stage_row, 0, lane, v);
+      stage_piece32(stage_row, 4, lane, v2);
+      if (q == 1) release(); else __syncwarp();
+      write_piece(g_row, col0 + q * 32, col0 + 64 + q * 32, false);
+      __syncwarp();
+    }
+    return;
+  }
+#pragma unroll 1
+  for (int pc = 0; pc < 2; ++pc) {
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      const int qq = pc * 2 + c;
+      tmem_ld_32x32b_x32(t_panel + qq * 32, raw);
+      tmem_ld_wait();
+      chunk_math(p, raw, v, col0 + qq * 32, s_row, ce);
+      stage_piece32(stage_row, c * 4, lane, v);
+    }
+    if (pc == 1) release(); else __syncwarp();
+    write_piece(g_row, col0 + pc * 64, col0 + pc * 64 + 32,
+                p.mode == VEX_EPI_RESIDUAL || p.mode == VEX_EPI_DROPOUT_ACC);
+    __syncwarp();
   }
 }
 
@@ -626,18 +884,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 //   full[stage]      : leader CTA only; both CTAs' TMA loads post their bytes on it (shared::cluster address)
 //   empty[stage]     : one per CTA; released by the leader's tcgen05.commit multicast to both CTAs
 //   tmem_full[acc]   : one per CTA; tcgen05.commit multicast
-//   tmem_empty[acc]  : leader CTA only, 8 arrivals (4 epilogue warps x 2 CTAs; the peer arrives remotely)
+//   tmem_empty[acc]  : leader CTA only, 16 arrivals (8 epilogue warps x 2 CTAs; the peer arrives remotely)
 // ---------------------------------------------------------------------------------------------
+constexpr int PAIR_THREADS = 384;  // TMA, MMA, TMEM-alloc, idle + 8 epilogue warps
+
 struct PairCfg {
   static constexpr int BN = 256;
   static constexpr int STAGES = 6;
   static constexpr int A_BYTES = BM * BK * 2;          // 16 KB
   static constexpr int B_BYTES = (BN / 2) * BK * 2;    // 16 KB: this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_WARP_BYTES = GemmCfg<256>::EPI_WARP_BYTES;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int EPI_WARP_BYTES = 32 * 128;      // 32 rows x 64 staged columns
   static constexpr int TMEM_COLS = 512;
   static constexpr int NUM_BARS = 2 * STAGES + 4;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * EPI_WARP_BYTES + NUM_BARS * 8 + 16 + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_WARP_BYTES + NUM_BARS * 8 + 16 + 1024;
 };
 
 struct PairTile {
@@ -666,7 +927,7 @@ __device__ __forceinline__ PairTile decode_pair_tile(int tile, int mp0, int mp1,
 }
 
 template <bool TB>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(PAIR_THREADS, 1)
     k3_grouped_gemm_pair(const __grid_constant__ GemmTmaps tm, const GemmDev p) {
   using Cfg = PairCfg;
   constexpr int BN = Cfg::BN;
@@ -674,7 +935,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + 4 * Cfg::EPI_WARP_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Cfg::EPI_WARPS * Cfg::EPI_WARP_BYTES);
   uint64_t* full_bar = bars;                   // used in the leader CTA
   uint64_t* empty_bar = bars + STAGES;         // per CTA
   uint64_t* tmem_full = bars + 2 * STAGES;     // per CTA
@@ -694,7 +955,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);
+      mbar_init(&tmem_empty[i], 2 * Cfg::EPI_WARPS);  // every epilogue warp of both CTAs
     }
     fence_mbar_init();
   }
@@ -835,8 +1096,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
   } else if (warp >= 4) {
     // =============================== epilogue (both CTAs, own 128 rows) ===============================
-    const int ew = warp - 4;
-    const uint32_t stage_base = smem_u32(epi_smem + ew * Cfg::EPI_WARP_BYTES);
+    const int ew = (warp - 4) & 3;    // TMEM lane quarter (== warp % 4)
+    const int half = (warp - 4) >> 2;  // which 128 accumulator columns
+    const uint32_t stage_base = smem_u32(epi_smem + (warp - 4) * Cfg::EPI_WARP_BYTES);
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -844,8 +1106,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const PairTile c = decode_pair_tile(tile, mp0, mp1, n_tiles);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN>(p, c.e, 2 * c.m2 + static_cast<int>(rank), c.n, cnt0, cnt1,
-                        t_lane + static_cast<uint32_t>(acc * BN), stage_base, lane, ew, [&]() {
+      epilogue_tile_half(p, c.e, 2 * c.m2 + static_cast<int>(rank), c.n, cnt0, cnt1,
+                        t_lane + static_cast<uint32_t>(acc * BN), stage_base, lane, ew, half, [&]() {
                           tc_fence_before();
                           __syncwarp();
                           if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
@@ -936,7 +1198,7 @@ static int launch_gemm_pair(const GemmTmaps& tm, const GemmDev& dev, cudaStream_
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(num_sms() & ~1);  // whole CTA pairs
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3(PAIR_THREADS);
   cfg.dynamicSmemBytes = PairCfg::SMEM_BYTES;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -1057,7 +1319,9 @@ extern "C" int vex_grouped_gemm(const vexGemmArgs* a, vexStream stream) {
   dev.ce_lse = a->ce_lse;
   dev.ce_w = a->ce_w;
   dev.ce_dloss = a->ce_dloss;
-  dev.ce_tiles = ceil_div(a->N, 256);
+  // softmax partial slots per row: one per 128-column HALF tile (the CTA-pair kernel's two epilogue warps of a row work
+  // independently; the single-CTA kernel fills slot 2n and neutralises slot 2n + 1)
+  dev.ce_tiles = 2 * ceil_div(a->N, 256);
   dev.bias = static_cast<const __nv_bfloat16*>(a->bias);
   dev.act = a->act;
   if (a->mode == VEX_EPI_DROPOUT_ACC) {

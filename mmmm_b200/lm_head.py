@@ -56,7 +56,7 @@ class _LMHeadCE(torch.autograd.Function):
             t = torch.empty(n, r, dtype=torch.bfloat16, device=dev)
             ops.grouped_gemm(h_sel, _bf16(spec.lora_A), None, t, counts, None, float(spec.scaling))
             lora_b = _bf16(spec.lora_B)
-        tiles = (V + 255) // 256
+        tiles = 2 * ((V + 255) // 256)  # one partial slot per 128-column half tile
         pmax, psum, zlabel, lse = f32(n, tiles), f32(n, tiles), f32(n), f32(n)
         loss = torch.zeros(1, dtype=torch.float32, device=dev)
         ops.lm_head_ce_forward(h_sel, _bf16(spec.weight), label_sel, w_sel, counts, t, lora_b, r, pmax, psum, zlabel,

@@ -468,7 +468,7 @@ def lm_head_ce_forward(h_sel: torch.Tensor, w: torch.Tensor, label_sel: torch.Te
     :610-627): the vocabulary GEMM over the selected rows with the softmax statistics in its epilogue (VEX_EPI_CE,
     no logits in HBM) + vex_ce_reduce.  ``loss`` (fp32 [1]) must be zero on entry."""
     V = w.shape[0]
-    tiles = (V + 255) // 256
+    tiles = 2 * ((V + 255) // 256)  # one partial slot per 128-column half tile (include/vex.h)
     cap = h_sel.shape[0]
     if pmax.numel() < cap * tiles or psum.numel() < cap * tiles or zlabel.numel() < cap or lse.numel() < cap:
         raise ValueError("partials / lse buffers too small")
