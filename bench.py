@@ -59,45 +59,103 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md clocks line).  Sampled in-process through
+    NVML (pynvml: no start-up delay, so even a 100 ms timed region gets samples); `nvidia-smi -lms` is the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    PERIOD_S = 0.005
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self._stop = index, [], None, None, threading.Event()
+        self.thread = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        idx = self.index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:  # NVML enumerates physical devices
+            try:
+                idx = int(vis.split(",")[self.index])
+            except ValueError:
+                pass
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
 
     def start(self):
         try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            time.sleep(1.0)  # nvidia-smi needs a moment before its first line
         except Exception:
             self.proc = None
+
+    def _poll_nvml(self):
+        n, h = self.nvml, self.handle
+        bits = (("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown),
+                ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown),
+                ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap))
+        mx = None
+        try:
+            mx = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+        except Exception:
+            pass
+        while not self._stop.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                try:
+                    pw = n.nvmlDeviceGetPowerUsage(h) / 1e3
+                except Exception:
+                    pw = 0.0
+                self.rows.append([str(self.index), sm, mx, pw] + ["Active" if mask & b else "Not Active" for _, b in bits])
+            except Exception:
+                pass
+            self._stop.wait(self.PERIOD_S)
 
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for r in self.rows:
+    def mark(self):
+        """Index of the next sample: bracket the timed region with two marks to select its samples."""
+        return len(self.rows)
+
+    def stop(self, lo: int = 0, hi: int | None = None):
+        if self.nvml is None and self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvml and nvidia-smi unavailable"])
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+        rows = self.rows[lo:hi] if (hi is None or hi > lo) else self.rows
+        sm, mx, reasons, power = [], None, set(), []
+        for r in rows:
             try:
                 sm.append(float(r[1]))
-                mx = float(r[2])
+                mx = float(r[2]) if r[2] is not None else mx
+                power.append(float(r[3]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                    if v.lower().startswith("active"):
+                    if str(v).lower().startswith("active"):
                         reasons.add(name)
             except Exception:
                 continue
         if not sm:
             return dict(sm_mhz=None, sm_max_mhz=mx, reasons=["no samples"])
-        loaded = sorted(sm)[len(sm) // 2:]  # upper half ~ samples under load
-        return dict(sm_mhz=statistics.median(loaded), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm),
+                    power_w_max=max(power) if power else None,
+                    source="nvml" if self.nvml is not None else "nvidia-smi")
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
@@ -279,11 +337,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    marks = {}
+
+    def timed(fn, steps, warmup, sampler=None):
         with torch.no_grad():
             for _ in range(warmup):
                 fn()
             barrier()
+            if sampler is not None:
+                marks["lo"] = sampler.mark()
             t0 = time.perf_counter()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             instrument.reset()
@@ -294,6 +356,8 @@ def run_ours(args):
             launches = instrument.launches()
             barrier()
             wall_ms = (time.perf_counter() - t0) * 1e3
+            if sampler is not None:
+                marks["hi"] = sampler.mark()
         ms = max(e0.elapsed_time(e1), 0.0)
         return ms, wall_ms, launches
 
@@ -310,8 +374,8 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_total, _, launches = timed(step, args.steps, args.warmup)
-    clocks = sampler.stop() if rank == 0 else None
+    ms_total, _, launches = timed(step, args.steps, args.warmup, sampler if rank == 0 else None)
+    clocks = sampler.stop(marks.get("lo", 0), marks.get("hi")) if rank == 0 else None
     ms_step = max_over_ranks(ms_total, dev) / args.steps
     if args.graph:  # launches inside a replayed graph are not visible to the Python counter: count one eager step
         with torch.no_grad():
@@ -432,6 +496,9 @@ def run_train(args):
     torch.cuda.synchronize()
     ar_ms.clear()
     instrument.reset()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -441,6 +508,7 @@ def run_train(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
     ms_step = max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
     allreduce_ms = sum(a.elapsed_time(b_) for a, b_ in ar_ms) / max(len(ar_ms), 1)
     if rank == 0:
@@ -467,7 +535,7 @@ def run_train(args):
                                  "train: fwd (activations kept in HBM) + bwd + LoRA-grad allreduce")),
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
             "allreduce_ms": allreduce_ms, "allreduce_bytes": reducer.nbytes, "trainable_params": reducer.flat.numel(),
-            "gpu_launches": launches, "kernels": kernels,
+            "gpu_launches": launches, "clocks": clocks, "kernels": kernels,
             "step_tflops_per_gpu": flop / (ms_step / 1e3) / 1e12,
             "step_frac_of_bf16_peak": flop / (ms_step / 1e3) / 1e12 / pk["bf16_tflops"], "peaks": pk,
             "note": "forward, recompute and backward all run on the native sm_100a kernels (K1-K9); only the "

@@ -209,23 +209,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       float alpha = 1.0f;
       bool rescale = false;
       if (mx > m_run && (mx - m_run) * scale_log2 > TC_RESCALE_THRESHOLD) {  // also true for m_run == -inf
-        alpha = exp2f((m_run - mx) * scale_log2);
+        alpha = ex2_approx((m_run - mx) * scale_log2);
         m_run = mx;
         rescale = j > 0;
       }
       const float msc = m_run * scale_log2;
-      float rs0 = 0.f, rs1 = 0.f;
+      // exp2(s * scale - m): packed FFMA2 for the affine part, one MUFU.EX2 per element (ex2.approx.ftz -- exp2f()
+      // costs FSETP + 2 FMUL around the MUFU for denormal results that vanish in the bf16 rounding of P anyway),
+      // packed FADD2 row sums on two chains.
+      const uint64_t sc2 = f2_pack(scale_log2, scale_log2), nm2 = f2_pack(-msc, -msc);
+      uint64_t rs2[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)};
       // P (bf16 pairs) is packed in place: pair i of chunk c lands in sraw[c][i / 2], which is already consumed
 #pragma unroll
       for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = exp2f(fmaf(__uint_as_float(sraw[c][i]), scale_log2, -msc));
-          const float p1 = exp2f(fmaf(__uint_as_float(sraw[c][i + 1]), scale_log2, -msc));
-          rs0 += p0;
-          rs1 += p1;
+          float x0, x1;
+          f2_unpack(f2_fma(f2_pack(__uint_as_float(sraw[c][i]), __uint_as_float(sraw[c][i + 1])), sc2, nm2), x0, x1);
+          const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+          rs2[(i >> 1) & 1] = f2_add(rs2[(i >> 1) & 1], f2_pack(p0, p1));
           sraw[c][i >> 1] = pack_bf16(p0, p1);
         }
+      float rs0, rs1;
+      f2_unpack(f2_add(rs2[0], rs2[1]), rs0, rs1);
       l_run = l_run * alpha + (rs0 + rs1);
 
       if (j > 0) {  // P buffer and O are free once P_{j-1}.V_{j-1} has completed
@@ -249,7 +255,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           tmem_ld_32x32b_x32(tO + lane_sel + hf * 64 + c * 32, o);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          for (int i = 0; i < 32; i += 2) {
+            float a0, a1;
+            f2_unpack(f2_mul(f2_pack(__uint_as_float(o[i]), __uint_as_float(o[i + 1])), f2_pack(alpha, alpha)), a0, a1);
+            o[i] = __float_as_uint(a0);
+            o[i + 1] = __float_as_uint(a1);
+          }
           tmem_st_32x32b_x32(tO + lane_sel + hf * 64 + c * 32, o);
         }
         tmem_st_wait();
