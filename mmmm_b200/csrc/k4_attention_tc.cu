@@ -324,6 +324,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   }
 }
 
+// shared with k4_attention_tc2.cu (a __global__ function cannot be launched from another translation unit without -rdc)
+int launch_zero_tail_rows(void* qkv, const int32_t* cu_seqlens, int B, int rows_cap, int row_elems, cudaStream_t s) {
+  zero_tail_rows<<<32, 256, 0, s>>>(static_cast<__nv_bfloat16*>(qkv), cu_seqlens, B, rows_cap, row_elems);
+  VEX_LAUNCH_CHECK();
+  return VEX_OK;
+}
+
 int launch_attention_tc(const void* qkv, const int32_t* cu_seqlens, int B, int max_len_cap, int heads,
                         const int32_t* out_row_map, void* out, float scale, int rows_cap, float* lse, int causal,
                         cudaStream_t s) {
@@ -337,9 +344,7 @@ int launch_attention_tc(const void* qkv, const int32_t* cu_seqlens, int B, int m
   std::memset(&tm, 0, sizeof(tm));
   int rc = make_tmap_2d(&tm, qkv, rows_cap, 3 * static_cast<uint64_t>(H), 3 * static_cast<uint64_t>(H), 128);
   if (rc != VEX_OK) return rc;
-  zero_tail_rows<<<32, 256, 0, s>>>(static_cast<__nv_bfloat16*>(const_cast<void*>(qkv)), cu_seqlens, B, rows_cap,
-                                    3 * H);
-  VEX_LAUNCH_CHECK();
+  if ((rc = launch_zero_tail_rows(const_cast<void*>(qkv), cu_seqlens, B, rows_cap, 3 * H, s)) != VEX_OK) return rc;
   dim3 grid(ceil_div(max_len_cap, TC_BQ), heads, B);
   k4_attention_tc<<<grid, TC_THREADS, TC_SMEM, s>>>(tm, cu_seqlens, heads, out_row_map,
                                                     static_cast<__nv_bfloat16*>(out),

@@ -1,0 +1,412 @@
+// K4 (fast path, second generation) -- two-query-tile ping-pong flash attention on tcgen05 / TMEM for sm_100a.
+//
+// Same contract as k4_attention_tc.cu (attention_fn prefill branch, modeling_cogvlm.py:106-128: per sample, token i
+// attends to tokens j <= i in token-rank order, scale d^-0.5, fp32 online softmax, P rounded to bf16 before P.V;
+// non-causal block-diagonal form for the vision encoder, visual.py:96-98).
+//
+// Why a second kernel: in the one-tile kernel the softmax of a 128 x 128 score block (16 384 MUFU.EX2 = 1 024 cycles
+// at 16 / clk / SM, plus TMEM loads, row max, packing) is a serial stage between S = Q.K^T and O += P.V -- two threads
+// per query row had to exchange the row maximum through shared memory behind a 256-thread barrier, which put both
+// warps of every scheduler in lock-step; ncu: tensor pipe 32 % active, ~3 200 cycles per block
+// (profiles/r1_attn_tc_s5a.md).  Here one CTA owns TWO query tiles (A, B: 2 x 128 rows of one (sample, head)) that
+// share the K/V stream:
+//   warp 0 / lane 0 : TMA producer -- Q_A, Q_B once, then K_j, V_j through ONE 3-slot ring (K_j, V_j, K_{j+1} in
+//                     flight), straight out of the token-order QKV buffer [rows_cap, 3*heads*128].
+//   warp 1 / lane 0 : MMA issuer: S_A(0), S_B(0), then per key block  PV_A(j), S_A(j+1), PV_B(j), S_B(j+1): while the
+//                     softmax warps of one tile work, the tensor core runs the other tile's two GEMMs.
+//   warp 2          : TMEM allocate / free: S_A, S_B, O_A, O_B = 4 x 128 columns.
+//   warps 4..7      : softmax of tile A, ONE thread per query row (TMEM lane == row: no shuffles, no exchange);
+//   warps 8..11     : softmax of tile B.  Each scheduler hosts one A warp and one B warp in different phases, so the
+//                     MUFU-bound exp loop of one overlaps the TMEM-load / max / pack code of the other.  The 128 scores
+//                     of a row stay in registers (setmaxnreg: 224 for the softmax warpgroups, 56 for warps 0..3).
+//   P               : PT = true  -> bf16 pairs written back into the first 64 columns of the tile's S accumulator
+//                                   (tcgen05.st) and consumed as the TMEM A operand of O += P.V: no shared-memory
+//                                   round trip (an SS-mode M128 x N128 MMA already reads 128 B / clk of operands);
+//                     PT = false -> shared memory in the UMMA K-major 128B-swizzle layout (A/B switch VEX_ATTN_P=smem).
+// Ordering: S_X(j+1) is issued after PV_X(j), and tcgen05.commit tracks every earlier MMA of the issuing thread, so
+// s_full_X(j+1) also means "PV_X(j) done": P_X and O_X are free without a separate barrier inside the loop.
+#include <cuda.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace vex {
+
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+int launch_zero_tail_rows(void* qkv, const int32_t* cu_seqlens, int B, int rows_cap, int row_elems, cudaStream_t s);
+
+constexpr int A2_BQ = 128, A2_BK = 128, A2_D = 128;
+constexpr int A2_THREADS = 384;          // TMA, MMA, TMEM-alloc, idle + 2 x 4 softmax warps
+constexpr int A2_TILE = 128 * 128 * 2;   // 32 KB: one 128 x 128 bf16 tile = two 64-column atoms of 16 KB
+constexpr int A2_ATOM = 128 * 64 * 2;    // 16 KB
+constexpr int A2_KV_SLOTS = 3;
+constexpr float A2_RESCALE_THRESHOLD = 8.0f;  // log2 units
+constexpr int A2_REGS_SOFTMAX = 224, A2_REGS_OTHER = 56;
+
+template <bool PT>
+struct A2Cfg {
+  static constexpr int TILES = 2 + A2_KV_SLOTS + (PT ? 0 : 2);  // Q_A, Q_B, KV ring, (P_A, P_B)
+  static constexpr int SMEM = TILES * A2_TILE + 256 + 1024;     // + barriers + alignment slack
+};
+
+struct Attn2Bars {
+  uint64_t q_full, kv_full[A2_KV_SLOTS], kv_empty[A2_KV_SLOTS], s_full[2], p_full[2], pv_done[2];
+  uint32_t tmem_base;
+};
+
+// D[tmem] (+)= A[tmem] . B[smem]: A = 128 lanes x K columns (two bf16 per 32-bit column), K-major by construction
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int N>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
+template <bool PT>
+__global__ void __launch_bounds__(A2_THREADS, 1)
+    k4_attention_tc2(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* __restrict__ cu_seqlens, int heads,
+                     const int32_t* __restrict__ out_row_map, __nv_bfloat16* __restrict__ out, float scale_log2,
+                     float* __restrict__ lse, int rows_cap, int causal) {
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int seq0 = cu_seqlens[b], len = cu_seqlens[b + 1] - seq0;
+  const int qp = gridDim.x - 1 - blockIdx.x;  // heaviest query-tile pairs first
+  const int q0 = qp * 2 * A2_BQ;              // first row of tile A; tile B starts at q0 + 128
+  if (q0 >= len) return;
+  // key blocks per tile.  causal: up to the tile's diagonal block; non-causal: every key block of the sample.
+  const int n_all = (len + A2_BK - 1) / A2_BK;
+  const bool b_active = q0 + A2_BQ < len;
+  const int nA = causal ? 2 * qp + 1 : n_all;
+  const int nB = b_active ? (causal ? 2 * qp + 2 : n_all) : 0;
+  const int n_max = max(nA, nB);
+  const int H = heads * A2_D;
+
+  extern __shared__ uint8_t a2_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(a2_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                     // 2 tiles
+  uint8_t* sKV = smem + 2 * A2_TILE;      // ring of A2_KV_SLOTS tiles
+  uint8_t* sP = smem + (2 + A2_KV_SLOTS) * A2_TILE;  // 2 tiles (PT = false only)
+  Attn2Bars* bars = reinterpret_cast<Attn2Bars*>(smem + A2Cfg<PT>::TILES * A2_TILE);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars->q_full, 1);
+    for (int i = 0; i < A2_KV_SLOTS; ++i) {
+      mbar_init(&bars->kv_full[i], 1);
+      mbar_init(&bars->kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->s_full[i], 1);
+      mbar_init(&bars->p_full[i], 4);  // one arrive per softmax warp of the tile
+      mbar_init(&bars->pv_done[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_qkv);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  // columns: S_A [0,128), S_B [128,256), O_A [256,384), O_B [384,512); P_X aliases S_X columns [0,64) (PT)
+
+  if (warp < 4) {
+    reg_dealloc<A2_REGS_OTHER>();
+    if (warp == 0 && lane == 0) {
+      // =============================== TMA producer ===============================
+      const int colq = h * A2_D, colk = H + h * A2_D, colv = 2 * H + h * A2_D;
+      mbar_arrive_expect_tx(&bars->q_full, 2 * A2_TILE);
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {  // rows past the buffer are zero-filled by TMA; rows past `len` are never stored
+        tma_load_2d(sQ + x * A2_TILE, &tm_qkv, &bars->q_full, colq, seq0 + q0 + x * A2_BQ);
+        tma_load_2d(sQ + x * A2_TILE + A2_ATOM, &tm_qkv, &bars->q_full, colq + 64, seq0 + q0 + x * A2_BQ);
+      }
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_max; ++j) {
+        const int row = seq0 + j * A2_BK;
+#pragma unroll
+        for (int kv = 0; kv < 2; ++kv) {  // item 2j = K_j, item 2j + 1 = V_j
+          const int col = kv ? colv : colk;
+          mbar_wait(&bars->kv_empty[slot], phase ^ 1);
+          mbar_arrive_expect_tx(&bars->kv_full[slot], A2_TILE);
+          tma_load_2d(sKV + slot * A2_TILE, &tm_qkv, &bars->kv_full[slot], col, row);
+          tma_load_2d(sKV + slot * A2_TILE + A2_ATOM, &tm_qkv, &bars->kv_full[slot], col + 64, row);
+          if (++slot == A2_KV_SLOTS) {
+            slot = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // =============================== MMA issuer ===============================
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);  // B (= V) is MN-major
+      const uint32_t aKV = smem_u32(sKV);
+      auto wait_item = [&](int idx) {  // ring item idx: K_j = 2j, V_j = 2j + 1
+        mbar_wait(&bars->kv_full[idx % A2_KV_SLOTS], (idx / A2_KV_SLOTS) & 1);
+        tc_fence_after();
+      };
+      auto release_item = [&](int idx) { umma_commit(&bars->kv_empty[idx % A2_KV_SLOTS]); };
+      auto issue_s = [&](int x, int j) {  // S_x = Q_x . K_j^T
+        wait_item(2 * j);
+        const uint32_t aQ = smem_u32(sQ + x * A2_TILE);
+        const uint32_t aK = aKV + ((2 * j) % A2_KV_SLOTS) * A2_TILE;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {  // d = 128 in K = 16 steps; atom = kk / 4, 32 B per step inside the atom
+          const uint32_t off = (kk >> 2) * A2_ATOM + (kk & 3) * 32;
+          umma_ss(tmem + x * 128, umma_desc_kmajor_sw128(aQ + off), umma_desc_kmajor_sw128(aK + off), idesc_s, kk > 0);
+        }
+        umma_commit(&bars->s_full[x]);
+      };
+      auto issue_pv = [&](int x, int j) {  // O_x (+)= P_x . V_j
+        mbar_wait(&bars->p_full[x], j & 1);
+        wait_item(2 * j + 1);
+        const uint32_t aV = aKV + ((2 * j + 1) % A2_KV_SLOTS) * A2_TILE;
+        const uint32_t tO = tmem + 256 + x * 128;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {  // 128 keys in K = 16 steps
+          // B = V: MN-major; 16 keys = 2 groups of 8 rows (SBO 1024 B), d chunks of 64 are 16 KB apart (LBO)
+          const uint64_t db = umma_desc_mnmajor_sw128(aV + kk * 2048, A2_ATOM, 1024);
+          if constexpr (PT) {
+            umma_ts(tO, tmem + x * 128 + kk * 8, db, idesc_pv, (j > 0) || (kk > 0));  // 16 keys = 8 packed columns
+          } else {
+            const uint32_t aP = smem_u32(sP + x * A2_TILE);
+            umma_ss(tO, umma_desc_kmajor_sw128(aP + (kk >> 2) * A2_ATOM + (kk & 3) * 32), db, idesc_pv,
+                    (j > 0) || (kk > 0));
+          }
+        }
+        umma_commit(&bars->pv_done[x]);
+      };
+      const bool has_b = nB > 0;
+      mbar_wait(&bars->q_full, 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      if (has_b) issue_s(1, 0);
+      release_item(0);
+      for (int j = 0; j < n_max; ++j) {
+        if (j < nA) {
+          issue_pv(0, j);
+          if (j >= nB) release_item(2 * j + 1);
+          if (j + 1 < nA) {
+            issue_s(0, j + 1);
+            if (j + 1 >= nB) release_item(2 * j + 2);
+          }
+        }
+        if (j < nB) {
+          issue_pv(1, j);
+          release_item(2 * j + 1);
+          if (j + 1 < nB) {
+            issue_s(1, j + 1);
+            release_item(2 * j + 2);
+          }
+        }
+      }
+    }
+  } else {
+    // =============================== softmax + epilogue ===============================
+    reg_alloc<A2_REGS_SOFTMAX>();
+    const int x = (warp - 4) >> 2;  // tile: 0 = A, 1 = B
+    const int ew = warp & 3;        // TMEM lane quarter
+    const int r = ew * 32 + lane;   // query row inside the tile == TMEM lane
+    const int nX = x ? nB : nA;
+    const int qx0 = q0 + x * A2_BQ;
+    const uint32_t lane_sel = static_cast<uint32_t>(ew * 32) << 16;
+    const uint32_t tS = tmem + lane_sel + x * 128;
+    const uint32_t tO = tmem + lane_sel + 256 + x * 128;
+    float m_run = -INFINITY, l_run = 0.f;
+
+    for (int j = 0; j < nX; ++j) {
+      mbar_wait(&bars->s_full[x], j & 1);
+      tc_fence_after();
+      uint32_t s[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+      tmem_ld_wait();
+      if (j == nX - 1) {
+        // last block.  causal: the tile's diagonal block, key (j*128 + k) visible iff k <= r.  non-causal: keys past
+        // the end of the sample (the next sample's tokens / the zeroed tail) are masked, k <= len - 1 - j*128
+        const int kmax = causal ? r : len - 1 - j * A2_BK;
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i > kmax) s[i] = 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 128; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(s[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      // lazy rescale: keep the stale max unless the new one is more than 2^8 larger
+      float alpha = 1.0f;
+      bool rescale = false;
+      if (mx > m_run && (mx - m_run) * scale_log2 > A2_RESCALE_THRESHOLD) {  // also true for m_run == -inf
+        alpha = ex2_approx((m_run - mx) * scale_log2);
+        m_run = mx;
+        rescale = j > 0;
+      }
+      const float msc = m_run * scale_log2;
+      // exp2(s * scale - m): packed FFMA2 for the affine part, one MUFU.EX2 per element, packed FADD2 row sums on two
+      // chains; P (bf16 pairs) is packed in place: pair i lands in s[i / 2], which is already consumed
+      const uint64_t sc2 = f2_pack(scale_log2, scale_log2), nm2 = f2_pack(-msc, -msc);
+      uint64_t rs2[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)};
+#pragma unroll
+      for (int i = 0; i < 128; i += 2) {
+        float x0, x1;
+        f2_unpack(f2_fma(f2_pack(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), sc2, nm2), x0, x1);
+        const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+        rs2[(i >> 1) & 1] = f2_add(rs2[(i >> 1) & 1], f2_pack(p0, p1));
+        s[i >> 1] = pack_bf16(p0, p1);
+      }
+      float rs0, rs1;
+      f2_unpack(f2_add(rs2[0], rs2[1]), rs0, rs1);
+      l_run = l_run * alpha + (rs0 + rs1);
+
+      // s_full(j) was committed after PV(j-1): P and O of this tile are free here
+      if constexpr (PT) {
+        tmem_st_32x32b_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+        tmem_st_32x32b_x32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+      } else {
+        // UMMA K-major SWIZZLE_128B: key atom a = keys [64a, 64a + 64); (row, 16-byte chunk c16) at
+        // row*128 + ((c16 ^ row%8) * 16); chunk c16 of atom a = packed pairs s[32a + 4*c16 .. + 3]
+        const uint32_t p_row = smem_u32(sP + x * A2_TILE) + r * 128;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int c16 = 0; c16 < 8; ++c16) {
+            const uint32_t addr = p_row + a * A2_ATOM + ((c16 ^ (r & 7)) << 4);
+            const uint32_t* pp = &s[32 * a + 4 * c16];
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pp[0]), "r"(pp[1]), "r"(pp[2]),
+                         "r"(pp[3])
+                         : "memory");
+          }
+      }
+      if (__any_sync(0xffffffffu, rescale)) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(tO + c * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float a0, a1;
+            f2_unpack(f2_mul(f2_pack(__uint_as_float(o[i]), __uint_as_float(o[i + 1])), f2_pack(alpha, alpha)), a0, a1);
+            o[i] = __float_as_uint(a0);
+            o[i + 1] = __float_as_uint(a1);
+          }
+          tmem_st_32x32b_x32(tO + c * 32, o);
+        }
+      }
+      if constexpr (PT) {
+        tmem_st_wait();
+      } else {
+        tmem_st_wait();
+        fence_proxy_async_smem();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->p_full[x]);
+    }
+
+    if (nX > 0) {
+      // ---- epilogue: normalise the row, stage it in the tile's (dead) Q buffer, scatter coalesced rows ----
+      mbar_wait(&bars->pv_done[x], (nX - 1) & 1);  // every MMA of this tile (S and PV) has completed
+      tc_fence_after();
+      const float inv_l = 1.0f / l_run;
+      const uint32_t stage = smem_u32(sQ + x * A2_TILE) + ew * 8192;  // this warp's 32 rows x 256 B
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(tO + c * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int piece = c * 4 + i;  // 16 pieces of 16 B per row
+          const uint32_t addr = stage + lane * 256 + ((piece ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr),
+                       "r"(pack_bf16(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l)),
+                       "r"(pack_bf16(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l)),
+                       "r"(pack_bf16(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l)),
+                       "r"(pack_bf16(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l))
+                       : "memory");
+        }
+      }
+      __syncwarp();
+      const int tok = seq0 + qx0 + r;
+      const bool row_ok = qx0 + r < len;
+      const int my_dst = row_ok ? (out_row_map ? out_row_map[tok] : tok) : -1;
+      // training: log2-domain log-sum-exp of the scaled scores, [heads, rows_cap] (read back by the backward kernels)
+      if (lse != nullptr && row_ok) lse[static_cast<int64_t>(h) * rows_cap + tok] = fmaf(m_run, scale_log2, log2f(l_run));
+#pragma unroll 4
+      for (int it = 0; it < 16; ++it) {  // 2 rows of 256 B per iteration, 16 lanes each
+        const int rr = it * 2 + (lane >> 4), piece = lane & 15;
+        const int dst = __shfl_sync(0xffffffffu, my_dst, rr);
+        if (dst >= 0) {
+          uint4 v;
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                       : "r"(stage + rr * 256 + ((piece ^ (rr & 7)) << 4)));
+          *reinterpret_cast<uint4*>(out + static_cast<int64_t>(dst) * H + h * A2_D + piece * 8) = v;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+template <bool PT>
+static int launch_tc2(const CUtensorMap& tm, const int32_t* cu_seqlens, int B, int max_len_cap, int heads,
+                      const int32_t* out_row_map, void* out, float scale, int rows_cap, float* lse, int causal,
+                      cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    VEX_CUDA_TRY(cudaFuncSetAttribute(k4_attention_tc2<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      A2Cfg<PT>::SMEM));
+    configured = true;
+  }
+  dim3 grid(ceil_div(max_len_cap, 2 * A2_BQ), heads, B);
+  k4_attention_tc2<PT><<<grid, A2_THREADS, A2Cfg<PT>::SMEM, s>>>(tm, cu_seqlens, heads, out_row_map,
+                                                                 static_cast<__nv_bfloat16*>(out),
+                                                                 scale * 1.4426950408889634f, lse, rows_cap, causal);
+  VEX_LAUNCH_CHECK();
+  return VEX_OK;
+}
+
+int launch_attention_tc2(const void* qkv, const int32_t* cu_seqlens, int B, int max_len_cap, int heads,
+                         const int32_t* out_row_map, void* out, float scale, int rows_cap, float* lse, int causal,
+                         cudaStream_t s) {
+  const int H = heads * A2_D;
+  CUtensorMap tm;
+  std::memset(&tm, 0, sizeof(tm));
+  int rc = make_tmap_2d(&tm, qkv, rows_cap, 3 * static_cast<uint64_t>(H), 3 * static_cast<uint64_t>(H), 128);
+  if (rc != VEX_OK) return rc;
+  if ((rc = launch_zero_tail_rows(const_cast<void*>(qkv), cu_seqlens, B, rows_cap, 3 * H, s)) != VEX_OK) return rc;
+  const char* pe = std::getenv("VEX_ATTN_P");  // A/B switch: where P lives between the softmax and O += P.V
+  if (pe && std::strcmp(pe, "smem") == 0)
+    return launch_tc2<false>(tm, cu_seqlens, B, max_len_cap, heads, out_row_map, out, scale, rows_cap, lse, causal, s);
+  return launch_tc2<true>(tm, cu_seqlens, B, max_len_cap, heads, out_row_map, out, scale, rows_cap, lse, causal, s);
+}
+
+}  // namespace vex

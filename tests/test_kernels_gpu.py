@@ -519,11 +519,14 @@ def test_k8_lora_wgrad(Tv, Tl, F, r):
 
 
 # ------------------------------------------------------------------------------------------ K4
-@pytest.mark.parametrize("impl", ["tc", "mma"])
-@pytest.mark.parametrize("lens", [[1], [64], [65, 3, 128], [129, 128, 127], [300, 17, 1, 255], [1357], [700, 1485]])
+@pytest.mark.parametrize("impl", ["tc2", "tc2-smem", "tc1", "mma"])
+@pytest.mark.parametrize("lens", [[1], [64], [65, 3, 128], [129, 128, 127], [300, 17, 1, 255], [257, 256, 255, 384],
+                                  [1357], [700, 1485]])
 def test_k4_attention_vs_oracle(lens, impl, monkeypatch):
-    """Both implementations (tcgen05/TMEM fast path and the mma.sync baseline) against the oracle."""
-    monkeypatch.setenv("VEX_ATTN_IMPL", impl)
+    """Every implementation -- the two-tile tcgen05 kernel with P in TMEM (default) or in shared memory, the one-tile
+    tcgen05 kernel and the mma.sync baseline -- against the oracle."""
+    monkeypatch.setenv("VEX_ATTN_IMPL", impl.split("-")[0])
+    monkeypatch.setenv("VEX_ATTN_P", "smem" if impl.endswith("smem") else "tmem")
     ops = _ops()
     heads = 3
     B, Lmax = len(lens), max(lens)

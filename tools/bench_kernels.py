@@ -26,7 +26,7 @@ def timeit(fn, iters=20, warmup=5):
     return e0.elapsed_time(e1) / iters
 
 
-def bench_attention(B=8, nv=1225, nt=256, heads=32):
+def bench_attention(B=8, nv=1225, nt=256, heads=32, only=None):
     tt, pos, pm = make_ids(B, nv, nt)
     plan = build_plan(tt.cuda(), pm.cuda())
     L = tt.shape[1]
@@ -35,14 +35,24 @@ def bench_attention(B=8, nv=1225, nt=256, heads=32):
     out = torch.empty(cap, heads * 128, device="cuda", dtype=torch.bfloat16)
     flop = B * 4 * heads * 128 * L * (L + 1) / 2
     res = {}
-    for impl in ("mma", "tc"):
-        os.environ["VEX_ATTN_IMPL"] = impl
-        ms = timeit(lambda: ops.attention(qkv, plan.cu_seqlens, B, L, heads, plan.token_to_sorted, out, 128 ** -0.5))
+    impls = only or ("mma", "tc1", "tc2-smem", "tc2")
+    for impl in impls:
+        os.environ["VEX_ATTN_IMPL"] = impl.split("-")[0]
+        os.environ["VEX_ATTN_P"] = "smem" if impl.endswith("smem") else "tmem"
+        out.zero_()
+        try:
+            ms = timeit(lambda: ops.attention(qkv, plan.cu_seqlens, B, L, heads, plan.token_to_sorted, out, 128 ** -0.5))
+        except Exception as e:  # keep measuring the other implementations
+            print(json.dumps({"kernel": f"attention_{impl}", "error": str(e)[:200]}))
+            continue
         res[impl] = out.clone()
         print(json.dumps({"kernel": f"attention_{impl}", "B": B, "L": L, "ms": ms, "tflops": flop / ms / 1e9}))
-    d = (res["mma"].float() - res["tc"].float()).abs().max().item()
-    print(json.dumps({"attention_mma_vs_tc_maxabs": d}))
+    for impl in impls:
+        if impl != "mma" and impl in res and "mma" in res:
+            d = (res["mma"].float() - res[impl].float()).abs().max().item()
+            print(json.dumps({f"attention_mma_vs_{impl}_maxabs": d}))
     os.environ.pop("VEX_ATTN_IMPL", None)
+    os.environ.pop("VEX_ATTN_P", None)
 
 
 def bench_gemm(Tv=9808, Tl=2072):
@@ -131,6 +141,8 @@ if __name__ == "__main__":
     if which in ("all", "attention"):
         bench_attention()
         bench_attention(B=2, nv=2048, nt=512)
+    if which.startswith("attention:"):  # one implementation (ncu captures): attention:tc2, attention:tc2-smem, ...
+        bench_attention(only=(which.split(":", 1)[1],))
     if which in ("all", "gemm"):
         bench_gemm()
     if which in ("all", "rowwise"):
