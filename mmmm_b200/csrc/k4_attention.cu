@@ -14,12 +14,15 @@ int launch_attention_tc2(const void* qkv, const int32_t* cu_seqlens, int B, int 
                          const int32_t* out_row_map, void* out, float scale, int rows_cap, float* lse, int causal,
                          cudaStream_t s);
 
-// VEX_ATTN_IMPL=tc1 selects the one-tile tcgen05 kernel (k4_attention_tc.cu); default: the two-tile ping-pong kernel
+// VEX_ATTN_IMPL=tc1 / tc2 selects the one-tile tcgen05 kernel (k4_attention_tc.cu) or the two-tile ping-pong kernel
+// (k4_attention_tc2.cu); unset: kDefaultTc2 decides.
+constexpr bool kDefaultTc2 = false;  // flipped once the two-tile kernel is parity-green and faster on B200
 static int launch_attention_tcgen05(const void* qkv, const int32_t* cu_seqlens, int B, int max_len_cap, int heads,
                                     const int32_t* out_row_map, void* out, float scale, int rows_cap, float* lse,
                                     int causal, cudaStream_t s) {
   const char* impl = std::getenv("VEX_ATTN_IMPL");
-  if (impl && std::strcmp(impl, "tc1") == 0)
+  const bool tc2 = impl ? std::strcmp(impl, "tc2") == 0 : kDefaultTc2;
+  if (!tc2)
     return launch_attention_tc(qkv, cu_seqlens, B, max_len_cap, heads, out_row_map, out, scale, rows_cap, lse, causal, s);
   return launch_attention_tc2(qkv, cu_seqlens, B, max_len_cap, heads, out_row_map, out, scale, rows_cap, lse, causal, s);
 }
