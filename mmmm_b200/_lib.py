@@ -57,8 +57,10 @@ def lib() -> C.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
-        path = _build.LIB
-        if not _build.is_fresh():
+        path = os.environ.get("VEX_LIB_PATH") or _build.LIB  # override: experiment builds (tools/attn_trace.py)
+        if path != _build.LIB:
+            pass
+        elif not _build.is_fresh():
             if os.path.isfile(_build.NVCC):
                 path = _build.build()
             elif not os.path.isfile(path):

@@ -16,7 +16,7 @@ int launch_attention_tc2(const void* qkv, const int32_t* cu_seqlens, int B, int 
 
 // VEX_ATTN_IMPL=tc1 / tc2 selects the one-tile tcgen05 kernel (k4_attention_tc.cu) or the two-tile ping-pong kernel
 // (k4_attention_tc2.cu); unset: kDefaultTc2 decides.
-constexpr bool kDefaultTc2 = false;  // flipped once the two-tile kernel is parity-green and faster on B200
+constexpr bool kDefaultTc2 = true;  // parity-green on B200 and 17 % faster than the one-tile kernel at c2 (profiles/r1_attn_tc2_s8a.md)
 static int launch_attention_tcgen05(const void* qkv, const int32_t* cu_seqlens, int B, int max_len_cap, int heads,
                                     const int32_t* out_row_map, void* out, float scale, int rows_cap, float* lse,
                                     int causal, cudaStream_t s) {

@@ -519,14 +519,15 @@ def test_k8_lora_wgrad(Tv, Tl, F, r):
 
 
 # ------------------------------------------------------------------------------------------ K4
-@pytest.mark.parametrize("impl", ["tc2", "tc2-smem", "tc1", "mma"])
+@pytest.mark.parametrize("impl", ["tc2", "tc2-smem", "tc2-tmem", "tc2-token", "tc1", "mma"])
 @pytest.mark.parametrize("lens", [[1], [64], [65, 3, 128], [129, 128, 127], [300, 17, 1, 255], [257, 256, 255, 384],
                                   [1357], [700, 1485]])
 def test_k4_attention_vs_oracle(lens, impl, monkeypatch):
-    """Every implementation -- the two-tile tcgen05 kernel with P in TMEM (default) or in shared memory, the one-tile
-    tcgen05 kernel and the mma.sync baseline -- against the oracle."""
+    """Every implementation -- the two-tile tcgen05 kernel in its four schedules (default: early S, P in shared memory;
+    P in shared memory with the serial schedule; P in TMEM; early S with exp turns), the one-tile tcgen05 kernel and
+    the mma.sync baseline -- against the oracle."""
     monkeypatch.setenv("VEX_ATTN_IMPL", impl.split("-")[0])
-    monkeypatch.setenv("VEX_ATTN_P", "smem" if impl.endswith("smem") else "tmem")
+    monkeypatch.setenv("VEX_ATTN_P", impl.split("-")[1] if "-" in impl else "early")
     ops = _ops()
     heads = 3
     B, Lmax = len(lens), max(lens)
