@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
   } else if (warp == 1) {
     // =============================== MMA issuer (whole warp: boundary fix-up) ===============================
     constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);  // A and B MN-major
+    const uint64_t dA0 = umma_desc_mnmajor_sw128(smem_u32(smem), 8192, 1024);  // stage 0; k-steps / stages are adds
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = 0; kb < n_kb; ++kb) {
@@ -125,12 +126,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
       }
       __syncwarp();
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a = smem_u32(sa), b = a + WG_A_BYTES;
+      // elected lane of the converged warp: operands stay in uniform registers (a `lane == 0` branch costs an elect /
+      // waterfall loop, four R2UR and two descriptor rebuilds per 32-cycle MMA)
+      const uint64_t da = dA0 + static_cast<uint64_t>(stage * (WG_STAGE_BYTES >> 4)), db = da + (WG_A_BYTES >> 4);
+      if (elect_one_sync()) {
 #pragma unroll
         for (int k = 0; k < WG_BK / 16; ++k)
-          umma_ss(tmem, umma_desc_mnmajor_sw128(a + k * 2048, 8192, 1024),
-                  umma_desc_mnmajor_sw128(b + k * 2048, 8192, 1024), idesc, (kb > 0) || (k > 0));
+          umma_ss(tmem, da + static_cast<uint64_t>((k * 2048) >> 4), db + static_cast<uint64_t>((k * 2048) >> 4), idesc,
+                  (kb > 0) || (k > 0));
         umma_commit(&empty_bar[stage]);
         if (kb == n_kb - 1) umma_commit(acc_full);
       }

@@ -253,25 +253,37 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
       tma_load_2d(sdO + st * AB_T64, &tm_do64, &bars->q_full[st], colq, row);
       tma_load_2d(sdO + st * AB_T64 + AB_T64 / 2, &tm_do64, &bars->q_full[st], colq + 64, row);
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // =============================== MMA issuer ===============================
+    // The whole warp runs the loop (warp-uniform control flow) and one elected lane issues: in a `lane == 0` branch
+    // ptxas wraps every tcgen05.mma in an elect / waterfall loop with four R2UR moves and rebuilds both descriptors
+    // (17 instructions per 32-cycle N = 64 MMA: the issuer, not the tensor pipe, set the pace).  Descriptors are one
+    // base per operand tile plus constant k-step offsets in the 14-bit address field.
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
     constexpr uint32_t idesc_acc = umma_idesc_bf16(128, 128, 0, 1);  // B MN-major
-    const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
+    const uint64_t dK = umma_desc_kmajor_sw128(smem_u32(sK)), dV = umma_desc_kmajor_sw128(smem_u32(sV));
+    const uint64_t dQk0 = umma_desc_kmajor_sw128(smem_u32(sQ));  // stage st: + st * AB_T64 / 16
+    const uint64_t ddOk0 = umma_desc_kmajor_sw128(smem_u32(sdO));  // stage st: + st * AB_T64 / 16
+    const uint64_t dQm0 = umma_desc_mnmajor_sw128(smem_u32(sQ), AB_T64 / 2, 1024);  // stage st: + st * AB_T64 / 16
+    const uint64_t ddOm0 = umma_desc_mnmajor_sw128(smem_u32(sdO), AB_T64 / 2, 1024);  // stage st: + st * AB_T64 / 16
+    const uint64_t dPk0 = umma_desc_kmajor_sw128(smem_u32(sP));  // stage st: + st * AB_P / 16
+    const uint64_t ddSk0 = umma_desc_kmajor_sw128(smem_u32(sdS));  // stage st: + st * AB_P / 16
     auto issue_s = [&](int s) {
       const int st = s & 1;
       mbar_wait(&bars->q_full[st], (s >> 1) & 1);
       tc_fence_after();
-      const uint32_t aQ = smem_u32(sQ + st * AB_T64), adO = smem_u32(sdO + st * AB_T64);
+      if (elect_one_sync()) {
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk)  // d = 128 in K = 16 steps
-        umma_ss(tS + st * 64, umma_desc_kmajor_sw128(aK + (kk >> 2) * (AB_T128 / 2) + (kk & 3) * 32),
-                umma_desc_kmajor_sw128(aQ + (kk >> 2) * (AB_T64 / 2) + (kk & 3) * 32), idesc_s, kk > 0);
+        for (int kk = 0; kk < 8; ++kk)  // d = 128 in K = 16 steps
+          umma_ss(tS + st * 64, dK + static_cast<uint64_t>(((kk >> 2) * (AB_T128 / 2) + (kk & 3) * 32) >> 4),
+                  (dQk0 + static_cast<uint64_t>(st * (AB_T64 >> 4))) + static_cast<uint64_t>(((kk >> 2) * (AB_T64 / 2) + (kk & 3) * 32) >> 4), idesc_s, kk > 0);
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk)
-        umma_ss(tdP + st * 64, umma_desc_kmajor_sw128(aV + (kk >> 2) * (AB_T128 / 2) + (kk & 3) * 32),
-                umma_desc_kmajor_sw128(adO + (kk >> 2) * (AB_T64 / 2) + (kk & 3) * 32), idesc_s, kk > 0);
-      umma_commit(&bars->s_full[st]);
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ss(tdP + st * 64, dV + static_cast<uint64_t>(((kk >> 2) * (AB_T128 / 2) + (kk & 3) * 32) >> 4),
+                  (ddOk0 + static_cast<uint64_t>(st * (AB_T64 >> 4))) + static_cast<uint64_t>(((kk >> 2) * (AB_T64 / 2) + (kk & 3) * 32) >> 4), idesc_s, kk > 0);
+        umma_commit(&bars->s_full[st]);
+      }
+      __syncwarp();
     };
     mbar_wait(&bars->kv_full, 0);
     issue_s(0);
@@ -280,20 +292,22 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
       const int st = s & 1;
       mbar_wait(&bars->p_full[st], (s >> 1) & 1);
       tc_fence_after();
-      const uint32_t aQ = smem_u32(sQ + st * AB_T64), adO = smem_u32(sdO + st * AB_T64);
-      const uint32_t aP = smem_u32(sP + st * AB_P), adS = smem_u32(sdS + st * AB_P);
+      if (elect_one_sync()) {
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk)  // 64 queries in K = 16 steps
-        umma_ss(tdV, umma_desc_kmajor_sw128(aP + kk * 32), umma_desc_mnmajor_sw128(adO + kk * 2048, AB_T64 / 2, 1024),
-                idesc_acc, (s > 0) || (kk > 0));
+        for (int kk = 0; kk < 4; ++kk)  // 64 queries in K = 16 steps
+          umma_ss(tdV, (dPk0 + static_cast<uint64_t>(st * (AB_P >> 4))) + static_cast<uint64_t>((kk * 32) >> 4), (ddOm0 + static_cast<uint64_t>(st * (AB_T64 >> 4))) + static_cast<uint64_t>((kk * 2048) >> 4),
+                  idesc_acc, (s > 0) || (kk > 0));
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        umma_ss(tdK, umma_desc_kmajor_sw128(adS + kk * 32), umma_desc_mnmajor_sw128(aQ + kk * 2048, AB_T64 / 2, 1024),
-                idesc_acc, (s > 0) || (kk > 0));
-      umma_commit(&bars->q_empty[st]);
-      umma_commit(&bars->p_empty[st]);
+        for (int kk = 0; kk < 4; ++kk)
+          umma_ss(tdK, (ddSk0 + static_cast<uint64_t>(st * (AB_P >> 4))) + static_cast<uint64_t>((kk * 32) >> 4), (dQm0 + static_cast<uint64_t>(st * (AB_T64 >> 4))) + static_cast<uint64_t>((kk * 2048) >> 4),
+                  idesc_acc, (s > 0) || (kk > 0));
+        umma_commit(&bars->q_empty[st]);
+        umma_commit(&bars->p_empty[st]);
+      }
+      __syncwarp();
     }
-    umma_commit(&bars->acc_full);
+    if (elect_one_sync()) umma_commit(&bars->acc_full);
+    __syncwarp();
   } else if (warp >= 4) {
     // =============================== softmax threads: two per KEY row (32 queries each) =====================
     const int sw = warp - 4;           // 0..7
@@ -476,25 +490,31 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
       tma_load_2d(sV + st * AB_T64, &tm_qkv64, &bars->kv_full[st], colv, row);
       tma_load_2d(sV + st * AB_T64 + AB_T64 / 2, &tm_qkv64, &bars->kv_full[st], colv + 64, row);
     }
-  } else if (warp == 1 && lane == 0) {
-    // =============================== MMA issuer ===============================
+  } else if (warp == 1) {
+    // =============================== MMA issuer (whole warp, elected lane issues; see k9_attn_bwd_dkdv) ===============
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
     constexpr uint32_t idesc_acc = umma_idesc_bf16(128, 128, 0, 1);
-    const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO);
+    const uint64_t dQ = umma_desc_kmajor_sw128(smem_u32(sQ)), ddO = umma_desc_kmajor_sw128(smem_u32(sdO));
+    const uint64_t dKk0 = umma_desc_kmajor_sw128(smem_u32(sK));  // stage st: + st * AB_T64 / 16
+    const uint64_t dVk0 = umma_desc_kmajor_sw128(smem_u32(sV));  // stage st: + st * AB_T64 / 16
+    const uint64_t dKm0 = umma_desc_mnmajor_sw128(smem_u32(sK), AB_T64 / 2, 1024);  // stage st: + st * AB_T64 / 16
+    const uint64_t ddSk0 = umma_desc_kmajor_sw128(smem_u32(sdS));  // stage st: + st * AB_P / 16
     auto issue_s = [&](int s) {
       const int st = s & 1;
       mbar_wait(&bars->kv_full[st], (s >> 1) & 1);
       tc_fence_after();
-      const uint32_t aK = smem_u32(sK + st * AB_T64), aV = smem_u32(sV + st * AB_T64);
+      if (elect_one_sync()) {
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk)
-        umma_ss(tS + st * 64, umma_desc_kmajor_sw128(aQ + (kk >> 2) * (AB_T128 / 2) + (kk & 3) * 32),
-                umma_desc_kmajor_sw128(aK + (kk >> 2) * (AB_T64 / 2) + (kk & 3) * 32), idesc_s, kk > 0);
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ss(tS + st * 64, dQ + static_cast<uint64_t>(((kk >> 2) * (AB_T128 / 2) + (kk & 3) * 32) >> 4),
+                  (dKk0 + static_cast<uint64_t>(st * (AB_T64 >> 4))) + static_cast<uint64_t>(((kk >> 2) * (AB_T64 / 2) + (kk & 3) * 32) >> 4), idesc_s, kk > 0);
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk)
-        umma_ss(tdP + st * 64, umma_desc_kmajor_sw128(adO + (kk >> 2) * (AB_T128 / 2) + (kk & 3) * 32),
-                umma_desc_kmajor_sw128(aV + (kk >> 2) * (AB_T64 / 2) + (kk & 3) * 32), idesc_s, kk > 0);
-      umma_commit(&bars->s_full[st]);
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ss(tdP + st * 64, ddO + static_cast<uint64_t>(((kk >> 2) * (AB_T128 / 2) + (kk & 3) * 32) >> 4),
+                  (dVk0 + static_cast<uint64_t>(st * (AB_T64 >> 4))) + static_cast<uint64_t>(((kk >> 2) * (AB_T64 / 2) + (kk & 3) * 32) >> 4), idesc_s, kk > 0);
+        umma_commit(&bars->s_full[st]);
+      }
+      __syncwarp();
     };
     mbar_wait(&bars->q_full, 0);
     issue_s(0);
@@ -503,15 +523,18 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
       const int st = s & 1;
       mbar_wait(&bars->p_full[st], (s >> 1) & 1);
       tc_fence_after();
-      const uint32_t aK = smem_u32(sK + st * AB_T64), adS = smem_u32(sdS + st * AB_P);
+      if (elect_one_sync()) {
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk)  // 64 keys in K = 16 steps
-        umma_ss(tdQ, umma_desc_kmajor_sw128(adS + kk * 32), umma_desc_mnmajor_sw128(aK + kk * 2048, AB_T64 / 2, 1024),
-                idesc_acc, (s > 0) || (kk > 0));
-      umma_commit(&bars->kv_empty[st]);
-      umma_commit(&bars->p_empty[st]);
+        for (int kk = 0; kk < 4; ++kk)  // 64 keys in K = 16 steps
+          umma_ss(tdQ, (ddSk0 + static_cast<uint64_t>(st * (AB_P >> 4))) + static_cast<uint64_t>((kk * 32) >> 4), (dKm0 + static_cast<uint64_t>(st * (AB_T64 >> 4))) + static_cast<uint64_t>((kk * 2048) >> 4),
+                  idesc_acc, (s > 0) || (kk > 0));
+        umma_commit(&bars->kv_empty[st]);
+        umma_commit(&bars->p_empty[st]);
+      }
+      __syncwarp();
     }
-    umma_commit(&bars->acc_full);
+    if (elect_one_sync()) umma_commit(&bars->acc_full);
+    __syncwarp();
   } else if (warp >= 4) {
     // =============================== softmax threads: two per QUERY row (32 keys each) ======================
     const int sw = warp - 4;
