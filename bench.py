@@ -85,6 +85,10 @@ class ClockSampler:
     def start(self):
         try:
             self.nvml, self.handle = self._nvml_handle()
+            # first queries in the calling thread: NVML loads its entry points lazily (hundreds of ms on a fresh box,
+            # longer than a 120 ms timed region), so the polling thread must start warm
+            self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)
+            self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
             self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
             self.thread.start()
             return
@@ -139,7 +143,8 @@ class ClockSampler:
         if self.proc is not None:
             time.sleep(0.15)
             self.proc.terminate()
-        rows = self.rows[lo:hi] if (hi is None or hi > lo) else self.rows
+        in_window = hi is None or hi > lo
+        rows = self.rows[lo:hi] if in_window else self.rows  # no sample inside the window: fall back to the whole run
         sm, mx, reasons, power = [], None, set(), []
         for r in rows:
             try:
@@ -154,6 +159,7 @@ class ClockSampler:
         if not sm:
             return dict(sm_mhz=None, sm_max_mhz=mx, reasons=["no samples"])
         return dict(sm_mhz=statistics.median(sm), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm),
+                    window="timed region" if in_window else "whole run (no sample fell inside the timed region)",
                     power_w_max=max(power) if power else None,
                     source="nvml" if self.nvml is not None else "nvidia-smi")
 
@@ -372,16 +378,15 @@ def run_ours(args):
     # per-launch device times (CUDA events on the launching stream) of one eager step, taken first so the dominant
     # kernel is timed at burst clocks (the denominator is the burst peak)
     kernels = None
+    sampler = ClockSampler(local)
     if rank == 0:
+        sampler.start()  # started early: the poller is warm long before the timed region
         with torch.no_grad():
             eager_step = lambda: forward(inp.hidden_states, inp.token_type_ids, inp.position_ids, inp.padding_mask)
             kernels = instrument.profile(eager_step, iters=5)
     barrier()
     time.sleep(0.5)
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ms_total, _, launches = timed(step, args.steps, args.warmup, sampler if rank == 0 else None)
     clocks = sampler.stop(marks.get("lo", 0), marks.get("hi")) if rank == 0 else None
     ms_step = max_over_ranks(ms_total, dev) / args.steps

@@ -14,17 +14,22 @@ int launch_attention_tc2(const void* qkv, const int32_t* cu_seqlens, int B, int 
                          const int32_t* out_row_map, void* out, float scale, int rows_cap, float* lse, int causal,
                          cudaStream_t s);
 
-// VEX_ATTN_IMPL=tc1 / tc2 selects the one-tile tcgen05 kernel (k4_attention_tc.cu) or the two-tile ping-pong kernel
-// (k4_attention_tc2.cu); unset: kDefaultTc2 decides.
-constexpr bool kDefaultTc2 = true;  // parity-green on B200 and 17 % faster than the one-tile kernel at c2 (profiles/r1_attn_tc2_s8a.md)
+int launch_attention_tc3(const void* qkv, const int32_t* cu_seqlens, int B, int max_len_cap, int heads,
+                         const int32_t* out_row_map, void* out, float scale, int rows_cap, float* lse, int causal,
+                         cudaStream_t s);
+
+// Default: the persistent two-tile kernel (k4_attention_tc3.cu).  VEX_ATTN_IMPL=tc2 / tc1 select the non-persistent
+// two-tile kernel (k4_attention_tc2.cu, schedules behind VEX_ATTN_P) and the one-tile kernel (k4_attention_tc.cu);
+// all three are parity-tested (tests/test_kernels_gpu.py) and timed side by side by tools/bench_kernels.py.
 static int launch_attention_tcgen05(const void* qkv, const int32_t* cu_seqlens, int B, int max_len_cap, int heads,
                                     const int32_t* out_row_map, void* out, float scale, int rows_cap, float* lse,
                                     int causal, cudaStream_t s) {
   const char* impl = std::getenv("VEX_ATTN_IMPL");
-  const bool tc2 = impl ? std::strcmp(impl, "tc2") == 0 : kDefaultTc2;
-  if (!tc2)
+  if (impl && std::strcmp(impl, "tc1") == 0)
     return launch_attention_tc(qkv, cu_seqlens, B, max_len_cap, heads, out_row_map, out, scale, rows_cap, lse, causal, s);
-  return launch_attention_tc2(qkv, cu_seqlens, B, max_len_cap, heads, out_row_map, out, scale, rows_cap, lse, causal, s);
+  if (impl && std::strcmp(impl, "tc2") == 0)
+    return launch_attention_tc2(qkv, cu_seqlens, B, max_len_cap, heads, out_row_map, out, scale, rows_cap, lse, causal, s);
+  return launch_attention_tc3(qkv, cu_seqlens, B, max_len_cap, heads, out_row_map, out, scale, rows_cap, lse, causal, s);
 }
 }  // namespace vex
 

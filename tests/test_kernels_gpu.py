@@ -519,7 +519,7 @@ def test_k8_lora_wgrad(Tv, Tl, F, r):
 
 
 # ------------------------------------------------------------------------------------------ K4
-@pytest.mark.parametrize("impl", ["tc2", "tc2-smem", "tc2-tmem", "tc2-token", "tc1", "mma"])
+@pytest.mark.parametrize("impl", ["tc3", "tc2", "tc2-smem", "tc2-tmem", "tc2-token", "tc1", "mma"])
 @pytest.mark.parametrize("lens", [[1], [64], [65, 3, 128], [129, 128, 127], [300, 17, 1, 255], [257, 256, 255, 384],
                                   [1357], [700, 1485]])
 def test_k4_attention_vs_oracle(lens, impl, monkeypatch):

@@ -35,7 +35,7 @@ def bench_attention(B=8, nv=1225, nt=256, heads=32, only=None):
     out = torch.empty(cap, heads * 128, device="cuda", dtype=torch.bfloat16)
     flop = B * 4 * heads * 128 * L * (L + 1) / 2
     res = {}
-    impls = only or ("mma", "tc1", "tc2-smem", "tc2-tmem", "tc2-token", "tc2")
+    impls = only or ("mma", "tc1", "tc2-tmem", "tc2", "tc3")
     for impl in impls:
         os.environ["VEX_ATTN_IMPL"] = impl.split("-")[0]
         os.environ["VEX_ATTN_P"] = impl.split("-")[1] if "-" in impl else "early"
