@@ -504,17 +504,23 @@ __global__ void a3_prepare(__nv_bfloat16* buf, const int32_t* __restrict__ cu_se
 int launch_attention_tc3(const void* qkv, const int32_t* cu_seqlens, int B, int max_len_cap, int heads,
                          const int32_t* out_row_map, void* out, float scale, int rows_cap, float* lse, int causal,
                          cudaStream_t s) {
-  static int sm_count = 0;
-  static unsigned int* counters = nullptr;
+  // per-device state (one process per GPU is the normal deployment, but a process may also drive several devices)
+  constexpr int kMaxDev = 64;
+  static int sm_counts[kMaxDev] = {};
+  static unsigned int* counter_base[kMaxDev] = {};
   static std::atomic<unsigned int> next_counter{0};
-  if (sm_count == 0) {
-    int dev = 0, n = 0;
-    VEX_CUDA_TRY(cudaGetDevice(&dev));
+  int dev = 0;
+  VEX_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDev) return VEX_E_UNSUPPORTED;
+  if (sm_counts[dev] == 0) {
+    int n = 0;
     VEX_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
     VEX_CUDA_TRY(cudaFuncSetAttribute(k4_attention_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM));
-    VEX_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&counters), g_a3_counters));
-    sm_count = n;
+    VEX_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&counter_base[dev]), g_a3_counters));
+    sm_counts[dev] = n;
   }
+  const int sm_count = sm_counts[dev];
+  unsigned int* counters = counter_base[dev];
   const int H = heads * A3_D;
   CUtensorMap tm;
   std::memset(&tm, 0, sizeof(tm));

@@ -552,6 +552,42 @@ def test_k4_attention_vs_oracle(lens, impl, monkeypatch):
     torch.testing.assert_close(got.float(), tok(want).reshape(T, heads * 128).float(), rtol=2e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("impl", ["tc3", "tc2"])
+def test_k4_attention_many_items_per_cta(impl, monkeypatch):
+    """512 work items (8 ragged samples x 16 heads x 4 query-tile pairs, some pairs past the sample's end, some with an
+    inactive second tile) on at most 148 persistent CTAs: every CTA walks several items, so the running barrier phases,
+    the Q / O hand-over between items and the scheduler ring of the persistent kernel are exercised; checked against
+    the oracle like the small cases."""
+    monkeypatch.setenv("VEX_ATTN_IMPL", impl)
+    monkeypatch.delenv("VEX_ATTN_P", raising=False)
+    ops = _ops()
+    heads, lens = 16, [700, 130, 1, 513, 257, 1024, 64, 385]
+    B, Lmax = len(lens), max(lens)
+    g = torch.Generator().manual_seed(77)
+    pm = torch.zeros(B, Lmax, dtype=torch.bool)
+    for b, n in enumerate(lens):
+        pm[b, :n] = True
+    q, k, v = [torch.randn(B, heads, Lmax, 128, generator=g).bfloat16() for _ in range(3)]
+    want = O.attention(q, k, v, pm)
+    T = sum(lens)
+    tok = lambda t: t.permute(0, 2, 1, 3)[pm]
+    qkv_buf = torch.full((B * Lmax, 3 * heads * 128), float("nan"), dtype=torch.bfloat16)
+    qkv_buf[:T] = torch.stack([tok(q), tok(k), tok(v)], dim=1).reshape(T, 3 * heads * 128)
+    cu = torch.zeros(B + 1, dtype=torch.int32)
+    cu[1:] = torch.tensor(lens).cumsum(0)
+    rmap = torch.randperm(B * Lmax, generator=g).int()
+    out = torch.zeros(B * Lmax, heads * 128, dtype=torch.bfloat16).cuda()
+    qkv_dev, cu_dev, rmap_dev = qkv_buf.cuda(), cu.cuda(), rmap.cuda()
+    for _ in range(3):  # repeated launches reuse / rotate the work counters
+        out.zero_()
+        ops.attention(qkv_dev, cu_dev, B, Lmax, heads, rmap_dev, out, 128 ** -0.5)
+        got = out.cpu()[rmap[:T].long()]
+        torch.testing.assert_close(got.float(), tok(want).reshape(T, heads * 128).float(), rtol=2e-2, atol=2e-2)
+    untouched = torch.ones(B * Lmax, dtype=torch.bool)
+    untouched[rmap[:T].long()] = False
+    assert not out.cpu()[untouched].any()  # rows that belong to no live token are never written
+
+
 # ------------------------------------------------------------------------------------------ K9 (attention backward)
 @pytest.mark.parametrize("lens", [[1], [64], [65, 3, 128], [129, 128, 127], [300, 17, 1, 255], [700, 1485]])
 def test_k9_attention_backward_vs_autograd(lens):

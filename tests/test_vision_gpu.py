@@ -144,7 +144,8 @@ def test_scatter_rows_bit_exact():
 
 
 # ------------------------------------------------------------------------------------------ K4 non-causal
-@pytest.mark.parametrize("lens,heads", [([129, 17, 256, 300], 2), ([1226, 1226], 16), ([1, 128, 127], 3)])
+@pytest.mark.parametrize("lens,heads", [([129, 17, 256, 300], 2), ([1226, 1226], 16), ([1, 128, 127], 3),
+                                        ([600, 1226, 77, 300, 1226, 129, 512, 1000], 16)])  # 640 items / 148 CTAs
 def test_attention_blockdiag(lens, heads):
     g = torch.Generator().manual_seed(sum(lens))
     B, max_len = len(lens), max(lens)
