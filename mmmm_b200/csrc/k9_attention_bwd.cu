@@ -178,6 +178,22 @@ __device__ __forceinline__ void store_grad_row(uint32_t taddr, bool rope, const 
   }
 }
 
+#ifdef VEX_ATTN_TRACE
+// timing experiment build (tools/attn_trace.py k9): cycle stamps of CTA (0, 0, 0) of the dK/dV kernel
+__device__ long long* g_k9_trace = nullptr;  // [64 steps][8 stamps], row 63 = CTA-level stamps
+extern "C" int vex_debug_k9_trace(long long* buf) {
+  return cudaMemcpyToSymbol(g_k9_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -1;
+}
+#define K9_TRACE(ptr, j, k)                                   \
+  do {                                                        \
+    if ((ptr) && (j) < 64) (ptr)[(j) * 8 + (k)] = clock64();  \
+  } while (0)
+#else
+#define K9_TRACE(ptr, j, k) \
+  do {                      \
+  } while (0)
+#endif
+
 // =============================================================================================
 // dK, dV
 // =============================================================================================
@@ -191,6 +207,10 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     k9_attn_bwd_dkdv(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_constant__ CUtensorMap tm_qkv64,
                      const __grid_constant__ CUtensorMap tm_do64, const BwdParams p) {
   const int b = blockIdx.z, h = blockIdx.y, jb = blockIdx.x;
+#ifdef VEX_ATTN_TRACE
+  long long* trc = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128) ? g_k9_trace : nullptr;
+  K9_TRACE(trc, 63, 0);
+#endif
   const int seq0 = p.cu_seqlens[b], len = p.cu_seqlens[b + 1] - seq0;
   const int kv0 = jb * 128;
   if (kv0 >= len) return;
@@ -329,15 +349,19 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
       return v;
     };
     float stat_next = load_stat(0);
+    K9_TRACE(trc, 63, 1);
     for (int s = 0; s < n_steps; ++s) {
       const int st = s & 1;
       const uint32_t ph = (s >> 1) & 1;
       const int q_base = (i0 + s) * 64;
+      K9_TRACE(trc, s, 0);
       if (sid < 128) sStat[st * 128 + sid] = stat_next;
       stat_next = load_stat(s + 1);
       named_bar_sync(1, 256);
+      K9_TRACE(trc, s, 1);
       mbar_wait(&bars->s_full[st], ph);
       tc_fence_after();
+      K9_TRACE(trc, s, 2);
       uint32_t sraw[32], draw[32];
       tmem_ld_32x32b_x32(tS + lane_sel + st * 64 + half * 32, sraw);
       tmem_ld_32x32b_x32(tdP + lane_sel + st * 64 + half * 32, draw);
@@ -382,17 +406,22 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
           dk[2 * j4 + 1] = pack_bf16(ds[2], ds[3]);
         }
       }
+      K9_TRACE(trc, s, 3);
       mbar_wait(&bars->p_empty[st], ph ^ 1);  // the MMAs of step s - 2 have finished reading this P / dS buffer
+      K9_TRACE(trc, s, 4);
       store_row_half(smem_u32(sP + st * AB_P), c, half, pk);
       store_row_half(smem_u32(sdS + st * AB_P), c, half, dk);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->p_full[st]);
+      K9_TRACE(trc, s, 5);
     }
     // ---- epilogue: dV (plain), dK (scale, rotary transpose) -> dqkv[token_to_sorted[tok]] ----
+    K9_TRACE(trc, 63, 2);
     mbar_wait(&bars->acc_full, 0);
     tc_fence_after();
+    K9_TRACE(trc, 63, 3);
     const bool valid = kv_idx < len;
     const int tok = seq0 + kv_idx;
     int dst = 0, pos = 0;
@@ -407,6 +436,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     else
       store_grad_row(tdK + lane_sel, true, p.rope_cos + static_cast<int64_t>(pos) * 128,
                      p.rope_sin + static_cast<int64_t>(pos) * 128, p.scale, row + H, valid, 0, 2);
+    K9_TRACE(trc, 63, 4);
   }
 
   tc_fence_before();
