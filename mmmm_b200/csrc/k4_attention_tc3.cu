@@ -45,21 +45,22 @@ constexpr int A3_SCHED = 4;                                // scheduler ring dep
 constexpr int A3_SCHED_READERS = 10;                       // 2 issuer warps + 8 softmax warps (lane 0 arrives)
 constexpr int A3_NCOUNTERS = 1024;                         // work counters, one per launch in flight (round-robin)
 constexpr int A3_TILES = 2 + A3_KV_SLOTS + 2;              // Q_A, Q_B, K/V ring, P_A, P_B
-constexpr int A3_SMEM = A3_TILES * A3_TILE + 256 + 1024;   // + barriers + alignment slack
+constexpr int A3_SMEM = A3_TILES * A3_TILE + 512 + 1024;   // + barriers / scheduler ring + alignment slack
+
+struct A3Item {  // a decoded work item as the scheduler publishes it; valid == -1: work exhausted, 0: nothing to do
+  int valid, seq0, len, h, q0, nA, nB, n_max;
+};
 
 struct Attn3Bars {
   uint64_t q_full, q_empty, kv_full[A3_KV_SLOTS], kv_empty[A3_KV_SLOTS];
   uint64_t s_full[2], s_free[2], p_full[2], pv_done[2], o_free[2];
   uint64_t sched_full[A3_SCHED], sched_empty[A3_SCHED];
-  int32_t sched_item[A3_SCHED];
+  A3Item sched_item[A3_SCHED];
   uint32_t tmem_base;
 };
+static_assert(sizeof(Attn3Bars) <= 512, "barrier block");
 
 __device__ unsigned int g_a3_counters[A3_NCOUNTERS];
-
-struct A3Item {
-  int seq0, len, h, q0, nA, nB, n_max;
-};
 
 // item -> (sample, head, query-tile pair).  Groups (sample, head) are taken in waves of `wave_groups` (about one item
 // per CTA and wave); inside a wave the items are ordered heaviest pair first across the wave's groups, so the groups of a
@@ -76,23 +77,24 @@ __device__ __forceinline__ bool a3_decode(int item, int heads, int nqp, int n_gr
   it.seq0 = __ldg(cu_seqlens + b);
   it.len = __ldg(cu_seqlens + b + 1) - it.seq0;
   it.q0 = qp * 2 * A3_BQ;
-  if (it.q0 >= it.len) return false;
+  it.valid = it.q0 < it.len;
   const int n_all = (it.len + A3_BK - 1) / A3_BK;
   it.nA = causal ? 2 * qp + 1 : n_all;
   it.nB = (it.q0 + A3_BQ < it.len) ? (causal ? 2 * qp + 2 : n_all) : 0;
   it.n_max = max(it.nA, it.nB);
-  return true;
+  return it.valid != 0;
 }
 
-// Readers of the scheduler ring (issuer / softmax warps): next item of this CTA, -1 when the work is exhausted.
-__device__ __forceinline__ int a3_next_item(Attn3Bars* bars, int& n_fetch, int lane) {
+// Readers of the scheduler ring (issuer / softmax warps): next DECODED item of this CTA (the scheduler thread did the
+// cu_seqlens loads once, so no reader waits on global memory between two items); false when the work is exhausted.
+__device__ __forceinline__ bool a3_next_item(Attn3Bars* bars, int& n_fetch, int lane, A3Item& w) {
   const int slot = n_fetch % A3_SCHED;
   mbar_wait(&bars->sched_full[slot], (n_fetch / A3_SCHED) & 1);
-  const int item = bars->sched_item[slot];
+  w = bars->sched_item[slot];
   __syncwarp();
   if (lane == 0) mbar_arrive(&bars->sched_empty[slot]);
   ++n_fetch;
-  return item;
+  return w.valid >= 0;
 }
 
 template <int N>
@@ -164,18 +166,28 @@ __global__ void __launch_bounds__(A3_THREADS, 1)
           phase ^= 1;
         }
       };
-      int n_done = 0;  // valid items so far
-      for (int n_fetch = 0;; ++n_fetch) {
-        // scheduler: fetch the next item and publish it to the other warps
+      int n_done = 0;   // valid items so far
+      int n_fetch = 0;  // items fetched / published so far
+      // scheduler: fetch the next item (atomic + cu_seqlens loads, ~2 500 cycles of latency), publish it decoded
+      auto fetch_publish = [&]() {
         const int slot_s = n_fetch % A3_SCHED;
         mbar_wait(&bars->sched_empty[slot_s], ((n_fetch / A3_SCHED) & 1) ^ 1);
         const unsigned int fetched = atomicAdd(work_counter, 1u);
-        const int item = fetched < static_cast<unsigned int>(n_items) ? static_cast<int>(fetched) : -1;
-        bars->sched_item[slot_s] = item;
+        A3Item it;
+        it.valid = -1;
+        if (fetched < static_cast<unsigned int>(n_items))
+          a3_decode(static_cast<int>(fetched), heads, nqp, n_groups, wave_groups, cu_seqlens, causal, it);
+        bars->sched_item[slot_s] = it;
         mbar_arrive(&bars->sched_full[slot_s]);  // release: the item is visible to whoever observes the phase
-        if (item < 0) break;
-        A3Item w;
-        if (!a3_decode(item, heads, nqp, n_groups, wave_groups, cu_seqlens, causal, w)) continue;
+        ++n_fetch;
+        return it;
+      };
+      A3Item w = fetch_publish();
+      while (w.valid >= 0) {
+        if (w.valid == 0) {
+          w = fetch_publish();
+          continue;
+        }
         const int colq = w.h * A3_D, colk = H + w.h * A3_D, colv = 2 * H + w.h * A3_D;
         if (n_done > 0) mbar_wait(&bars->q_empty, (n_done - 1) & 1);  // every S of the previous item has read Q
         mbar_arrive_expect_tx(&bars->q_full, 2 * A3_TILE);
@@ -191,6 +203,9 @@ __global__ void __launch_bounds__(A3_THREADS, 1)
           load_item(colv, w.seq0 + j * A3_BK);
         }
         ++n_done;
+        // fetched only now (not an item ahead): an item claimed early is an item no idle CTA can take, and with ~5 items
+        // per CTA (c4 shard) the early claim cost 6 % in tail imbalance
+        w = fetch_publish();
       }
     } else if (warp == 1 || warp == 3) {
       // =============================== MMA issuers: warp 1 tile A, warp 3 tile B ===============================
@@ -257,10 +272,9 @@ __global__ void __launch_bounds__(A3_THREADS, 1)
       };
       int n_fetch = 0;
       for (;;) {
-        const int item = a3_next_item(bars, n_fetch, lane);
-        if (item < 0) break;
         A3Item w;
-        if (!a3_decode(item, heads, nqp, n_groups, wave_groups, cu_seqlens, causal, w)) continue;
+        if (!a3_next_item(bars, n_fetch, lane, w)) break;
+        if (w.valid == 0) continue;
         const int nX = x ? w.nB : w.nA;
         mbar_wait(&bars->q_full, n_done & 1);
         tc_fence_after();
@@ -297,13 +311,16 @@ __global__ void __launch_bounds__(A3_THREADS, 1)
 
     int n_fetch = 0;
     for (;;) {
-      const int item = a3_next_item(bars, n_fetch, lane);
-      if (item < 0) break;
       A3Item w;
-      if (!a3_decode(item, heads, nqp, n_groups, wave_groups, cu_seqlens, causal, w)) continue;
+      if (!a3_next_item(bars, n_fetch, lane, w)) break;
+      if (w.valid == 0) continue;
       const int nX = x ? w.nB : w.nA;
       if (nX == 0) continue;
       const int qx0 = w.q0 + x * A3_BQ;
+      // destination row of this thread's query row, loaded now so that the epilogue does not wait on global memory
+      const int tok = w.seq0 + qx0 + r;
+      const bool row_ok = qx0 + r < w.len;
+      const int my_dst = row_ok ? (out_row_map ? __ldg(out_row_map + tok) : tok) : -1;
       float m_run = -INFINITY, l_run = 0.f;  // m_run: running reference in scaled log2 units (integer-valued)
 
       for (int j = 0; j < nX; ++j, ++c) {
@@ -459,9 +476,6 @@ __global__ void __launch_bounds__(A3_THREADS, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->o_free[x]);
-      const int tok = w.seq0 + qx0 + r;
-      const bool row_ok = qx0 + r < w.len;
-      const int my_dst = row_ok ? (out_row_map ? out_row_map[tok] : tok) : -1;
       // training: log2-domain log-sum-exp of the scaled scores, [heads, rows_cap] (read back by the backward kernels)
       if (lse != nullptr && row_ok) lse[static_cast<int64_t>(w.h) * rows_cap + tok] = m_run + log2f(l_run);
 #pragma unroll 4
