@@ -28,6 +28,22 @@
 
 #include "common.cuh"
 
+#ifdef VEX_ATTN_TRACE
+// timing experiment build (tools/a3_trace.py): cycle stamps of tile A's softmax warp 0 in CTA 0
+__device__ long long* g_a3_trace = nullptr;  // [128 blocks][8 stamps]
+extern "C" int vex_debug_a3_trace(long long* buf) {
+  return cudaMemcpyToSymbol(g_a3_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -1;
+}
+#define A3_TRACE(ptr, j, k)                                    \
+  do {                                                         \
+    if ((ptr) && (j) < 128) (ptr)[(j) * 8 + (k)] = clock64();  \
+  } while (0)
+#else
+#define A3_TRACE(ptr, j, k) \
+  do {                      \
+  } while (0)
+#endif
+
 namespace vex {
 
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
@@ -308,6 +324,9 @@ __global__ void __launch_bounds__(A3_THREADS, 1)
     const uint32_t p_tile = smem_u32(sP + x * A3_TILE);
     const float inv_scale_log2 = 1.0f / scale_log2;
     int c = 0;  // key blocks of this tile so far (s_full / s_free / p_full / pv_done phases)
+#ifdef VEX_ATTN_TRACE
+    long long* trc = (blockIdx.x == 0 && threadIdx.x == 128) ? g_a3_trace : nullptr;  // pointer stays in a register
+#endif
 
     int n_fetch = 0;
     for (;;) {
@@ -324,8 +343,10 @@ __global__ void __launch_bounds__(A3_THREADS, 1)
       float m_run = -INFINITY, l_run = 0.f;  // m_run: running reference in scaled log2 units (integer-valued)
 
       for (int j = 0; j < nX; ++j, ++c) {
+        A3_TRACE(trc, c, 0);
         mbar_wait(&bars->s_full[x], c & 1);
         tc_fence_after();
+        A3_TRACE(trc, c, 1);
         uint32_t s[128];
 #pragma unroll
         for (int q = 0; q < 4; ++q) tmem_ld_32x32b_x32(tS + q * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[q * 32]));
@@ -334,6 +355,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->s_free[x]);
+        A3_TRACE(trc, c, 2);
         if (j == nX - 1) {
           // last block.  causal: the tile's diagonal block, key (j*128 + k) visible iff k <= r.  non-causal: keys past
           // the end of the sample (the next sample's tokens / the zeroed tail) are masked, k <= len - 1 - j*128
@@ -351,6 +373,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1)
           mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
         }
         const float mxs = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+        A3_TRACE(trc, c, 3);
         // lazy rescale against an integer-valued reference (see k4_attention_tc2.cu)
         float alpha = 1.0f;
         bool rescale = false;
@@ -406,11 +429,13 @@ __global__ void __launch_bounds__(A3_THREADS, 1)
         float rs0, rs1;
         f2_unpack(f2_add(rs2[0], rs2[1]), rs0, rs1);
         l_run = l_run * alpha + (rs0 + rs1);
+        A3_TRACE(trc, c, 4);
 
         if (j > 0) {  // P_x and O_x are free once the previous PV_x has completed (first block: the epilogue waited)
           mbar_wait(&bars->pv_done[x], (c - 1) & 1);
           tc_fence_after();
         }
+        A3_TRACE(trc, c, 5);
         // UMMA K-major SWIZZLE_128B: key atom a = keys [64a, 64a + 64); (row, 16-byte chunk c16) at
         // row*128 + ((c16 ^ row%8) * 16); chunk c16 of atom a = packed pairs s[32a + 4*c16 .. + 3]
         const uint32_t p_row = p_tile + r * 128;
@@ -446,7 +471,9 @@ __global__ void __launch_bounds__(A3_THREADS, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->p_full[x]);
+        A3_TRACE(trc, c, 6);
       }
+      A3_TRACE(trc, c - 1, 7);  // marks the item's last block; the next block's stamp 0 closes the item boundary
 
       // ---- epilogue: normalise the row, stage it in this warp's own rows of the (dead) P tile, scatter coalesced ----
       mbar_wait(&bars->pv_done[x], (c - 1) & 1);  // the item's last PV_x (and every earlier MMA of the tile) is done

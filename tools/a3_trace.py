@@ -63,16 +63,6 @@ def run():
         nxt = int(t[c + 1, 0]) if c + 1 < 128 else 0
         tail = f"  E gap {nxt - r[6]:6d}" if r[7] and nxt else ""
         print(f"  {c:3d} @ {r[0] - t0:7d} | " + " ".join(f"{r[i + 1] - r[i]:6d}" for i in range(6)) + f" | {r[6] - r[0]:6d}{tail}")
-    print(" item | issuer A: @got item, +q_full wait, +S(0) issued (s_free + K_0 waits), @item issue done || producer: @item start, "
-          "+q_empty wait, +Q,K_0 issued, +next item fetched, @last load issued")
-    for i in range(12):
-        a = [int(v) for v in t[64 + i, :8]]
-        b = [int(v) for v in t[96 + i, :5]]
-        if not a[0]:
-            break
-        print(f"      last PV: reached @ {a[4] - t0:7d}, p_full seen @ {a[6] - t0:7d}, V landed @ {a[7] - t0:7d}, issued @ {a[5] - t0:7d}")
-        print(f"  {i:2d} | @ {a[0] - t0:7d} {a[1] - a[0]:6d} {a[2] - a[1]:6d} @ {a[3] - t0:7d} || @ {b[0] - t0:7d} {b[1] - b[0]:6d} "
-              f"{b[2] - b[1]:6d} {b[3] - b[2]:6d} @ {b[4] - t0:7d}")
 
 
 if __name__ == "__main__":
