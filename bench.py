@@ -58,6 +58,26 @@ def peaks():
     return p
 
 
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout
+    when the process group comes up), so file descriptor 1 is pointed at stderr for the rest of the run and the result
+    line goes to a private duplicate of the original stdout."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: str):
+    out = _RESULT_OUT or sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 class ClockSampler:
     """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md clocks line).  Sampled in-process through
     NVML (pynvml: no start-up delay, so even a 100 ms timed region gets samples); `nvidia-smi -lms` is the fallback."""
@@ -203,7 +223,7 @@ def run_reference_arm(args):
     cores = torch.get_num_threads()
     b, nv, nt = WORKLOADS[args.workload]
     sample = f"1 of {b} samples per step ({tokens} tokens: {nv} vision + {nt} text), fp32 eager, 1 layer"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "visual-expert prefill tokens/s", "value": val, "unit": "tokens/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
@@ -439,7 +459,7 @@ def run_ours(args):
     h2d = sum(t.numel() * t.element_size() for t in (h_host, tt_host, pos_host, pm_host))
     d2h = out_host[0].numel() * out_host[0].element_size()
     cfg = config_dict(args, tokens)
-    print(json.dumps({
+    emit(json.dumps({
         "metric": "visual-expert prefill tokens/s", "value": value, "unit": "tokens/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
@@ -538,7 +558,7 @@ def run_train(args):
         flop = args.layers * ((g_fwd + lora_f) + rec * (g_fwd - g_down + lora_f) + (g_fwd + lora_f) + 2 * lora_f
                               + (1 + rec) * attn_f + 2.5 * attn_f)
         pk = peaks()
-        print(json.dumps({
+        emit(json.dumps({
             "metric": "visual-expert LoRA train tokens/s", "value": total / (ms_step / 1e3), "unit": "tokens/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -650,7 +670,7 @@ def run_vision(args):
                     "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": None,
                     "peak_source": pk["source"] + " (burst figure)", "ms_per_launch": ms_launch}
         total = tokens * world
-        print(json.dumps({
+        emit(json.dumps({
             "metric": "vision-encoder prefill tokens/s", "value": total / (ms_step / 1e3), "unit": "tokens/s",
             "images_per_s": b * world / (ms_step / 1e3), "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -690,6 +710,7 @@ def main():
     ap.add_argument("--vision", action="store_true", help="SURVEY 8(f)-4: time the EVA2-CLIP-E vision encoder instead")
     ap.add_argument("--vision-layers", type=int, default=63)
     args = ap.parse_args()
+    claim_stdout()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
