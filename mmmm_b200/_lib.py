@@ -57,10 +57,13 @@ def lib() -> C.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
-        path = os.environ.get("VEX_LIB_PATH") or _build.LIB  # override: experiment builds (tools/attn_trace.py)
-        if path != _build.LIB:
-            pass
-        elif not _build.is_fresh():
+        path = os.environ.get("VEX_LIB_PATH")  # experiment builds (tools/*_trace.py) load their own library as is
+        if path:
+            if not os.path.isfile(path):
+                raise VexError(f"VEX_LIB_PATH={path} does not exist")
+        else:
+            path = _build.LIB
+        if path == _build.LIB and not _build.is_fresh():
             if os.path.isfile(_build.NVCC):
                 path = _build.build()
             elif not os.path.isfile(path):
