@@ -181,7 +181,10 @@ int vex_grouped_gemm(const vexGemmArgs* args, vexStream stream);
  *   qkv [rows_cap = B*max_len_cap, 3, heads, 128] bf16, rows [0, T) live (q and k already rotated); rows
  *   [T, T+128) are scratch and are zeroed by the call.  out rows are scattered through out_row_map
  *   (token_to_sorted; NULL = identity) into [rows_cap, heads*128] bf16.
- *   Environment VEX_ATTN_IMPL=mma selects the mma.sync baseline kernel instead of the tcgen05 one. */
+ *   Default implementation: the persistent two-tile tcgen05 kernel (k4_attention_tc3.cu); it draws work items from
+ *   one of 1024 device-side counters handed out round-robin per launch and reset by the call itself (stream-ordered;
+ *   captured launches keep their counter).  Environment, for A/B measurements: VEX_ATTN_IMPL=tc2 | tc1 (earlier
+ *   tcgen05 kernels) | mma (mma.sync baseline, forward only); VEX_ATTN_P=tmem|smem|token (tc2 schedules). */
 int vex_attention(const void* qkv, const int32_t* cu_seqlens, int B, int max_len_cap, int heads,
                   const int32_t* out_row_map, void* out, float scale, vexStream stream);
 
