@@ -12,19 +12,23 @@
 // share the K/V stream:
 //   warp 0 / lane 0 : TMA producer -- Q_A, Q_B once, then K_j, V_j through ONE 3-slot ring (K_j, V_j, K_{j+1} in
 //                     flight), straight out of the token-order QKV buffer [rows_cap, 3*heads*128].
-//   warp 1 / lane 0 : MMA issuer: S_A(0), S_B(0), then per key block  PV_A(j), S_A(j+1), PV_B(j), S_B(j+1): while the
-//                     softmax warps of one tile work, the tensor core runs the other tile's two GEMMs.
+//   warp 1, warp 3  : MMA issuers of tile A / tile B.  The whole warp runs the loop and one elected lane issues
+//                     (a single-thread issuer for both tiles set the pace of the first version: ~110 cycles per
+//                     64-cycle MMA, profiles/r1_attn_tc2_s8.md).  Per key block and tile: S_x(j+1) and PV_x(j), in the
+//                     order the schedule (below) prescribes; ring slots are released by both issuers.
 //   warp 2          : TMEM allocate / free: S_A, S_B, O_A, O_B = 4 x 128 columns.
 //   warps 4..7      : softmax of tile A, ONE thread per query row (TMEM lane == row: no shuffles, no exchange);
-//   warps 8..11     : softmax of tile B.  Each scheduler hosts one A warp and one B warp in different phases, so the
-//                     MUFU-bound exp loop of one overlaps the TMEM-load / max / pack code of the other.  The 128 scores
-//                     of a row stay in registers (setmaxnreg: 224 for the softmax warpgroups, 56 for warps 0..3).
-//   P               : PT = true  -> bf16 pairs written back into the first 64 columns of the tile's S accumulator
-//                                   (tcgen05.st) and consumed as the TMEM A operand of O += P.V: no shared-memory
-//                                   round trip (an SS-mode M128 x N128 MMA already reads 128 B / clk of operands);
-//                     PT = false -> shared memory in the UMMA K-major 128B-swizzle layout (A/B switch VEX_ATTN_P=smem).
-// Ordering: S_X(j+1) is issued after PV_X(j), and tcgen05.commit tracks every earlier MMA of the issuing thread, so
-// s_full_X(j+1) also means "PV_X(j) done": P_X and O_X are free without a separate barrier inside the loop.
+//   warps 8..11     : softmax of tile B.  The 128 scores of a row stay in registers (setmaxnreg: 224 for the softmax
+//                     warpgroups, 56 for warps 0..3); half of the exp2 pairs run on the FMA pipe (A2_EMU).
+// Schedules (VEX_ATTN_P; the persistent kernel k4_attention_tc3.cu uses the default one):
+//   "early" (default, ES = 1): P in shared memory in the UMMA K-major 128B-swizzle layout; S_x(j+1) is issued as soon
+//                     as the softmax warps hold S_x(j) in registers (s_free), so the softmax of block j+1 starts the
+//                     moment block j is done and overlaps PV_x(j); pv_done gates the next P store / O rescale.
+//   "token" (ES = 2): "early" plus exp loops of the two tiles of a scheduler taking turns (named-barrier pairs).
+//   "tmem"  (PT)    : bf16 pairs written back into the first 64 columns of the tile's S accumulator (tcgen05.st) and
+//                     consumed as the TMEM A operand of O += P.V; S_x(j+1) is issued after PV_x(j), and tcgen05.commit
+//                     tracks every earlier MMA of the issuing thread, so s_full_x(j+1) also means "PV_x(j) done".
+//   "smem"          : the "tmem" order with P in shared memory.
 #include <cuda.h>
 
 #include <cstdlib>
