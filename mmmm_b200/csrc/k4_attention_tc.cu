@@ -116,24 +116,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       tma_load_2d(sV + s * TC_TILE, &tm_qkv, &bars->v_full[s], colv, row);
       tma_load_2d(sV + s * TC_TILE + TC_ATOM, &tm_qkv, &bars->v_full[s], colv + 64, row);
     }
-  } else if (warp == 1 && lane == 0) {
-    // =============================== MMA issuer ===============================
+  } else if (warp == 1) {
+    // =============================== MMA issuer (whole warp, elected lane issues; see k4_attention_tc2.cu) ==========
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
     constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);  // B (= V) is MN-major
-    const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
+    const uint64_t dQ = umma_desc_kmajor_sw128(smem_u32(sQ)), dP = umma_desc_kmajor_sw128(smem_u32(sP));
+    const uint64_t dK0 = umma_desc_kmajor_sw128(smem_u32(sK));                  // stage s adds s * TILE / 16
+    const uint64_t dV0 = umma_desc_mnmajor_sw128(smem_u32(sV), TC_ATOM, 1024);  // 16 keys = 2 groups of 8 rows
     auto issue_s = [&](int j) {
       const int s = j & 1;
       mbar_wait(&bars->k_full[s], (j >> 1) & 1);
       tc_fence_after();
-      const uint32_t aK = smem_u32(sK + s * TC_TILE);
+      const uint64_t dk = dK0 + static_cast<uint64_t>(s * (TC_TILE >> 4));
+      if (elect_one_sync()) {
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {  // d = 128 in K=16 steps; atom = kk / 4, 32 B per step inside the atom
-        const uint32_t off = (kk >> 2) * TC_ATOM + (kk & 3) * 32;
-        umma_ss(tS0 + s * 128, umma_desc_kmajor_sw128(aQ + off), umma_desc_kmajor_sw128(aK + off), idesc_s,
-                kk > 0);
+        for (int kk = 0; kk < 8; ++kk) {  // d = 128 in K=16 steps; atom = kk / 4, 32 B per step inside the atom
+          const uint64_t off = static_cast<uint64_t>(((kk >> 2) * TC_ATOM + (kk & 3) * 32) >> 4);
+          umma_ss(tS0 + s * 128, dQ + off, dk + off, idesc_s, kk > 0);
+        }
+        umma_commit(&bars->k_empty[s]);
+        umma_commit(&bars->s_full[s]);
       }
-      umma_commit(&bars->k_empty[s]);
-      umma_commit(&bars->s_full[s]);
+      __syncwarp();
     };
     mbar_wait(&bars->q_full, 0);
     issue_s(0);
@@ -143,17 +147,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_wait(&bars->p_full, j & 1);
       mbar_wait(&bars->v_full[s], (j >> 1) & 1);
       tc_fence_after();
-      const uint32_t aV = smem_u32(sV + s * TC_TILE);
+      const uint64_t dv = dV0 + static_cast<uint64_t>(s * (TC_TILE >> 4));
+      if (elect_one_sync()) {
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {  // 128 keys in K=16 steps
-        // A = P: K-major, atom = kk / 4 (64 keys each), 32 B per step.
-        const uint64_t da = umma_desc_kmajor_sw128(aP + (kk >> 2) * TC_ATOM + (kk & 3) * 32);
-        // B = V: MN-major; 16 keys = 2 groups of 8 rows (SBO 1024 B), d chunks of 64 are 16 KB apart (LBO).
-        const uint64_t db = umma_desc_mnmajor_sw128(aV + kk * 2048, TC_ATOM, 1024);
-        umma_ss(tO, da, db, idesc_pv, (j > 0) || (kk > 0));
+        for (int kk = 0; kk < 8; ++kk)  // 128 keys in K=16 steps: P K-major (atom = kk / 4), V MN-major (2048 B per step)
+          umma_ss(tO, dP + static_cast<uint64_t>(((kk >> 2) * TC_ATOM + (kk & 3) * 32) >> 4),
+                  dv + static_cast<uint64_t>(kk * (2048 >> 4)), idesc_pv, (j > 0) || (kk > 0));
+        umma_commit(&bars->v_empty[s]);
+        umma_commit(&bars->pv_done);
       }
-      umma_commit(&bars->v_empty[s]);
-      umma_commit(&bars->pv_done);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // =============================== softmax + epilogue ===============================
