@@ -39,7 +39,18 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 256;
-constexpr int GROUP_M = 16;
+constexpr int GROUP_M = 16;  // smallest raster group (m-tiles): 74 CTA pairs cover 8 x ~9 tiles, the minimal working set
+
+// Raster group height.  Tiles are walked group by group (group_m m-tiles x all n-tiles, m fastest): the A rows of a group
+// (group_m * 128 * K * 2 bytes) stay in L2 while the weights stream past once per group, so the weights of an expert
+// are read from DRAM ceil(m_tiles / group_m) times.  With the minimal group the c2 SwiGLU launch read 1.62 GB for
+// 0.72 GB of algorithmic traffic (ncu).  Take the tallest group whose A rows fit in a third of the 126 MB L2.
+__host__ inline int raster_group_for(int K) {
+  const long long per_tile = 128LL * K * 2;
+  long long g = (40LL << 20) / per_tile;
+  g = g < GROUP_M ? GROUP_M : (g > 128 ? 128 : g);
+  return static_cast<int>(g & ~1LL);
+}
 
 struct alignas(64) GemmTmaps {
   CUtensorMap a;         // activations [rows_cap, K]
@@ -78,6 +89,7 @@ struct GemmDev {
   // vision-encoder Linears (visual.py:84-85, :110-111: nn.Linear WITH bias; MLP activation ACT2FN['gelu'])
   const __nv_bfloat16* bias;  // [N] or nullptr: added to the fp32 accumulator before the bf16 rounding
   int act;                    // VEX_ACT_NONE / VEX_ACT_GELU (exact erf form, on the bf16-rounded Linear output)
+  int raster_group;           // m-tiles (128 rows) per raster group, even; see raster_group_for()
 };
 
 template <int BN>
@@ -110,7 +122,7 @@ struct TileCoord {
   int e, m, n;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(int tile, int mt0, int mt1, int n_tiles) {
+__device__ __forceinline__ TileCoord decode_tile(int tile, int mt0, int mt1, int n_tiles, int group_m) {
   TileCoord c;
   int mt_e = mt0;
   c.e = 0;
@@ -120,11 +132,11 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, int mt0, int mt1, int
     tile -= t0;
     mt_e = mt1;
   }
-  const int per_group = GROUP_M * n_tiles;
+  const int per_group = group_m * n_tiles;
   const int g = tile / per_group;
   const int r = tile - g * per_group;
-  const int m_lo = g * GROUP_M;
-  const int gm = min(GROUP_M, mt_e - m_lo);
+  const int m_lo = g * group_m;
+  const int gm = min(group_m, mt_e - m_lo);
   c.n = r / gm;
   c.m = m_lo + (r - c.n * gm);
   return c;
@@ -730,7 +742,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord c = decode_tile(tile, mt0, mt1, n_tiles);
+      const TileCoord c = decode_tile(tile, mt0, mt1, n_tiles, p.raster_group);
       const int row0 = (c.e ? cnt0 : 0) + c.m * BM;
       const int nrow0 = c.n * n_span;
       const int nrow1 = swiglu ? nrow0 : nrow0 + BN / 2;
@@ -795,7 +807,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord c = decode_tile(tile, mt0, mt1, n_tiles);
+      const TileCoord c = decode_tile(tile, mt0, mt1, n_tiles, p.raster_group);
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -852,7 +864,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord c = decode_tile(tile, mt0, mt1, n_tiles);
+      const TileCoord c = decode_tile(tile, mt0, mt1, n_tiles, p.raster_group);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       epilogue_tile<BN>(p, c.e, c.m, c.n, cnt0, cnt1, t_lane + static_cast<uint32_t>(acc * BN), stage_base, lane, ew,
@@ -905,7 +917,7 @@ struct PairTile {
   int e, m2, n;  // expert, index of the 256-row super-tile inside the expert segment, n-tile
 };
 
-__device__ __forceinline__ PairTile decode_pair_tile(int tile, int mp0, int mp1, int n_tiles) {
+__device__ __forceinline__ PairTile decode_pair_tile(int tile, int mp0, int mp1, int n_tiles, int group_pairs) {
   PairTile c;
   int mp_e = mp0;
   c.e = 0;
@@ -915,7 +927,7 @@ __device__ __forceinline__ PairTile decode_pair_tile(int tile, int mp0, int mp1,
     tile -= t0;
     mp_e = mp1;
   }
-  constexpr int GROUP = GROUP_M / 2;  // 8 super-tiles = 16 m-tiles per raster group
+  const int GROUP = group_pairs;  // super-tiles (256 rows) per raster group
   const int per_group = GROUP * n_tiles;
   const int g = tile / per_group;
   const int r = tile - g * per_group;
@@ -984,7 +996,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1)
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-      const PairTile c = decode_pair_tile(tile, mp0, mp1, n_tiles);
+      const PairTile c = decode_pair_tile(tile, mp0, mp1, n_tiles, p.raster_group / 2);
       const int row0 = (c.e ? cnt0 : 0) + (2 * c.m2 + static_cast<int>(rank)) * BM;
       // this CTA's half of the 256 accumulator columns: leader = [0,128), peer = [128,256).
       // SwiGLU: leader half = gate_proj rows, peer half = up_proj rows of the same 128 output columns.
@@ -1047,7 +1059,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1)
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-      const PairTile c = decode_pair_tile(tile, mp0, mp1, n_tiles);
+      const PairTile c = decode_pair_tile(tile, mp0, mp1, n_tiles, p.raster_group / 2);
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -1103,7 +1115,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1)
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-      const PairTile c = decode_pair_tile(tile, mp0, mp1, n_tiles);
+      const PairTile c = decode_pair_tile(tile, mp0, mp1, n_tiles, p.raster_group / 2);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       epilogue_tile_half(p, c.e, 2 * c.m2 + static_cast<int>(rank), c.n, cnt0, cnt1,
@@ -1309,6 +1321,10 @@ extern "C" int vex_grouped_gemm(const vexGemmArgs* a, vexStream stream) {
   dev.rows_cap = a->rows_cap;
   dev.N = a->N;
   dev.K = a->K;
+  {
+    const char* rg = std::getenv("VEX_GEMM_RASTER");  // A/B switch: m-tiles per raster group
+    dev.raster_group = rg ? std::max(2, std::atoi(rg) & ~1) : raster_group_for(a->K);
+  }
   dev.mode = a->mode;
   dev.single_expert = a->single_expert;
   dev.trans_b = tb;
