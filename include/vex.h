@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VEX_ABI_VERSION 6
+#define VEX_ABI_VERSION 7
 
 #define VEX_OK 0
 #define VEX_E_INVALID (-1)     /* bad argument (null pointer, size, alignment) */
@@ -60,8 +60,9 @@ int vex_device_check(void);
  * from it (:96-97, :244-245, :278-279, :307, :326) and _to_tensor_list (:100-104).
  *   vision[b,l]   = tt[b,l]==1 && tt[b,l+1]==1 (l < L-1; last column false), && padding_mask
  *   language[b,l] = !vision_raw && padding_mask
- * Requires L > 1 (the L == 1 decode rule of :67 is out of scope).  All index outputs have B*L entries;
- * entries past the respective count are -1.
+ * Requires L > 1: the L == 1 rule of :67 (every token of a decode step goes to the language expert) needs no
+ * partition -- the decode step calls vex_grouped_gemm with single_expert = 1 on the language weights.  All index
+ * outputs have B*L entries; entries past the respective count are -1.
  *   sorted_to_flat [s] : flat position of sorted row s       ([0,Tv) == nonzero(vision), [Tv,Tv+Tl) == nonzero(language))
  *   flat_to_sorted [f] : inverse, -1 for padded positions
  *   sorted_to_token[s] : token rank of sorted row s
@@ -171,6 +172,18 @@ typedef struct vexGemmArgs {
                                encoder's Linears, visual.py:84-85, :110-111, and the patch convolution), added to the fp32
                                accumulator before the single bf16 rounding; NULL = none.  N % 32 == 0, forward form only */
   int32_t act;              /* VEX_EPI_PLAIN: activation applied to the bf16-rounded output (VEX_ACT_*) */
+  /* VEX_EPI_ROPE second output -- KV-cache production (modeling_cogvlm.py:252-262): when kv_k / kv_v are
+     set, the post-rotary K heads and the V heads of every live row are ALSO written to the cache
+     kv_x[b][head][l + *kv_pos][0..127], layout [B, heads, kv_capacity, 128] bf16 (the reference's [B, heads, L, 128]
+     with pre-allocated headroom), where (b, l) = divmod(sorted_to_flat[row], kv_seq_len).  Prefill: kv_seq_len = L,
+     kv_pos = NULL.  Decode step (q_len == 1): kv_seq_len = 1, sorted_to_flat = identity, kv_pos = device counter of
+     the positions already cached -- the append of :258-260 without torch.cat.  Rows with l + *kv_pos >= kv_capacity
+     are dropped.  Requires N == 3 * rope_cols / 2 (the QKV projection). */
+  void* kv_k;
+  void* kv_v;
+  const int32_t* kv_pos;
+  int32_t kv_seq_len;
+  int32_t kv_capacity;
 } vexGemmArgs;
 
 int vex_grouped_gemm(const vexGemmArgs* args, vexStream stream);
@@ -183,8 +196,8 @@ int vex_grouped_gemm(const vexGemmArgs* args, vexStream stream);
  *   (token_to_sorted; NULL = identity) into [rows_cap, heads*128] bf16.
  *   Default implementation: the persistent two-tile tcgen05 kernel (k4_attention_tc3.cu); it draws work items from
  *   one of 1024 device-side counters handed out round-robin per launch and reset by the call itself (stream-ordered;
- *   captured launches keep their counter).  Environment, for A/B measurements: VEX_ATTN_IMPL=tc2 | tc1 (earlier
- *   tcgen05 kernels) | mma (mma.sync baseline, forward only); VEX_ATTN_P=tmem|smem|token (tc2 schedules). */
+ *   captured launches keep their counter).  The kernels it superseded live in csrc/baselines/ and are built into a
+ *   separate libvex_baselines.so for A/B measurements; the product library contains this implementation only. */
 int vex_attention(const void* qkv, const int32_t* cu_seqlens, int B, int max_len_cap, int heads,
                   const int32_t* out_row_map, void* out, float scale, vexStream stream);
 
@@ -200,6 +213,24 @@ int vex_attention_lse(const void* qkv, const int32_t* cu_seqlens, int B, int max
  * out [B, heads*128].  Query scaled in bf16, bf16 scores, fp32 softmax cast to bf16, like the eager reference. */
 int vex_attention_decode(const void* q, int64_t ldq, const void* k, const void* v, const uint8_t* mask, void* out,
                          int B, int heads, int L, float scale, vexStream stream);
+
+/* K4d over a pre-allocated cache: k_cache / v_cache [B, heads, kv_capacity, 128]; *kv_len (device) =
+ * positions cached BEFORE this step, the step attends to positions [0, *kv_len] (the current token's K / V were appended
+ * by the VEX_EPI_ROPE epilogue, see vexGemmArgs.kv_k), clamped to min(kv_capacity, mask_len); mask [B, mask_len] uint8,
+ * rows ld_mask bytes apart.  Nothing is read from the host, so a decode step replays as a CUDA graph while *kv_len
+ * advances (vex_advance_counter). */
+int vex_attention_decode_cache(const void* q, int64_t ldq, const void* k_cache, const void* v_cache,
+                               const uint8_t* mask, int64_t ld_mask, int mask_len, void* out, int B, int heads,
+                               int kv_capacity, const int32_t* kv_len, float scale, vexStream stream);
+
+/* *counter += by, on the stream (the decode graph's own "past length += 1"). */
+int vex_advance_counter(int32_t* counter, int by, vexStream stream);
+
+/* Cache rows of padded prefill positions: k_cache[b, :, l, :] = v_cache[b, :, l, :] = 0 where flat_to_sorted[b*L + l]
+ * < 0 (padding_mask == False) -- the reference's cache holds zeros there (:243); live positions are written by the
+ * VEX_EPI_ROPE epilogue. */
+int vex_kv_clear_padded(void* k_cache, void* v_cache, const int32_t* flat_to_sorted, int B, int L, int heads,
+                        int kv_capacity, vexStream stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Training-step variant (BASELINE config 5): backward of the layer for LoRA fine-tuning.  The reference has no

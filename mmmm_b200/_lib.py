@@ -23,6 +23,7 @@ SYMBOLS = [
     "vex_attention", "vex_attention_decode", "vex_gather_rows", "vex_silu_mul_backward", "vex_rmsnorm_backward",
     "vex_lora_wgrad", "vex_attention_lse", "vex_attention_backward", "vex_dropout_rows", "vex_label_rows", "vex_ce_reduce",
     "vex_attention_blockdiag", "vex_layernorm", "vex_patchify", "vex_maxpool_tokens", "vex_scatter_rows",
+    "vex_attention_decode_cache", "vex_advance_counter", "vex_kv_clear_padded",
 ]
 
 
@@ -43,6 +44,8 @@ class GemmArgs(C.Structure):
         ("ce_labels", C.c_void_p), ("ce_pmax", C.c_void_p), ("ce_psum", C.c_void_p), ("ce_zlabel", C.c_void_p),
         ("ce_lse", C.c_void_p), ("ce_w", C.c_void_p), ("ce_dloss", C.c_void_p),
         ("bias", C.c_void_p), ("act", C.c_int32),
+        ("kv_k", C.c_void_p), ("kv_v", C.c_void_p), ("kv_pos", C.c_void_p),
+        ("kv_seq_len", C.c_int32), ("kv_capacity", C.c_int32),
     ]
 
 
@@ -98,6 +101,9 @@ def lib() -> C.CDLL:
         L.vex_patchify.argtypes = [p, i32, i32, i32, i32, i32, i32, i32, p, i64, p]
         L.vex_maxpool_tokens.argtypes = [p, i64, i32, i32, i32, i32, i32, i32, p, i64, i32, p]
         L.vex_scatter_rows.argtypes = [p, p, p, i32, p, i32, p]
+        L.vex_attention_decode_cache.argtypes = [p, i64, p, p, p, i64, i32, p, i32, i32, i32, p, f32, p]
+        L.vex_advance_counter.argtypes = [p, i32, p]
+        L.vex_kv_clear_padded.argtypes = [p, p, p, i32, i32, i32, i32, p]
         for name in SYMBOLS:
             fn = getattr(L, name)
             if name not in ("vex_error_string",):

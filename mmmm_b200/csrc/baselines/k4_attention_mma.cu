@@ -4,12 +4,12 @@
 // memory_efficient_attention under BlockDiagonalCausalMask -- per sample, token i attends to tokens j <= i of
 // the same sample in token-rank order, scale = d^-0.5, fp32 online softmax, P rounded to bf16 before P.V.
 // This register-accumulator kernel is the correctness baseline and the fallback shape handler; the tcgen05/TMEM
-// kernel in k4_attention_tc.cu is the fast path (VEX_ATTN_IMPL selects, see vex_attention).
+// kernels are the fast path (this file is built into libvex_baselines.so only, see abi_baselines.cu).
 //
 // CTA = 64 query rows x 1 head, 4 warps (16 rows each); K/V blocks of 64 keys double-buffered with cp.async;
 // 16-byte-chunk XOR swizzle in shared memory so ldmatrix is conflict-free.  q/k/v are read in place from the
 // token-order QKV buffer [T, 3, heads, 128]; output rows are scattered through out_row_map.
-#include "common.cuh"
+#include "../common.cuh"
 
 namespace vex {
 

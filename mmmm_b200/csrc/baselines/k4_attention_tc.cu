@@ -21,7 +21,7 @@
 
 #include <cstring>
 
-#include "common.cuh"
+#include "../common.cuh"
 
 namespace vex {
 

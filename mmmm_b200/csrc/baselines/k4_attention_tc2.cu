@@ -34,7 +34,7 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "common.cuh"
+#include "../common.cuh"
 
 #ifdef VEX_ATTN_TRACE
 // timing experiment build (tools/attn_trace.py): cycle stamps of one CTA's softmax warps and MMA issuer

@@ -90,7 +90,32 @@ struct GemmDev {
   const __nv_bfloat16* bias;  // [N] or nullptr: added to the fp32 accumulator before the bf16 rounding
   int act;                    // VEX_ACT_NONE / VEX_ACT_GELU (exact erf form, on the bf16-rounded Linear output)
   int raster_group;           // m-tiles (128 rows) per raster group, even; see raster_group_for()
+  // VEX_EPI_ROPE second output: post-rotary K and V written straight into the KV cache
+  // [B, heads, kv_cap, 128] at position l (+ *kv_pos) of sample b, (b, l) = divmod(sorted_to_flat[row], kv_seq)
+  __nv_bfloat16* kv_k;
+  __nv_bfloat16* kv_v;
+  const int32_t* kv_pos;
+  int kv_seq, kv_cap;
 };
+
+// Row of the KV cache ([B * heads * kv_cap] rows of 128) that sorted row s_row's head slot goes to, for the 128-column
+// panel starting at column colp of the QKV output; -1 = this panel is a query head / the row is dead / out of capacity.
+// `which` (warp-uniform) receives the cache base pointer (nullptr: nothing to write).
+__device__ __forceinline__ int kv_cache_row(const GemmDev& p, int colp, int s_row, bool valid, __nv_bfloat16*& which) {
+  which = nullptr;
+  if (p.kv_k == nullptr) return -1;
+  const int Hh = p.rope_cols >> 1;  // hidden size: q and k columns are the rotated ones
+  if (colp < Hh || colp >= 3 * Hh) return -1;
+  const bool is_v = colp >= 2 * Hh;
+  which = is_v ? p.kv_v : p.kv_k;
+  if (!valid) return -1;
+  const int head = (colp - (is_v ? 2 * Hh : Hh)) >> 7;
+  const int flat = p.sorted_to_flat[s_row];
+  const int b = flat / p.kv_seq;
+  const int l = flat - b * p.kv_seq + (p.kv_pos ? p.kv_pos[0] : 0);
+  if (l < 0 || l >= p.kv_cap) return -1;
+  return (b * (Hh >> 7) + head) * p.kv_cap + l;
+}
 
 template <int BN>
 struct GemmCfg {
@@ -196,15 +221,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, int e, int m, in
   const uint32_t stage_row = stage_base + static_cast<uint32_t>(lane * PITCH);
 
   // coalesced write-out of one staged panel: out[g, col0 + ...] for the 32 rows of this warp
-  auto write_panel = [&](int g_row, int col0, bool add_residual) {
+  auto write_panel = [&](int g_row, int col0, bool add_residual, __nv_bfloat16* kv_base = nullptr, int kv_row = -1) {
 #pragma unroll 4
     for (int it = 0; it < 32 / RPI; ++it) {
       const int rr = it * RPI + lane / LPR;
       const int piece = lane % LPR;
       const int g = __shfl_sync(0xffffffffu, g_row, rr);
+      const int kr = kv_base ? __shfl_sync(0xffffffffu, kv_row, rr) : -1;  // kv_base is warp-uniform
       const int col = col0 + piece * 8;
       if (g >= 0 && col < p.N) {
         uint4 v = ld_shared_v4(stage_base + static_cast<uint32_t>(rr * PITCH + ((piece ^ (rr & 7)) << 4)));
+        if (kr >= 0) *reinterpret_cast<uint4*>(kv_base + static_cast<int64_t>(kr) * 128 + piece * 8) = v;
         const int64_t off = static_cast<int64_t>(g) * p.ldo + col;
         if (add_residual) {
           const uint4 r4 = ld_stream(p.residual + off);
@@ -422,7 +449,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, int e, int m, in
       } else {
         __syncwarp();
       }
-      write_panel(g_row, col0, p.mode == VEX_EPI_RESIDUAL || p.mode == VEX_EPI_DROPOUT_ACC);
+      if (p.mode == VEX_EPI_ROPE && PANEL == 128) {
+        __nv_bfloat16* kv_base;
+        const int kv_row = kv_cache_row(p, col0, s_row, valid, kv_base);
+        write_panel(g_row, col0, false, kv_base, kv_row);
+      } else {
+        write_panel(g_row, col0, p.mode == VEX_EPI_RESIDUAL || p.mode == VEX_EPI_DROPOUT_ACC);
+      }
       __syncwarp();
     }
   }
@@ -533,15 +566,20 @@ __device__ __forceinline__ void epilogue_tile_half(const GemmDev& p, int e, int 
 
   // coalesced write-out of one staged 64-column piece: staged columns [0, 32) go to global columns [colA, colA + 32),
   // staged columns [32, 64) to [colB, colB + 32) (colB = colA + 32 except for the rotary halves)
+  const int panel_col0 = n * BN + half * 128;  // first output column of this warp's 128-column panel
+  __nv_bfloat16* kv_base = nullptr;            // VEX_EPI_ROPE: K / V panels are mirrored into the KV cache
+  int kv_row = -1;
   auto write_piece = [&](int g_row, int colA, int colB, bool add_residual) {
 #pragma unroll 4
     for (int it = 0; it < 8; ++it) {
       const int rr = it * 4 + (lane >> 3);
       const int piece = lane & 7;
       const int g = __shfl_sync(0xffffffffu, g_row, rr);
+      const int kr = kv_base ? __shfl_sync(0xffffffffu, kv_row, rr) : -1;  // kv_base is warp-uniform
       const int col = piece < 4 ? colA + piece * 8 : colB + (piece - 4) * 8;
       if (g >= 0 && col < p.N) {
         uint4 v = ld_shared_v4(stage_base + static_cast<uint32_t>(rr * PITCH + ((piece ^ (rr & 7)) << 4)));
+        if (kr >= 0) *reinterpret_cast<uint4*>(kv_base + static_cast<int64_t>(kr) * 128 + (col - panel_col0)) = v;
         const int64_t off = static_cast<int64_t>(g) * p.ldo + col;
         if (add_residual) {
           const uint4 r4 = ld_stream(p.residual + off);
@@ -568,6 +606,7 @@ __device__ __forceinline__ void epilogue_tile_half(const GemmDev& p, int e, int 
       pos = static_cast<int>(min(max(pz, int64_t(0)), int64_t(p.rope_len - 1)));
     }
   }
+  if (p.mode == VEX_EPI_ROPE) kv_row = kv_cache_row(p, panel_col0, s_row, valid, kv_base);
   uint32_t raw[32];
   float v[32];
 
@@ -1138,53 +1177,10 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1)
 }
 
 // ---------------------------------------------------------------------------------------------
-// host side: tensor maps + launch
+// host side: launch (tensor-map encoding lives in tmap.cu)
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  });
-  return fn;
-}
-
-// 2D bf16 row-major [rows, cols] with row stride ld (elements); box = 64 columns x box_rows, 128B swizzle
-int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return VEX_E_CUDA;
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16 != 0) return VEX_E_INVALID;
-  cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {ld * 2};
-  cuuint32_t box[2] = {64, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    g_last_cuda_error = static_cast<int>(r);
-    return VEX_E_CUDA;
-  }
-  return VEX_OK;
-}
-
-int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
-}
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+int num_sms();
 
 template <int BN, bool TB>
 static int launch_gemm(const GemmTmaps& tm, const GemmDev& dev, cudaStream_t s) {
@@ -1340,6 +1336,16 @@ extern "C" int vex_grouped_gemm(const vexGemmArgs* a, vexStream stream) {
   dev.ce_tiles = 2 * ceil_div(a->N, 256);
   dev.bias = static_cast<const __nv_bfloat16*>(a->bias);
   dev.act = a->act;
+  if (a->kv_k || a->kv_v) {
+    if (a->mode != VEX_EPI_ROPE || !a->kv_k || !a->kv_v || a->kv_seq_len <= 0 || a->kv_capacity <= 0) return VEX_E_INVALID;
+    if (a->N != 3 * (a->rope_cols / 2)) return VEX_E_UNSUPPORTED;  // the QKV projection: [q | k | v], q and k rotated
+    if ((reinterpret_cast<uintptr_t>(a->kv_k) | reinterpret_cast<uintptr_t>(a->kv_v)) & 15) return VEX_E_INVALID;
+    dev.kv_k = static_cast<__nv_bfloat16*>(a->kv_k);
+    dev.kv_v = static_cast<__nv_bfloat16*>(a->kv_v);
+    dev.kv_pos = a->kv_pos;
+    dev.kv_seq = a->kv_seq_len;
+    dev.kv_cap = a->kv_capacity;
+  }
   if (a->mode == VEX_EPI_DROPOUT_ACC) {
     dev.drop_thresh16 = static_cast<uint32_t>(a->dropout_p * 65536.0f + 0.5f);
     dev.drop_seed_lo = static_cast<uint32_t>(a->dropout_seed);

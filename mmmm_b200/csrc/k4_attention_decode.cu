@@ -32,19 +32,25 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* red) {
   return v;
 }
 
+// `kv_len` (device, may be null): number of cache positions already filled BEFORE this step; the step attends to
+// *kv_len + 1 positions (the current token's K / V were appended by the QKV epilogue).  Null = attend to all L.
+// Cache rows of one (sample, head) are `cap` positions apart (cap >= L: pre-allocated headroom); the mask row
+// stride is ld_mask.
 __global__ void __launch_bounds__(DEC_THREADS)
     k4_attention_decode(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k,
-                        const __nv_bfloat16* __restrict__ v, const uint8_t* __restrict__ mask,
-                        __nv_bfloat16* __restrict__ out, int heads, int L, float scale) {
+                        const __nv_bfloat16* __restrict__ v, const uint8_t* __restrict__ mask, int64_t ld_mask,
+                        __nv_bfloat16* __restrict__ out, int heads, int L_host, int cap,
+                        const int32_t* __restrict__ kv_len, float scale) {
   extern __shared__ float sc[];  // L scores, then probabilities
   __shared__ float qs[128];
   __shared__ float red[4];
   __shared__ float osum[4][128];
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int L = kv_len ? min(max(kv_len[0] + 1, 1), L_host) : L_host;
   qs[tid] = bf16r(__bfloat162float(q[static_cast<int64_t>(b) * ldq + h * 128 + tid]) * scale);
   __syncthreads();
-  const int64_t base = (static_cast<int64_t>(b) * heads + h) * L;
-  const uint8_t* mrow = mask + static_cast<int64_t>(b) * L;
+  const int64_t base = (static_cast<int64_t>(b) * heads + h) * cap;
+  const uint8_t* mrow = mask + static_cast<int64_t>(b) * ld_mask;
 
   float mx = -INFINITY;
   for (int l = tid; l < L; l += DEC_THREADS) {
@@ -99,16 +105,52 @@ __global__ void __launch_bounds__(DEC_THREADS)
   out[static_cast<int64_t>(b) * heads * 128 + h * 128 + tid] = __float2bfloat16_rn(o);
 }
 
+__global__ void k4_advance_counter(int32_t* p, int by) { if (threadIdx.x == 0) p[0] += by; }
+
+// scores live in dynamic shared memory: opt in beyond the 48 KB default once, bound by the 227 KB per-CTA limit
+constexpr int DEC_MAX_L = (200 * 1024) / 4;
+
+static int launch_decode(const void* q, int64_t ldq, const void* k, const void* v, const uint8_t* mask,
+                         int64_t ld_mask, void* out, int B, int heads, int L, int cap, const int32_t* kv_len,
+                         float scale, cudaStream_t s) {
+  if (!q || !k || !v || !mask || !out || B <= 0 || heads <= 0 || L <= 0 || cap < L) return VEX_E_INVALID;
+  if (B > 65535 || L > DEC_MAX_L) return VEX_E_UNSUPPORTED;
+  static bool configured = false;
+  if (!configured) {
+    VEX_CUDA_TRY(cudaFuncSetAttribute(k4_attention_decode, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      DEC_MAX_L * 4));
+    configured = true;
+  }
+  dim3 grid(heads, B);
+  k4_attention_decode<<<grid, DEC_THREADS, L * sizeof(float), s>>>(
+      static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k),
+      static_cast<const __nv_bfloat16*>(v), mask, ld_mask, static_cast<__nv_bfloat16*>(out), heads, L, cap, kv_len,
+      scale);
+  VEX_LAUNCH_CHECK();
+  return VEX_OK;
+}
+
 }  // namespace vex
 
 extern "C" int vex_attention_decode(const void* q, int64_t ldq, const void* k, const void* v, const uint8_t* mask,
                                     void* out, int B, int heads, int L, float scale, vexStream stream) {
-  if (!q || !k || !v || !mask || !out || B <= 0 || heads <= 0 || L <= 0) return VEX_E_INVALID;
-  if (B > 65535 || L > 48 * 1024 / 4) return VEX_E_UNSUPPORTED;  // scores live in (default-limit) shared memory
-  dim3 grid(heads, B);
-  vex::k4_attention_decode<<<grid, vex::DEC_THREADS, L * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k),
-      static_cast<const __nv_bfloat16*>(v), mask, static_cast<__nv_bfloat16*>(out), heads, L, scale);
+  return vex::launch_decode(q, ldq, k, v, mask, L, out, B, heads, L, L, nullptr, scale,
+                            static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vex_attention_decode_cache(const void* q, int64_t ldq, const void* k_cache, const void* v_cache,
+                                          const uint8_t* mask, int64_t ld_mask, int mask_len, void* out, int B,
+                                          int heads, int kv_capacity, const int32_t* kv_len, float scale,
+                                          vexStream stream) {
+  if (!kv_len || mask_len <= 0 || ld_mask < mask_len || kv_capacity <= 0) return VEX_E_INVALID;
+  const int l_max = mask_len < kv_capacity ? mask_len : kv_capacity;  // host bound on the positions attended to
+  return vex::launch_decode(q, ldq, k_cache, v_cache, mask, ld_mask, out, B, heads, l_max, kv_capacity, kv_len, scale,
+                            static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vex_advance_counter(int32_t* counter, int by, vexStream stream) {
+  if (!counter) return VEX_E_INVALID;
+  vex::k4_advance_counter<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(counter, by);
   VEX_LAUNCH_CHECK();
   return VEX_OK;
 }

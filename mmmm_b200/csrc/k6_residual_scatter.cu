@@ -2,6 +2,8 @@
 // (3 * H * 2 bytes per row), plus the pass-through of padded rows.
 // Restates out[mask] = expert(x[mask]) followed by residual + out (modeling_cogvlm.py:278-279 + :321,
 // :96-97 + :330): one bf16 rounding of the sum, like the eager add of two bf16 tensors.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace vex {
@@ -47,7 +49,40 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// KV cache rows of padded positions: k[b, :, l, :] = v[b, :, l, :] = 0 where padding_mask[b, l] == False (the
+// reference multiplies the projected q / k / v by the mask, modeling_cogvlm.py:243, so its cache holds zeros there).
+// One warp per (flat position, head); valid positions are written by the QKV epilogue and skipped here.
+__global__ void __launch_bounds__(256)
+    k6_kv_clear_padded(__nv_bfloat16* __restrict__ k, __nv_bfloat16* __restrict__ v,
+                       const int32_t* __restrict__ flat_to_sorted, int B, int L, int heads, int cap) {
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  const int lane = lane_id();
+  const int64_t n = static_cast<int64_t>(B) * L * heads;
+  for (int64_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps_total) {
+    const int f = static_cast<int>(i / heads), h = static_cast<int>(i - static_cast<int64_t>(f) * heads);
+    if (flat_to_sorted[f] >= 0) continue;
+    const int b = f / L, l = f - b * L;
+    const int64_t row = (static_cast<int64_t>(b) * heads + h) * cap + l;
+    if (lane < 16) {
+      reinterpret_cast<uint4*>(k + row * 128)[lane] = make_uint4(0, 0, 0, 0);
+      reinterpret_cast<uint4*>(v + row * 128)[lane] = make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+
 }  // namespace vex
+
+extern "C" int vex_kv_clear_padded(void* k_cache, void* v_cache, const int32_t* flat_to_sorted, int B, int L, int heads,
+                                   int kv_capacity, vexStream stream) {
+  if (!k_cache || !v_cache || !flat_to_sorted || B <= 0 || L <= 0 || heads <= 0 || kv_capacity < L) return VEX_E_INVALID;
+  const int64_t n = static_cast<int64_t>(B) * L * heads;
+  const int grid = static_cast<int>(std::min<int64_t>((n + 7) / 8, 148 * 8));
+  vex::k6_kv_clear_padded<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(k_cache), static_cast<__nv_bfloat16*>(v_cache), flat_to_sorted, B, L, heads,
+      kv_capacity);
+  VEX_LAUNCH_CHECK();
+  return VEX_OK;
+}
 
 extern "C" int vex_residual_scatter(const void* y, const void* residual, const int32_t* row_dst,
                                     const int32_t* n_rows, void* out, int rows_cap, int H, vexStream stream) {

@@ -16,11 +16,16 @@ from .plan import GLOBAL_PLAN_CACHE
 
 
 class GraphedPrefill:
+    """``sorted_stream`` (default: on for a stack of layers, off for a single layer): run the stack through
+    ``decoder_stack_forward`` -- residual stream in expert-sorted order across all layers -- instead
+    of the per-layer module calls in the flat [B, L, H] layout."""
+
     def __init__(self, layers: Union[nn.Module, Sequence[nn.Module]], hidden_states: torch.Tensor,
                  token_type_ids: torch.Tensor, position_ids: torch.Tensor, padding_mask: torch.Tensor,
-                 final_norm: nn.Module = None, warmup: int = 2):
+                 final_norm: nn.Module = None, warmup: int = 2, sorted_stream: bool = None):
         self.layers = list(layers) if isinstance(layers, (list, tuple, nn.ModuleList)) else [layers]
         self.final_norm = final_norm
+        self.sorted_stream = (len(self.layers) > 1) if sorted_stream is None else bool(sorted_stream)
         # static input buffers: refill them (copy_) and call replay()
         self.hidden_states = hidden_states.clone()
         self.token_type_ids = token_type_ids.clone()
@@ -39,6 +44,11 @@ class GraphedPrefill:
         GLOBAL_PLAN_CACHE.clear()
 
     def _forward(self) -> torch.Tensor:
+        if self.sorted_stream:
+            from .modeling_cogvlm import decoder_stack_forward
+            plan = GLOBAL_PLAN_CACHE.get(self.token_type_ids, self.padding_mask)
+            return decoder_stack_forward(self.layers, self.final_norm, self.hidden_states, plan,
+                                         self.position_ids.long().contiguous())[0]
         h = self.hidden_states
         for layer in self.layers:
             h = layer(h, token_type_ids=self.token_type_ids, position_ids=self.position_ids,
@@ -69,12 +79,13 @@ class PipelinedHostPrefill:
     ``result(slot)`` blocks until that slot's output has landed in host memory."""
 
     def __init__(self, layers, hidden_states, token_type_ids, position_ids, padding_mask, final_norm=None,
-                 depth: int = 2, device=None):
+                 depth: int = 2, device=None, sorted_stream: bool = None):
         dev = torch.device(device) if device is not None else (
             hidden_states.device if hidden_states.is_cuda else torch.device("cuda", torch.cuda.current_device()))
         on_dev = lambda t: t.to(dev, non_blocking=False)
         ex = tuple(map(on_dev, (hidden_states, token_type_ids, position_ids, padding_mask)))
-        self.slots = [GraphedPrefill(layers, *ex, final_norm=final_norm) for _ in range(depth)]
+        self.slots = [GraphedPrefill(layers, *ex, final_norm=final_norm, sorted_stream=sorted_stream)
+                      for _ in range(depth)]
         self.out_host = [torch.empty(ex[0].shape, dtype=ex[0].dtype).pin_memory() for _ in range(depth)]
         self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         mk = lambda: [torch.cuda.Event() for _ in range(depth)]

@@ -216,20 +216,33 @@ _cast_cache: dict = {}
 
 
 def _bf16(t: torch.Tensor) -> torch.Tensor:
-    """Adapter / norm tensors may be fp32 (PEFT ``autocast_adapter_dtype``); the kernels want bf16.  Cached on
-    (storage, version) so a frozen tensor is converted once and an optimiser step invalidates the copy."""
-    t = t.detach()
+    """Adapter / norm tensors may be fp32 (PEFT ``autocast_adapter_dtype``); the kernels want bf16.  The bf16 copy is
+    cached per SOURCE tensor object (the Parameter the wrapper holds -- its identity is stable across calls, unlike
+    the result of ``detach()``) and revalidated on (storage, version, dtype, shape), so a frozen tensor is converted
+    once and an optimiser step (in-place update -> version bump) refreshes the copy."""
     if t.dtype == torch.bfloat16 and t.is_contiguous():
-        return t
-    key = (t.data_ptr(), t._version, tuple(t.shape), t.dtype)
+        return t.detach()
+    sig = (t.data_ptr(), None if t.is_inference() else t._version, t.dtype, tuple(t.shape))
     hit = _cast_cache.get(id(t))
-    if hit is not None and hit[0] == key:
-        return hit[1]
-    c = t.to(torch.bfloat16).contiguous()
-    if len(_cast_cache) > 512:
+    if hit is not None and hit[0] is t and hit[1] == sig:
+        return hit[2]
+    c = t.detach().to(torch.bfloat16).contiguous()
+    if len(_cast_cache) > 4096:  # 32 layers x 20 adapter tensors = 640 live entries; stale ones are dropped wholesale
         _cast_cache.clear()
-    _cast_cache[id(t)] = (key, c, t)
+    _cast_cache[id(t)] = (t, sig, c)  # holding `t` keeps id(t) from being recycled by another tensor
     return c
+
+
+def _base_weight(t: torch.Tensor) -> torch.Tensor:
+    """A frozen base ``nn.Linear`` weight as the TMA operand: must already be contiguous bf16 (bf16-true,
+    mmmm.py:468-492).  An fp32 base weight is rejected instead of being converted on every call (one 4096 x 11008
+    matrix is 90 MB per copy)."""
+    if t.dtype != torch.bfloat16:
+        raise TypeError(f"base Linear weights must be bfloat16 (bf16-true model, mmmm.py:468-492), got {t.dtype}; "
+                        f"cast the model once with .to(torch.bfloat16)")
+    if not t.is_contiguous():
+        raise ValueError("base Linear weights must be contiguous [out_features, in_features]")
+    return t.detach()
 
 
 def _fuse_default() -> bool:
@@ -287,18 +300,36 @@ def _lora_t(x_sorted: torch.Tensor, specs: Tuple[LinearSpec, LinearSpec], counts
 def visual_expert_layer_forward(layer: "CogVLMDecoderLayer", hidden_states: torch.Tensor, plan: RoutingPlan,
                                 position_ids: torch.Tensor, *, use_cache: bool = False,
                                 fuse_epilogue: Optional[bool] = None, keep: Optional[dict] = None,
-                                dropout_seed: Optional[int] = None):
-    """The whole layer on the device; returns (out [B, L, H], present_kv or None).  ``keep`` (training recompute):
-    a dict that receives the intermediates the backward needs (gate/up are then materialised separately, the
-    attention also writes its log-sum-exp, and the call returns (None, None) right before the down projection)."""
+                                dropout_seed: Optional[int] = None, sorted_stream: bool = False,
+                                kv_capacity: Optional[int] = None, kv_out: Optional[tuple] = None):
+    """The whole layer on the device; returns (out, present_kv or None).
+
+    ``sorted_stream=False`` (the drop-in module call): ``hidden_states`` / ``out`` are [B, L, H] in the reference's
+    flat layout; rows are gathered into expert-sorted order by K2 and scattered back by the residual epilogues.
+    ``sorted_stream=True`` (used by ``decoder_stack_forward``): ``hidden_states`` is the residual
+    stream ALREADY in expert-sorted order, [B*L, H]; the layer updates it IN PLACE (h += attn(norm(h)); h +=
+    mlp(norm(h))) with identity row maps -- no gather, no scatter, no padded-row copy, no second activation buffer --
+    and returns the same tensor.
+
+    ``keep`` (training recompute, flat layout only): a dict that receives the intermediates the backward needs
+    (gate/up are then materialised separately, the attention also writes its log-sum-exp, and the call returns
+    (None, None) right before the down projection).
+    ``use_cache``: post-rotary K and V are written by the QKV epilogue straight into a [B, heads, kv_capacity, 128]
+    cache pair (zeros at padded positions, :243, :262) -- ``kv_out`` = (k, v) if the caller owns the cache, otherwise
+    allocated here with ``KV_HEADROOM`` spare positions; ``present`` = views of the first L positions."""
     fuse = _fuse_default() if fuse_epilogue is None else fuse_epilogue
     attn, mlp = layer.self_attn, layer.mlp
-    B, L, H = hidden_states.shape
+    B, L = plan.batch, plan.seq_len
+    H = hidden_states.shape[-1]
     cap, heads = B * L, attn.num_heads
     I = mlp.vision_mlp.intermediate_size
     dev = hidden_states.device
     hf = hidden_states.view(cap, H)
     counts, s2f = plan.counts, plan.sorted_to_flat
+    if sorted_stream and (keep is not None or not fuse):
+        raise NotImplementedError("the sorted residual stream is the fused inference path (no keep / unfused mode)")
+    # row maps of the residual stream: flat layout goes through sorted_to_flat, the sorted stream is the identity
+    stream_map = None if sorted_stream else s2f
     new = lambda *shape: torch.empty(*shape, dtype=torch.bfloat16, device=dev)
 
     ln1, ln2 = resolve_norm(layer.input_layernorm), resolve_norm(layer.post_attention_layernorm)
@@ -307,7 +338,7 @@ def visual_expert_layer_forward(layer: "CogVLMDecoderLayer", hidden_states: torc
     gate_s = (resolve_linear(mlp.vision_mlp.gate_proj), resolve_linear(mlp.language_mlp.gate_proj))
     up_s = (resolve_linear(mlp.vision_mlp.up_proj), resolve_linear(mlp.language_mlp.up_proj))
     down_s = (resolve_linear(mlp.vision_mlp.down_proj), resolve_linear(mlp.language_mlp.down_proj))
-    W = lambda pair: [_bf16(pair[0].weight), None, _bf16(pair[1].weight), None]
+    W = lambda pair: [_base_weight(pair[0].weight), None, _base_weight(pair[1].weight), None]
     if dropout_seed is None and any(sp[0].dropout > 0 for sp in (qkv_s, dense_s, gate_s, up_s, down_s)):
         dropout_seed = next_dropout_seed()  # wrappers in training mode: nn.Dropout would be active
     lt = lambda x, sp, k, nm: _lora_t(x, sp, counts, n_valid=plan.n_valid, seed=dropout_seed, stream=k, keep=keep,
@@ -315,39 +346,57 @@ def visual_expert_layer_forward(layer: "CogVLMDecoderLayer", hidden_states: torc
 
     # ---- attention block ----
     xn = new(cap, H)
-    ops.rmsnorm_gather(hf, ln1.weight.detach(), ln1.variance_epsilon, s2f, plan.n_valid, xn)
+    ops.rmsnorm_gather(hf, ln1.weight.detach(), ln1.variance_epsilon, stream_map, plan.n_valid, xn)
     cos, sin = attn.rotary_emb.tables(max(L, attn.max_position_embeddings), dev, torch.bfloat16)
     pos_flat = position_ids.reshape(-1)
+    _debug_check_positions(pos_flat, cos.shape[0])
     qkv = new(cap, 3 * H)  # token order: row t = [q(heads*128) | k | v], q and k rotated
     t, r, lb = lt(xn, qkv_s, 0, "qkv")
     if keep is not None:
         keep.update(xn1=xn, t_qkv=t, specs=dict(qkv=qkv_s, dense=dense_s, gate=gate_s, up=up_s, down=down_s),
                     ln1=ln1, ln2=ln2, cos=cos, sin=sin, dropout_seed=dropout_seed)
         xn = new(cap, H)  # the second norm gets its own buffer (xn1 is needed by the backward)
-    ops.grouped_gemm_fused(keep["xn1"] if keep is not None else xn, W(qkv_s), qkv, counts, ops.EPI_ROPE, plan.sorted_to_token, None, [t, None],
-                           [lb[0], None, lb[1], None], r, [cos, sin, pos_flat, s2f], 2 * H, False, 1.0)
+    present, kv = None, None
+    if use_cache:
+        # a9: K (post-rotary) and V leave the QKV epilogue in the reference's cache layout [B, heads, L_cap, 128]; padded
+        # positions are zeroed by one small kernel (the reference multiplies by the mask, :243)
+        if kv_out is not None:
+            kv = kv_out
+        else:
+            kcap = max(int(kv_capacity or 0), L) if kv_capacity else L + KV_HEADROOM
+            kv = torch.empty(2, B, heads, kcap, HEAD_DIM, dtype=torch.bfloat16, device=dev)
+        ops.kv_clear_padded(kv[0], kv[1], plan.flat_to_sorted, B, L)
+        present = (kv[0][:, :, :L], kv[1][:, :, :L])
+    ops.grouped_gemm_fused(keep["xn1"] if keep is not None else xn, W(qkv_s), qkv, counts, ops.EPI_ROPE,
+                           plan.sorted_to_token, None, [t, None], [lb[0], None, lb[1], None], r,
+                           [cos, sin, pos_flat, s2f], 2 * H, False, 1.0,
+                           None if kv is None else kv[0], None if kv is None else kv[1], L, None)
     ctx = new(cap, H)      # expert-sorted order again: the A operand of the dense GEMM
     if keep is not None:   # training recompute: the backward kernels need the log-sum-exp
         keep["lse"] = torch.empty(heads, cap, dtype=torch.float32, device=dev)
         ops.attention_train(qkv, plan.cu_seqlens, B, L, heads, plan.token_to_sorted, ctx, HEAD_DIM ** -0.5, keep["lse"])
     else:
         ops.attention(qkv, plan.cu_seqlens, B, L, heads, plan.token_to_sorted, ctx, HEAD_DIM ** -0.5)
-    h1 = new(B, L, H)
-    ops.copy_padded_rows(hf, plan.flat_to_sorted, h1.view(cap, H))
+    if sorted_stream:
+        h1 = hidden_states          # in place: h[r] += dense(ctx)[r]
+    else:
+        h1 = new(B, L, H)
+        ops.copy_padded_rows(hf, plan.flat_to_sorted, h1.view(cap, H))
+    h1f = h1.view(cap, H)
     t, r, lb = lt(ctx, dense_s, 1, "dense")
     if keep is not None:
         keep.update(qkv=qkv, ctx=ctx, t_dense=t)
     if fuse:
-        ops.grouped_gemm_fused(ctx, W(dense_s), h1.view(cap, H), counts, ops.EPI_RESIDUAL, s2f, hf, [t, None],
-                               [lb[0], None, lb[1], None], r, [], 0, False, 1.0)
+        ops.grouped_gemm_fused(ctx, W(dense_s), h1f, counts, ops.EPI_RESIDUAL, stream_map,
+                               None if sorted_stream else hf, [t, None], [lb[0], None, lb[1], None], r, [], 0, False, 1.0)
     else:
         y = new(cap, H)
         ops.grouped_gemm_fused(ctx, W(dense_s), y, counts, ops.EPI_PLAIN, None, None, [t, None],
                                [lb[0], None, lb[1], None], r, [], 0, False, 1.0)
-        ops.residual_scatter(y, hf, s2f, plan.n_valid, h1.view(cap, H))
+        ops.residual_scatter(y, hf, s2f, plan.n_valid, h1f)
 
     # ---- MLP block ----
-    ops.rmsnorm_gather(h1.view(cap, H), ln2.weight.detach(), ln2.variance_epsilon, s2f, plan.n_valid, xn)
+    ops.rmsnorm_gather(h1f, ln2.weight.detach(), ln2.variance_epsilon, stream_map, plan.n_valid, xn)
     act = new(cap, I)
     tg, rg, lbg = lt(xn, gate_s, 2, "gate")
     tu, ru, lbu = lt(xn, up_s, 3, "up")
@@ -356,7 +405,8 @@ def visual_expert_layer_forward(layer: "CogVLMDecoderLayer", hidden_states: torc
     if keep is not None:
         keep.update(xn2=xn, t_gate=tg, t_up=tu)
     if fuse and keep is None:
-        w4 = [_bf16(gate_s[0].weight), _bf16(up_s[0].weight), _bf16(gate_s[1].weight), _bf16(up_s[1].weight)]
+        w4 = [_base_weight(gate_s[0].weight), _base_weight(up_s[0].weight), _base_weight(gate_s[1].weight),
+              _base_weight(up_s[1].weight)]
         ops.grouped_gemm_fused(xn, w4, act, counts, ops.EPI_SWIGLU, None, None, [tg, tu],
                                [lbg[0], lbu[0], lbg[1], lbu[1]], rg, [], 0, False, 1.0)
     else:
@@ -377,11 +427,11 @@ def visual_expert_layer_forward(layer: "CogVLMDecoderLayer", hidden_states: torc
         # down projection writes a fresh buffer instead of accumulating in place
         out = new(B, L, H)
         ops.copy_padded_rows(hf, plan.flat_to_sorted, out.view(cap, H))
-        ops.grouped_gemm_fused(act, W(down_s), out.view(cap, H), counts, ops.EPI_RESIDUAL, s2f, h1.view(cap, H),
+        ops.grouped_gemm_fused(act, W(down_s), out.view(cap, H), counts, ops.EPI_RESIDUAL, s2f, h1f,
                                [t, None], [lb[0], None, lb[1], None], r, [], 0, False, 1.0)
         return out, None
-    if fuse:  # in place: h1[row] += down(act)[row]; padded rows of h1 already hold the input
-        ops.grouped_gemm_fused(act, W(down_s), h1.view(cap, H), counts, ops.EPI_RESIDUAL, s2f, None, [t, None],
+    if fuse:  # in place: h1[row] += down(act)[row]; (flat layout) padded rows of h1 already hold the input
+        ops.grouped_gemm_fused(act, W(down_s), h1f, counts, ops.EPI_RESIDUAL, stream_map, None, [t, None],
                                [lb[0], None, lb[1], None], r, [], 0, False, 1.0)
         out = h1
     else:
@@ -389,17 +439,53 @@ def visual_expert_layer_forward(layer: "CogVLMDecoderLayer", hidden_states: torc
         ops.grouped_gemm_fused(act, W(down_s), y, counts, ops.EPI_PLAIN, None, None, [t, None],
                                [lb[0], None, lb[1], None], r, [], 0, False, 1.0)
         out = h1.clone()
-        ops.residual_scatter(y, h1.view(cap, H), s2f, plan.n_valid, out.view(cap, H))
-
-    present = None
-    if use_cache:  # post-rotary k and v as [B, heads, L, 128], zeros at padded positions (:243, :262)
-        f2s = plan.flat_to_sorted.long()
-        valid = f2s >= 0
-        tok = plan.sorted_to_token.long()[f2s.clamp_min(0)]
-        kv = qkv.view(cap, 3, heads, HEAD_DIM)[tok, 1:] * valid[:, None, None, None]
-        kv = kv.view(B, L, 2, heads, HEAD_DIM).permute(2, 0, 3, 1, 4)
-        present = (kv[0], kv[1])
+        ops.residual_scatter(y, h1f, s2f, plan.n_valid, out.view(cap, H))
     return out, present
+
+
+def decoder_stack_forward(layers, final_norm: Optional[nn.Module], inputs_embeds: torch.Tensor, plan: RoutingPlan,
+                          position_ids: torch.Tensor, *, use_cache: bool = False, kv_capacity: Optional[int] = None,
+                          kv_out=None):
+    """``CogVLMModel.llm_forward``'s layer loop + final norm (modeling_cogvlm.py:547-573) with the residual stream kept
+    in expert-sorted order across ALL layers (routing is layer-invariant): ONE gather at entry, per
+    layer two in-place residual GEMM epilogues on the sorted stream, ONE scatter at exit fused into the final masked
+    RMSNorm (``_mask_set(h, pm, norm(h[pm]))``).  Rows with ``padding_mask == False`` never enter the stream; they come
+    out as the input embeddings (the reference leaves them at whatever the masked assignments skipped).
+    Returns (last_hidden_state [B, L, H], tuple of per-layer (k, v) or None)."""
+    B, L, H = inputs_embeds.shape
+    cap = B * L
+    x = inputs_embeds.view(cap, H)
+    stream = torch.empty(cap, H, dtype=inputs_embeds.dtype, device=inputs_embeds.device)
+    ops.gather_rows(x, plan.sorted_to_flat, plan.n_valid, stream)
+    cache = () if use_cache else None
+    for i, layer in enumerate(layers):
+        _, present = visual_expert_layer_forward(layer, stream, plan, position_ids, use_cache=use_cache,
+                                                 sorted_stream=True, kv_capacity=kv_capacity,
+                                                 kv_out=None if kv_out is None else kv_out[i])
+        if use_cache:
+            cache += (present,)
+    out = torch.empty_like(inputs_embeds)
+    of = out.view(cap, H)
+    ops.copy_padded_rows(x, plan.flat_to_sorted, of)
+    if final_norm is not None:
+        mod = resolve_norm(final_norm)
+        ops.rmsnorm_gather(stream, mod.weight.detach(), mod.variance_epsilon, None, plan.n_valid, of,
+                           plan.sorted_to_flat)
+    else:
+        ops.scatter_rows(stream, None, plan.sorted_to_flat, of)
+    return out, cache
+
+
+def _debug_check_positions(position_ids: torch.Tensor, table_len: int) -> None:
+    """The rotary tables are sized from a host-known bound, max(L, max_position_embeddings, largest length seen), where
+    the reference grows them to ``position_ids.max() + 1`` with a device->host sync (:255, :174); the kernels clamp
+    positions into the table.  Real VividMed position ids never exceed the sequence length (data/utils.py:111-124),
+    so the bound holds by construction; VEX_DEBUG_POSITIONS=1 verifies it (one host sync per call)."""
+    if os.environ.get("VEX_DEBUG_POSITIONS", "0") == "1" and not torch.cuda.is_current_stream_capturing():
+        hi = int(position_ids.max())
+        if hi >= table_len or int(position_ids.min()) < 0:
+            raise ValueError(f"position_ids reach {hi}, outside the rotary table of {table_len} rows: raise "
+                             f"config.max_position_embeddings (the kernels clamp instead of growing the table)")
 
 
 _decode_consts: dict = {}
@@ -425,33 +511,29 @@ def _lora_t_single(x: torch.Tensor, spec: LinearSpec, counts: torch.Tensor):
     return t, spec.r, _bf16(spec.lora_B)
 
 
-def visual_expert_layer_decode(layer: "CogVLMDecoderLayer", hidden_states: torch.Tensor, position_ids: torch.Tensor,
-                               padding_mask: torch.Tensor, past_key_value, use_cache: bool = True):
-    """One generation step (q_len == 1 with a KV cache): the reference's L == 1 rules -- every token goes to the
-    LANGUAGE expert regardless of padding (get_expert_mask :67), plain RMSNorm on every row (:308-309, :327-328),
-    cache concat on dim 2 (:258-260) and the generation branch of attention_fn (:129-141)."""
+def decode_core(layer: "CogVLMDecoderLayer", hf: torch.Tensor, position_ids: torch.Tensor, k_cache: torch.Tensor,
+                v_cache: torch.Tensor, mask: torch.Tensor, kv_pos: torch.Tensor) -> torch.Tensor:
+    """One generation step of one layer against a PRE-ALLOCATED cache: ``hf`` [B, H]; ``k_cache`` / ``v_cache``
+    [B, heads, capacity, 128]; ``kv_pos`` int32 [1] on the device = positions already cached; ``mask`` bool
+    [B, >= kv_pos + 1].  The reference's L == 1 rules: every token goes to the LANGUAGE expert regardless of padding
+    (get_expert_mask :67), plain RMSNorm on every row (:308-309, :327-328), the new K / V are appended at position
+    kv_pos (the ``torch.cat`` of :258-260, done in place by the QKV epilogue) and the generation branch of
+    attention_fn (:129-141) runs over positions [0, kv_pos].  No host synchronisation, nothing read from the host:
+    the step replays as a CUDA graph while ``kv_pos`` advances on the device.  Returns the layer output [B, H]."""
     attn, mlp = layer.self_attn, layer.mlp
-    B, L, H = hidden_states.shape
-    heads = attn.num_heads
+    B, H = hf.shape
     I = mlp.language_mlp.intermediate_size
-    dev = hidden_states.device
-    past_k, past_v = past_key_value
-    if past_k.shape[0] != B or past_k.shape[1] != heads or past_k.shape[3] != HEAD_DIM:
-        raise ValueError(f"past_key_value must be [B, {heads}, L_past, {HEAD_DIM}]")
-    Lkv = past_k.shape[2] + 1
-    if padding_mask.shape != (B, Lkv):
-        raise ValueError(f"padding_mask must cover past + current positions: expected {(B, Lkv)}")
+    dev = hf.device
     counts, ident = _decode_constants(B, dev)
     n_rows = counts[2:3]
     new = lambda *shape: torch.empty(*shape, dtype=torch.bfloat16, device=dev)
-    hf = hidden_states.view(B, H)
     ln1, ln2 = resolve_norm(layer.input_layernorm), resolve_norm(layer.post_attention_layernorm)
     qkv_s = resolve_linear(attn.language_expert_query_key_value)
     dense_s = resolve_linear(attn.language_expert_dense)
     gate_s, up_s = resolve_linear(mlp.language_mlp.gate_proj), resolve_linear(mlp.language_mlp.up_proj)
     down_s = resolve_linear(mlp.language_mlp.down_proj)
 
-    def gemm(a, w, out, mode, spec_pair, residual=None, rope=(), rope_cols=0):
+    def gemm(a, w, out, mode, spec_pair, residual=None, rope=(), rope_cols=0, kv=(None, None, 0, None)):
         t, r, lb = [None, None], 0, [None] * 4
         for h, sp in enumerate(spec_pair):
             th, rh, bh = _lora_t_single(a, sp, counts)
@@ -459,28 +541,90 @@ def visual_expert_layer_decode(layer: "CogVLMDecoderLayer", hidden_states: torch
                 t[h], r, lb[h] = th, rh, bh
         if len(spec_pair) == 2 and (t[0] is None) != (t[1] is None):
             raise NotImplementedError("gate_proj and up_proj adapters must come in pairs")
-        ops.grouped_gemm_fused(a, w, out, counts, mode, None, residual, t, lb, r, list(rope), rope_cols, True, 1.0)
+        ops.grouped_gemm_fused(a, w, out, counts, mode, None, residual, t, lb, r, list(rope), rope_cols, True, 1.0, *kv)
 
     xn = new(B, H)
     ops.rmsnorm_gather(hf, ln1.weight.detach(), ln1.variance_epsilon, None, n_rows, xn)
-    max_pos = max(Lkv, attn.max_position_embeddings)
+    max_pos = max(k_cache.shape[2], attn.max_position_embeddings)
     cos, sin = attn.rotary_emb.tables(max_pos, dev, torch.bfloat16)
+    pos_flat = position_ids.reshape(-1)
+    _debug_check_positions(pos_flat, cos.shape[0])
     qkv = new(B, 3 * H)
-    gemm(xn, [_bf16(qkv_s.weight)], qkv, ops.EPI_ROPE, [qkv_s],
-         rope=(cos, sin, position_ids.reshape(-1), ident), rope_cols=2 * H)
-    k_new = qkv[:, H:2 * H].reshape(B, heads, 1, HEAD_DIM)
-    v_new = qkv[:, 2 * H:].reshape(B, heads, 1, HEAD_DIM)
-    k = torch.cat([past_k, k_new], dim=2)   # :259-260 (the tuple-cache API reallocates every step)
-    v = torch.cat([past_v, v_new], dim=2)
+    gemm(xn, [_base_weight(qkv_s.weight)], qkv, ops.EPI_ROPE, [qkv_s], rope=(cos, sin, pos_flat, ident),
+         rope_cols=2 * H, kv=(k_cache, v_cache, 1, kv_pos))
     ctx = new(B, H)
-    ops.attention_decode(qkv[:, :H], k, v, padding_mask, ctx, HEAD_DIM ** -0.5)
+    ops.attention_decode_cache(qkv[:, :H], k_cache, v_cache, mask, kv_pos, ctx, HEAD_DIM ** -0.5)
     h1 = new(B, H)
-    gemm(ctx, [_bf16(dense_s.weight)], h1, ops.EPI_RESIDUAL, [dense_s], residual=hf)
+    gemm(ctx, [_base_weight(dense_s.weight)], h1, ops.EPI_RESIDUAL, [dense_s], residual=hf)
     ops.rmsnorm_gather(h1, ln2.weight.detach(), ln2.variance_epsilon, None, n_rows, xn)
     act = new(B, I)
-    gemm(xn, [_bf16(gate_s.weight), _bf16(up_s.weight)], act, ops.EPI_SWIGLU, [gate_s, up_s])
-    gemm(act, [_bf16(down_s.weight)], h1, ops.EPI_RESIDUAL, [down_s])  # in place: h1 += down(act)
-    return h1.view(B, 1, H), ((k, v) if use_cache else None)
+    gemm(xn, [_base_weight(gate_s.weight), _base_weight(up_s.weight)], act, ops.EPI_SWIGLU, [gate_s, up_s])
+    gemm(act, [_base_weight(down_s.weight)], h1, ops.EPI_RESIDUAL, [down_s])  # in place: h1 += down(act)
+    return h1
+
+
+KV_HEADROOM = int(os.environ.get("VEX_KV_HEADROOM", "256"))  # positions pre-allocated past the prefill length
+_kv_pos_cache: dict = {}
+
+
+def _kv_pos_tensor(past_len: int, device) -> torch.Tensor:
+    """Device scalar holding ``past_len`` for the tuple-cache API (shared by the 32 layers of one step)."""
+    key = (device, past_len)
+    t = _kv_pos_cache.get(key)
+    if t is None:
+        if len(_kv_pos_cache) > 8:
+            _kv_pos_cache.clear()
+        t = _kv_pos_cache[key] = torch.tensor([past_len], dtype=torch.int32, device=device)
+    return t
+
+
+def _cache_capacity(t: torch.Tensor) -> int:
+    """Capacity (positions) of the pre-allocated buffer a [B, heads, L, 128] cache view lives in, 0 if it is not such
+    a view (e.g. the contiguous result of a ``torch.cat`` / beam-search ``index_select``)."""
+    B, heads, L, d = t.shape
+    if d != HEAD_DIM or t.stride(3) != 1 or t.stride(2) != HEAD_DIM or t.storage_offset() != 0:
+        return 0
+    cap = t.stride(1) // HEAD_DIM
+    if t.stride(1) != cap * HEAD_DIM or (B > 1 and t.stride(0) != heads * cap * HEAD_DIM) or cap < L:
+        return 0
+    if t.untyped_storage().nbytes() < B * heads * cap * HEAD_DIM * t.element_size():
+        return 0
+    return cap
+
+
+def visual_expert_layer_decode(layer: "CogVLMDecoderLayer", hidden_states: torch.Tensor, position_ids: torch.Tensor,
+                               padding_mask: torch.Tensor, past_key_value, use_cache: bool = True):
+    """One generation step through the reference's tuple-cache interface (q_len == 1 with ``past_key_value`` =
+    (k, v) [B, heads, L_past, 128]; returns the layer output and (k, v) [B, heads, L_past + 1, 128]).  The cache the
+    prefill returned is a view of a buffer with ``KV_HEADROOM`` spare positions, so the step appends IN PLACE and hands
+    back longer views of the same storage; a cache that has no room left (or came from somewhere else, e.g. a
+    beam-search reorder) is moved once into a fresh buffer with headroom -- the reference reallocates on every step
+    (``torch.cat``, :258-260)."""
+    attn = layer.self_attn
+    B, L, H = hidden_states.shape
+    heads = attn.num_heads
+    past_k, past_v = past_key_value
+    if past_k.shape[0] != B or past_k.shape[1] != heads or past_k.shape[3] != HEAD_DIM or past_v.shape != past_k.shape:
+        raise ValueError(f"past_key_value must be [B, {heads}, L_past, {HEAD_DIM}]")
+    Lp = past_k.shape[2]
+    Lkv = Lp + 1
+    if padding_mask.shape != (B, Lkv):
+        raise ValueError(f"padding_mask must cover past + current positions: expected {(B, Lkv)}")
+    cap = min(_cache_capacity(past_k), _cache_capacity(past_v))
+    if cap >= Lkv:
+        shape = (B, heads, cap, HEAD_DIM)
+        k_cache, v_cache = (torch.as_strided(t, shape, (heads * cap * HEAD_DIM, cap * HEAD_DIM, HEAD_DIM, 1), 0)
+                            for t in (past_k, past_v))
+    else:
+        cap = Lkv + KV_HEADROOM
+        kv = torch.empty(2, B, heads, cap, HEAD_DIM, dtype=past_k.dtype, device=past_k.device)
+        kv[0][:, :, :Lp].copy_(past_k)
+        kv[1][:, :, :Lp].copy_(past_v)
+        k_cache, v_cache = kv[0], kv[1]
+    out = decode_core(layer, hidden_states.view(B, H), position_ids, k_cache, v_cache, padding_mask,
+                      _kv_pos_tensor(Lp, hidden_states.device))
+    present = (k_cache[:, :, :Lkv], v_cache[:, :, :Lkv]) if use_cache else None
+    return out.view(B, 1, H), present
 
 
 class CogVLMDecoderLayer(nn.Module):
@@ -524,8 +668,11 @@ class CogVLMDecoderLayer(nn.Module):
             raise ValueError("token_type_ids / position_ids must be [B, L] like hidden_states")
         if not decode and hidden_states.shape[1] == 1:
             raise NotImplementedError("q_len == 1 without a KV cache is not part of the prefill path")
+        # Training path: autograd is on AND something differentiable is involved -- the input, a LoRA adapter or a
+        # modules_to_save norm copy.  A plain (un-wrapped) layer called without torch.no_grad() is inference, as with
+        # the reference: its base weights are constants of the fused forward (they are frozen under PEFT anyway).
         train = torch.is_grad_enabled() and (hidden_states.requires_grad or any(
-            p.requires_grad for p in self.parameters()))
+            p.requires_grad and ("lora_" in n or "modules_to_save" in n) for n, p in self.named_parameters()))
         if train and (decode or use_cache):
             raise NotImplementedError("autograd through the decode / use_cache paths is not implemented")
         if output_attentions:
@@ -577,8 +724,10 @@ class VisualExpertDecoder(nn.Module):
     vision encoder stay with the caller -- they are outside the hot path).  State-dict keys ``layers.N.*`` and
     ``norm.weight`` equal those of ``CogVLMModel``, so its checkpoint loads with ``strict=False``.
 
-    The routing plan (K1) is computed once and shared by all layers; with ``graph=True`` the whole prefill is
-    captured into one CUDA graph per input shape (``GraphedPrefill``)."""
+    Prefill (no grad) runs ``decoder_stack_forward``: the routing plan (K1) is computed once and the residual stream
+    stays in expert-sorted order across all layers; with ``graph=True`` the whole prefill is captured into one CUDA
+    graph per input shape (``GraphedPrefill``).  Generation: ``prefill_static`` + ``decode_step`` keep the KV cache
+    in pre-allocated buffers and replay each step as a CUDA graph (``kv_cache.StaticKVCache``)."""
 
     def __init__(self, config):
         super().__init__()
@@ -586,6 +735,10 @@ class VisualExpertDecoder(nn.Module):
         self.layers = nn.ModuleList([CogVLMDecoderLayer(config) for _ in range(config.num_hidden_layers)])
         self.norm = RMSNorm(config.hidden_size, eps=config.rms_norm_eps)
         self._graphs = {}
+
+    def _differentiable(self, inputs_embeds: torch.Tensor) -> bool:
+        return torch.is_grad_enabled() and (inputs_embeds.requires_grad or any(
+            p.requires_grad and ("lora_" in n or "modules_to_save" in n) for n, p in self.named_parameters()))
 
     def llm_forward(self, inputs_embeds: torch.Tensor, token_type_ids: torch.Tensor,
                     attention_mask: Optional[torch.Tensor] = None, position_ids: Optional[torch.Tensor] = None,
@@ -607,9 +760,15 @@ class VisualExpertDecoder(nn.Module):
                 self._graphs[key] = GraphedPrefill(self.layers, inputs_embeds, token_type_ids, position_ids,
                                                    padding_mask, final_norm=self.norm)
             return self._graphs[key](inputs_embeds, token_type_ids, position_ids, padding_mask), None
+        if past_key_values is None and L > 1 and not self._differentiable(inputs_embeds):
+            if not inputs_embeds.is_cuda or inputs_embeds.dtype != torch.bfloat16:
+                raise TypeError("inputs_embeds must be a CUDA bfloat16 tensor (no CPU path)")
+            plan = GLOBAL_PLAN_CACHE.get(token_type_ids, padding_mask)
+            return decoder_stack_forward(self.layers, self.norm, inputs_embeds.contiguous(), plan, position_ids,
+                                         use_cache=use_cache)
         h = inputs_embeds
         cache = () if use_cache else None
-        for i, layer in enumerate(self.layers):  # :547-569
+        for i, layer in enumerate(self.layers):  # :547-569 (training, decode through the tuple-cache interface)
             out = layer(h, token_type_ids=token_type_ids, position_ids=position_ids, padding_mask=padding_mask,
                         past_key_value=None if past_key_values is None else past_key_values[i], use_cache=use_cache)
             h = out[0]
@@ -622,3 +781,32 @@ class VisualExpertDecoder(nn.Module):
         return h, cache
 
     forward = llm_forward
+
+    # ---- generation with a static cache ----
+    def prefill_static(self, inputs_embeds: torch.Tensor, token_type_ids: torch.Tensor,
+                       attention_mask: Optional[torch.Tensor] = None, position_ids: Optional[torch.Tensor] = None,
+                       max_new_tokens: int = 256):
+        """Prefill that leaves K / V in a ``StaticKVCache`` with room for ``max_new_tokens`` more positions.
+        Returns (last_hidden_state [B, L, H], cache)."""
+        from .kv_cache import StaticKVCache
+        B, L, _ = inputs_embeds.shape
+        dev = inputs_embeds.device
+        if position_ids is None:
+            position_ids = torch.arange(L, dtype=torch.long, device=dev).unsqueeze(0).expand(B, L)
+        position_ids = position_ids.reshape(-1, L).long().contiguous()
+        if attention_mask is None:
+            attention_mask = torch.ones(B, L, dtype=torch.bool, device=dev)
+        padding_mask = attention_mask.bool().contiguous()
+        cache = StaticKVCache(len(self.layers), B, self.layers[0].self_attn.num_heads, L + max_new_tokens, dev)
+        plan = GLOBAL_PLAN_CACHE.get(token_type_ids, padding_mask)
+        with torch.no_grad():
+            h, _ = decoder_stack_forward(self.layers, self.norm, inputs_embeds.contiguous(), plan, position_ids,
+                                         use_cache=True, kv_out=cache.layers)
+        cache.start(padding_mask)
+        return h, cache
+
+    def decode_step(self, inputs_embeds: torch.Tensor, position_ids: torch.Tensor, cache, graph: bool = True):
+        """One generation step for every sample: ``inputs_embeds`` [B, 1, H], ``position_ids`` [B, 1]; appends to
+        ``cache`` in place and returns the final-normed hidden state [B, 1, H].  With ``graph`` the 32-layer step is one
+        CUDA-graph replay (captured on first use per cache)."""
+        return cache.step(self, inputs_embeds, position_ids, graph=graph)

@@ -143,14 +143,17 @@ def grouped_gemm_raw(a: torch.Tensor, w: Sequence[Optional[torch.Tensor]], out: 
                      rope: Optional[tuple] = None, rope_cols: int = 0, single_expert: bool = False,
                      alpha: float = 1.0, n_out: Optional[int] = None, w_transposed: bool = False,
                      dropout_p: float = 0.0, dropout_seed: int = 0, ce: Optional[dict] = None,
-                     bias: Optional[torch.Tensor] = None, act: int = ACT_NONE) -> None:
+                     bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+                     kv: Optional[tuple] = None) -> None:
     """K3 (vex_grouped_gemm).  ``w`` = [vision_w0, vision_w1, language_w0, language_w1] ([N, K] each; the *_w1
     entries are up_proj for SWIGLU, else None).  ``lora_b`` likewise; ``lora_t`` = [T_half0, T_half1].
     ``rope`` = (cos [S,128], sin [S,128], position_ids int64 [B*L], sorted_to_flat int32).
     ``w_transposed``: the weights are [K, N] (out = a . w, the dgrad form dX = dY . W over the nn.Linear weight as
     stored) and ``lora_b`` holds lora_A [r, N].
     ``bias`` (bf16 [N]) / ``act`` (ACT_GELU): nn.Linear with bias and the erf-GELU of the vision encoder's Linears
-    (visual.py:84-85, :110-117), PLAIN / RESIDUAL epilogues only."""
+    (visual.py:84-85, :110-117), PLAIN / RESIDUAL epilogues only.
+    ``kv`` = (k_cache, v_cache [B, heads, capacity, 128], seq_len, kv_pos or None): EPI_ROPE also writes the post-rotary
+    K heads and the V heads into the KV cache (vexGemmArgs.kv_k)."""
     _dev(a, "a", _BF16)
     if out is not None:
         _dev(out, "out", _BF16)
@@ -227,6 +230,16 @@ def grouped_gemm_raw(a: torch.Tensor, w: Sequence[Optional[torch.Tensor]], out: 
             raise ValueError("bias must have one entry per output feature")
         args.bias = bias.data_ptr()
     args.act = int(act)
+    if kv is not None:
+        k_cache, v_cache, kv_seq, kv_pos = kv
+        _dev(k_cache, "k_cache", _BF16), _dev(v_cache, "v_cache", _BF16)
+        if k_cache.dim() != 4 or k_cache.shape != v_cache.shape or k_cache.shape[-1] != 128:
+            raise ValueError("KV cache tensors must be [B, heads, capacity, 128]")
+        if mode != EPI_ROPE or k_cache.shape[1] * 128 * 3 != N:
+            raise ValueError("the KV-cache output belongs to the QKV projection's EPI_ROPE epilogue")
+        args.kv_k, args.kv_v = k_cache.data_ptr(), v_cache.data_ptr()
+        args.kv_pos = _ptr(None if kv_pos is None else _dev(kv_pos, "kv_pos", torch.int32))
+        args.kv_seq_len, args.kv_capacity = int(kv_seq), k_cache.shape[2]
     name = ("gemm_plain", "gemm_rope", "gemm_swiglu", "gemm_residual", "gemm_dropout_acc", "gemm_ce", "gemm_ce_bwd")[mode] + ("_n64" if N <= 64 else "") + \
         ("_dgrad" if w_transposed else "") + ("_gelu" if act == ACT_GELU else "")
     with instrument.region(name):
@@ -243,15 +256,20 @@ def grouped_gemm(a: torch.Tensor, w_vision: torch.Tensor, w_language: Optional[t
                      single_expert=w_language is None)
 
 
-@torch.library.custom_op("vex::grouped_gemm_fused", mutates_args=("out",))
+@torch.library.custom_op("vex::grouped_gemm_fused", mutates_args=("out", "kv_k", "kv_v"))
 def grouped_gemm_fused(a: torch.Tensor, w: List[Optional[torch.Tensor]], out: torch.Tensor, counts: torch.Tensor,
                        mode: int, row_map: Optional[torch.Tensor], residual: Optional[torch.Tensor],
                        lora_t: List[Optional[torch.Tensor]], lora_b: List[Optional[torch.Tensor]], lora_r: int,
-                       rope: List[torch.Tensor], rope_cols: int, single_expert: bool, alpha: float) -> None:
-    """K3 with a fused epilogue (``mode`` = EPI_*), LoRA K-extension and scatter; see ``grouped_gemm_raw``."""
+                       rope: List[torch.Tensor], rope_cols: int, single_expert: bool, alpha: float,
+                       kv_k: Optional[torch.Tensor] = None, kv_v: Optional[torch.Tensor] = None, kv_seq_len: int = 0,
+                       kv_pos: Optional[torch.Tensor] = None) -> None:
+    """K3 with a fused epilogue (``mode`` = EPI_*), LoRA K-extension and scatter; see ``grouped_gemm_raw``.
+    ``kv_k`` / ``kv_v`` [B, heads, capacity, 128]: KV-cache second output of EPI_ROPE (prefill: ``kv_seq_len`` = L;
+    decode: 1 and ``kv_pos`` = device counter of cached positions)."""
     grouped_gemm_raw(a, w, out, counts, mode, row_map=row_map, residual=residual, lora_t=lora_t, lora_b=lora_b,
                      lora_r=lora_r, rope=tuple(rope) if len(rope) else None, rope_cols=rope_cols,
-                     single_expert=single_expert, alpha=alpha)
+                     single_expert=single_expert, alpha=alpha,
+                     kv=None if kv_k is None else (kv_k, kv_v, kv_seq_len, kv_pos))
 
 
 @torch.library.custom_op("vex::grouped_gemm_dgrad", mutates_args=("out",))
@@ -360,6 +378,53 @@ def attention_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask: to
       rc = _lib.lib().vex_attention_decode(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), mask.data_ptr(),
                                            out.data_ptr(), B, heads, L, float(scale), _stream())
     _lib.check(rc, "vex_attention_decode")
+
+
+@torch.library.custom_op("vex::attention_decode_cache", mutates_args=("out",))
+def attention_decode_cache(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, mask: torch.Tensor,
+                           kv_len: torch.Tensor, out: torch.Tensor, scale: float) -> None:
+    """K4d over the pre-allocated cache (vex_attention_decode_cache): k_cache / v_cache [B, heads, capacity, 128],
+    mask bool [B, M] covering the attended positions (row-strided view is fine), kv_len int32 [1] on the device =
+    positions cached before this step; attends to positions [0, kv_len] (clamped to min(capacity, M))."""
+    _dev(k_cache, "k_cache", _BF16), _dev(v_cache, "v_cache", _BF16), _dev(out, "out", _BF16)
+    _dev(kv_len, "kv_len", torch.int32)
+    if not q.is_cuda or q.dtype != _BF16 or q.stride(-1) != 1:
+        raise ValueError("q must be a CUDA bf16 tensor with unit inner stride")
+    B, heads, cap, d = k_cache.shape
+    if d != 128 or v_cache.shape != k_cache.shape or q.shape != (B, heads * 128):
+        raise ValueError("shape mismatch (head_dim 128 only)")
+    if not mask.is_cuda or mask.dtype != torch.bool or mask.dim() != 2 or mask.shape[0] != B or mask.stride(1) != 1:
+        raise ValueError("mask must be a CUDA bool [B, M] tensor with unit inner stride")
+    with instrument.region("attention_decode"):
+      rc = _lib.lib().vex_attention_decode_cache(q.data_ptr(), q.stride(0), k_cache.data_ptr(), v_cache.data_ptr(),
+                                                 mask.data_ptr(), mask.stride(0) if B > 1 else mask.shape[1],
+                                                 mask.shape[1], out.data_ptr(), B, heads, cap,
+                                                 kv_len.data_ptr(), float(scale), _stream())
+    _lib.check(rc, "vex_attention_decode_cache")
+
+
+@torch.library.custom_op("vex::advance_counter", mutates_args=("counter",))
+def advance_counter(counter: torch.Tensor, by: int) -> None:
+    """counter[0] += by on the stream (vex_advance_counter): the decode graph's own past-length increment."""
+    _dev(counter, "counter", torch.int32)
+    with instrument.region("advance_counter"):
+      rc = _lib.lib().vex_advance_counter(counter.data_ptr(), int(by), _stream())
+    _lib.check(rc, "vex_advance_counter")
+
+
+@torch.library.custom_op("vex::kv_clear_padded", mutates_args=("k_cache", "v_cache"))
+def kv_clear_padded(k_cache: torch.Tensor, v_cache: torch.Tensor, flat_to_sorted: torch.Tensor, batch: int,
+                    seq_len: int) -> None:
+    """Zeroes the cache rows of padded prefill positions (vex_kv_clear_padded; the reference cache holds zeros there,
+    modeling_cogvlm.py:243)."""
+    _dev(k_cache, "k_cache", _BF16), _dev(v_cache, "v_cache", _BF16), _dev(flat_to_sorted, "flat_to_sorted", torch.int32)
+    B, heads, cap, d = k_cache.shape
+    if d != 128 or v_cache.shape != k_cache.shape or B != batch or cap < seq_len or flat_to_sorted.numel() < B * seq_len:
+        raise ValueError("KV cache must be [B, heads, capacity >= L, 128]")
+    with instrument.region("kv_clear_padded"):
+      rc = _lib.lib().vex_kv_clear_padded(k_cache.data_ptr(), v_cache.data_ptr(), flat_to_sorted.data_ptr(), B, seq_len,
+                                          heads, cap, _stream())
+    _lib.check(rc, "vex_kv_clear_padded")
 
 
 # ------------------------------------------------------------------------------------------ K7 (backward, row-wise)
@@ -617,6 +682,6 @@ def lora_wgrad(x: torch.Tensor, y: torch.Tensor, out_vision: Optional[torch.Tens
     _lib.check(rc, "vex_lora_wgrad")
 
 
-for _op in (linear_bias_act, attention_blockdiag, layernorm, patchify, maxpool_tokens, scatter_rows, label_rows, lm_head_ce_forward, lm_head_ce_backward, dropout_rows, attention_train, attention_backward, lora_wgrad, gather_rows, silu_mul_backward, rmsnorm_backward, grouped_gemm_dgrad, attention_decode, partition, rmsnorm_gather, silu_mul, residual_scatter, copy_padded_rows, grouped_gemm, grouped_gemm_fused,
+for _op in (attention_decode_cache, advance_counter, kv_clear_padded, linear_bias_act, attention_blockdiag, layernorm, patchify, maxpool_tokens, scatter_rows, label_rows, lm_head_ce_forward, lm_head_ce_backward, dropout_rows, attention_train, attention_backward, lora_wgrad, gather_rows, silu_mul_backward, rmsnorm_backward, grouped_gemm_dgrad, attention_decode, partition, rmsnorm_gather, silu_mul, residual_scatter, copy_padded_rows, grouped_gemm, grouped_gemm_fused,
             attention):
     _op.register_fake(lambda *a, **k: None)

@@ -67,6 +67,15 @@ def build_plan(token_type_ids: torch.Tensor, padding_mask: torch.Tensor) -> Rout
     return RoutingPlan(B, L, idx[0], idx[1], idx[2], idx[3], idx[4], cu, counts)
 
 
+def _version_of(t: torch.Tensor):
+    """In-place-mutation stamp of a key tensor.  Inference tensors (created under ``torch.inference_mode()``, which
+    is how the reference's evaluation drivers call ``generate`` -- scripts/evaluate/models/mmmm.py:132) do not track a
+    version counter and raise when ``_version`` is read; they are keyed on identity + storage + shape instead."""
+    if t.is_inference():
+        return ("inference", t.data_ptr(), tuple(t.shape))
+    return t._version
+
+
 class PlanCache:
     """One-entry cache keyed on tensor identity + version counter (the caller loop passes the same
     ``token_type_ids`` / ``padding_mask`` objects to every layer, modeling_cogvlm.py:547-562).  Holding
@@ -79,10 +88,10 @@ class PlanCache:
     def get(self, token_type_ids: torch.Tensor, padding_mask: torch.Tensor) -> RoutingPlan:
         k = self._key
         if (k is not None and k[0] is token_type_ids and k[1] is padding_mask
-                and k[2] == token_type_ids._version and k[3] == padding_mask._version):
+                and k[2] == _version_of(token_type_ids) and k[3] == _version_of(padding_mask)):
             return self._plan
         plan = build_plan(token_type_ids, padding_mask)
-        self._key = (token_type_ids, padding_mask, token_type_ids._version, padding_mask._version)
+        self._key = (token_type_ids, padding_mask, _version_of(token_type_ids), _version_of(padding_mask))
         self._plan = plan
         return plan
 

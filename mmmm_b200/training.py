@@ -34,6 +34,11 @@ def _bf16(t: torch.Tensor) -> torch.Tensor:
     return cast(t)
 
 
+def _base_weight(t: torch.Tensor) -> torch.Tensor:
+    from .modeling_cogvlm import _base_weight as chk
+    return chk(t)
+
+
 class _GradSink:
     """fp32 accumulators for the trainable tensors of one layer backward (K8 / K7 add into them atomically)."""
 
@@ -78,12 +83,12 @@ def _routed_linear_backward(dy: torch.Tensor, x: torch.Tensor, t: Optional[torch
         if gA[0] is not None or gA[1] is not None:
             ops.lora_wgrad(x_dropped if p_drop > 0 else x, dt, gA[0], gA[1], True, counts)
     if p_drop > 0:
-        ops.grouped_gemm_dgrad(dy, [_bf16(sv.weight), _bf16(sl.weight)], out, counts, accumulate, row_map, None,
+        ops.grouped_gemm_dgrad(dy, [_base_weight(sv.weight), _base_weight(sl.weight)], out, counts, accumulate, row_map, None,
                                [None, None], 0, False, 1.0)
         ops.grouped_gemm_dgrad(dt, lora_a, out, counts, True, row_map, None, [None, None], 0, not both, 1.0,
                                p_drop, dropout_seed)
     else:
-        ops.grouped_gemm_dgrad(dy, [_bf16(sv.weight), _bf16(sl.weight)], out, counts, accumulate, row_map, dt, lora_a,
+        ops.grouped_gemm_dgrad(dy, [_base_weight(sv.weight), _base_weight(sl.weight)], out, counts, accumulate, row_map, dt, lora_a,
                                r, False, 1.0)
 
 

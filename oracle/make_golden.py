@@ -130,6 +130,12 @@ def main():
     # long positions (> 256) to exercise the bf16 arange collapse of the rotary table
     longp = layer_case(M, hidden=256, heads=2, inter=256, batch=2, nv=8, nt=300, seed=12)
     torch.save(longp, os.path.join(OUT, "layer_longpos.pt"))
+    # the ragged text lengths of layer_longpos top out at position 253; this one is ragged over [300, 600] text tokens,
+    # so every sample runs through the collapsed region of the bf16-built table (positions 257 .. ~600: bf16 arange
+    # steps of 2, then 4 above 512) -- the rotary quirk pinned at LAYER level by reference output
+    pos600 = layer_case(M, hidden=256, heads=2, inter=256, batch=2, nv=8, nt=600, seed=17)
+    assert int(pos600["position_ids"].max()) >= 512
+    torch.save(pos600, os.path.join(OUT, "layer_pos600.pt"))
     # lm_head + _sample_weighted_ce (modeling_cogvlm.py:610-627, :701-706) through the unmodified reference function
     g = torch.Generator().manual_seed(13)
     Bc, Lc, Hc, Vc = 3, 37, 64, 333

@@ -25,7 +25,7 @@ def test_header_symbols_exported_and_listed():
     assert decl == sorted(_lib.SYMBOLS), (decl, sorted(_lib.SYMBOLS))
     for name in decl:
         assert hasattr(lib, name), f"{name} not exported by libvex.so"
-    assert lib.vex_abi_version() == 6
+    assert lib.vex_abi_version() == 7
     assert lib.vex_error_string(-2).decode() == "unsupported shape"
 
 

@@ -526,9 +526,9 @@ def test_k4_attention_vs_oracle(lens, impl, monkeypatch):
     """Every implementation -- the two-tile tcgen05 kernel in its four schedules (default: early S, P in shared memory;
     P in shared memory with the serial schedule; P in TMEM; early S with exp turns), the one-tile tcgen05 kernel and
     the mma.sync baseline -- against the oracle."""
-    monkeypatch.setenv("VEX_ATTN_IMPL", impl.split("-")[0])
     monkeypatch.setenv("VEX_ATTN_P", impl.split("-")[1] if "-" in impl else "early")
     ops = _ops()
+    attend = ops.attention if impl == "tc3" else _baseline_attention(impl.split("-")[0])
     heads = 3
     B, Lmax = len(lens), max(lens)
     g = torch.Generator().manual_seed(sum(lens))
@@ -547,9 +547,15 @@ def test_k4_attention_vs_oracle(lens, impl, monkeypatch):
     cu[1:] = torch.tensor(lens).cumsum(0)
     rmap = torch.randperm(B * Lmax, generator=g).int()
     out = torch.zeros(B * Lmax, heads * 128, dtype=torch.bfloat16).cuda()
-    ops.attention(qkv_buf.cuda(), cu.cuda(), B, Lmax, heads, rmap.cuda(), out, 128 ** -0.5)
+    attend(qkv_buf.cuda(), cu.cuda(), B, Lmax, heads, rmap.cuda(), out, 128 ** -0.5)
     got = out.cpu()[rmap[:T].long()]
     torch.testing.assert_close(got.float(), tok(want).reshape(T, heads * 128).float(), rtol=2e-2, atol=2e-2)
+
+
+def _baseline_attention(impl):
+    """The superseded attention kernels live in libvex_baselines.so (csrc/baselines/), outside the product library."""
+    from tests.helpers import baselines
+    return lambda *a: baselines.attention(impl, *a)
 
 
 @pytest.mark.parametrize("impl", ["tc3", "tc2"])
@@ -558,9 +564,9 @@ def test_k4_attention_many_items_per_cta(impl, monkeypatch):
     inactive second tile) on at most 148 persistent CTAs: every CTA walks several items, so the running barrier phases,
     the Q / O hand-over between items and the scheduler ring of the persistent kernel are exercised; checked against
     the oracle like the small cases."""
-    monkeypatch.setenv("VEX_ATTN_IMPL", impl)
     monkeypatch.delenv("VEX_ATTN_P", raising=False)
     ops = _ops()
+    attend = ops.attention if impl == "tc3" else _baseline_attention(impl)
     heads, lens = 16, [700, 130, 1, 513, 257, 1024, 64, 385]
     B, Lmax = len(lens), max(lens)
     g = torch.Generator().manual_seed(77)
@@ -580,7 +586,7 @@ def test_k4_attention_many_items_per_cta(impl, monkeypatch):
     qkv_dev, cu_dev, rmap_dev = qkv_buf.cuda(), cu.cuda(), rmap.cuda()
     for _ in range(3):  # repeated launches reuse / rotate the work counters
         out.zero_()
-        ops.attention(qkv_dev, cu_dev, B, Lmax, heads, rmap_dev, out, 128 ** -0.5)
+        attend(qkv_dev, cu_dev, B, Lmax, heads, rmap_dev, out, 128 ** -0.5)
         got = out.cpu()[rmap[:T].long()]
         torch.testing.assert_close(got.float(), tok(want).reshape(T, heads * 128).float(), rtol=2e-2, atol=2e-2)
     untouched = torch.ones(B * Lmax, dtype=torch.bool)

@@ -43,7 +43,7 @@ def _run(layer, h, tt, pos, pm, **kw):
         return layer(h.cuda(), token_type_ids=tt.cuda(), position_ids=pos.cuda(), padding_mask=pm.cuda(), **kw)
 
 
-@pytest.mark.parametrize("name", ["layer_tiny.pt", "layer_longpos.pt"])
+@pytest.mark.parametrize("name", ["layer_tiny.pt", "layer_longpos.pt", "layer_pos600.pt"])
 @pytest.mark.parametrize("fuse", [True, False])
 def test_layer_vs_reference_golden(golden_dir, name, fuse):
     """Against outputs of the UNMODIFIED reference (bf16 run) stored by oracle/make_golden.py."""
@@ -567,3 +567,327 @@ def test_fused_lm_head_loss_full_vocabulary():
     assert abs(float(loss) - float(ref)) <= 2e-3 * abs(float(ref)), (float(loss), float(ref))
     e = float((x.grad.float() - xr.grad.float()).norm() / xr.grad.float().norm())
     assert e <= 2e-2, e
+
+
+# ------------------------------------------------------------------------------------------ full-width parity (round 2)
+def _full_layer(seed, lora_r=None, lora_seed=None):
+    H, I, heads = 4096, 11008, 32
+    w = O.random_weights(H, I, heads, seed=seed, dtype=torch.bfloat16)
+    ad = O.random_lora(H, I, r=lora_r, seed=lora_seed or seed + 1, dtype=torch.bfloat16, b_std=0.02) if lora_r else None
+    layer = _make_layer(w, dict(hidden_size=H, intermediate_size=I, num_attention_heads=heads), lora=ad)
+    return w, ad, layer, (H, I, heads)
+
+
+@pytest.mark.parametrize("lora_r", [None, 64])
+def test_c2_one_sample_full_width_vs_oracle(lora_r):
+    """One BASELINE config-2 sample at full width (1225 vision + 256 text = 1485 tokens, hidden 4096; positions run
+    to 260, i.e. INTO the collapsed region of the bf16-built rotary table), without and with LoRA r = 64 on all ten
+    Linears (K = 11 008 + K-extension on the down projection, N = 12 288 with ROPE + LoRA on QKV), vs the CPU oracle."""
+    from mmmm_b200.inputs import make_inputs
+    w, ad, layer, (H, I, heads) = _full_layer(3, lora_r)
+    inp = make_inputs(1, 1225, 256, H, seed=4)
+    assert int(inp.position_ids.max()) >= 257
+    (out,) = _run(layer, inp.hidden_states, inp.token_type_ids, inp.position_ids, inp.padding_mask)
+    (ref,) = O.decoder_layer(w, inp.hidden_states, inp.token_type_ids, inp.position_ids, inp.padding_mask,
+                             num_heads=heads, lora=ad)
+    mx, fro = _errs(out.cpu()[0], ref[0])
+    assert mx <= MAX_REL and fro <= FRO_REL, (mx, fro)
+
+
+def test_c2_batch_of_8_vs_per_sample_oracle():
+    """BASELINE config 2 at its full batch (8 x 1485 tokens, ragged text lengths) through ONE call; two of the eight
+    samples are checked against the CPU oracle run on that sample alone (samples are independent on this path)."""
+    from mmmm_b200.inputs import make_inputs
+    w, _, layer, (H, I, heads) = _full_layer(5)
+    inp = make_inputs(8, 1225, 256, H, ragged=True, seed=6)
+    (out,) = _run(layer, inp.hidden_states, inp.token_type_ids, inp.position_ids, inp.padding_mask)
+    out = out.cpu()
+    for b in (2, 7):
+        sl = slice(b, b + 1)
+        pm = inp.padding_mask[sl]
+        (ref,) = O.decoder_layer(w, inp.hidden_states[sl], inp.token_type_ids[sl], inp.position_ids[sl], pm,
+                                 num_heads=heads)
+        mx, fro = _errs(out[sl][pm], ref[pm])
+        assert mx <= MAX_REL and fro <= FRO_REL, (b, mx, fro)
+
+
+def test_c4_one_sample_full_width_vs_oracle():
+    """One BASELINE config-4 sample (2048 vision + 512 text = 2564 tokens: 21 key blocks per query tile; positions to
+    516, past the second bf16 collapse at 512) at full width: K4 alone vs O.attention, and the layer vs the oracle."""
+    from mmmm_b200 import ops
+    from mmmm_b200.inputs import make_inputs
+    w, _, layer, (H, I, heads) = _full_layer(7)
+    inp = make_inputs(1, 2048, 512, H, seed=8)
+    L = inp.padding_mask.shape[1]
+    assert L == 2564
+    # K4 on its own at this length (all 32 heads)
+    g = torch.Generator().manual_seed(9)
+    q, k, v = [torch.randn(1, heads, L, 128, generator=g).bfloat16() for _ in range(3)]
+    want = O.attention(q, k, v, inp.padding_mask)
+    tok = lambda t: t.permute(0, 2, 1, 3)[0]
+    qkv = torch.stack([tok(q), tok(k), tok(v)], dim=1).reshape(L, 3 * heads * 128).contiguous().cuda()
+    cu = torch.tensor([0, L], dtype=torch.int32).cuda()
+    got = torch.zeros(L, heads * 128, dtype=torch.bfloat16).cuda()
+    ops.attention(qkv, cu, 1, L, heads, None, got, 128 ** -0.5)
+    torch.testing.assert_close(got.cpu().float(), tok(want).reshape(L, heads * 128).float(), rtol=2e-2, atol=2e-2)
+    # the whole layer
+    (out,) = _run(layer, inp.hidden_states, inp.token_type_ids, inp.position_ids, inp.padding_mask)
+    (ref,) = O.decoder_layer(w, inp.hidden_states, inp.token_type_ids, inp.position_ids, inp.padding_mask,
+                             num_heads=heads)
+    mx, fro = _errs(out.cpu()[0], ref[0])
+    assert mx <= MAX_REL and fro <= FRO_REL, (mx, fro)
+
+
+def test_c4_two_sample_batch_properties():
+    """The config-4 per-GPU shard (2 x 2564 tokens) in one call equals the two samples run alone, bit for bit."""
+    from mmmm_b200.inputs import make_inputs
+    w, _, layer, (H, I, heads) = _full_layer(7)
+    inp = make_inputs(2, 2048, 512, H, ragged=True, seed=10)
+    pm = inp.padding_mask
+    (out,) = _run(layer, inp.hidden_states, inp.token_type_ids, inp.position_ids, pm)
+    for b in (0, 1):
+        sl = slice(b, b + 1)
+        (ob,) = _run(layer, inp.hidden_states[sl], inp.token_type_ids[sl], inp.position_ids[sl], pm[sl])
+        assert torch.equal(ob.cpu()[pm[sl]], out.cpu()[sl][pm[sl]])
+
+
+def test_training_step_full_width_r64_vs_oracle_autograd():
+    """BASELINE config 5 at full width: ONE sample (1225 vision + 256 text, hidden 4096), LoRA r = 64 on all ten
+    Linears + both norms trainable, forward + native backward vs torch.autograd over the oracle in fp32."""
+    from mmmm_b200.inputs import make_inputs
+    from mmmm_b200.modeling_cogvlm import CogVLMDecoderLayer, VexConfig
+    from mmmm_b200.peft_compat import attach_mock_lora
+    H, I, heads, r = 4096, 11008, 32, 64
+    w = O.random_weights(H, I, heads, seed=41, dtype=torch.bfloat16)
+    ad = O.random_lora(H, I, r=r, seed=42, dtype=torch.bfloat16, b_std=0.02)
+    layer = CogVLMDecoderLayer(VexConfig(hidden_size=H, intermediate_size=I, num_attention_heads=heads))
+    layer.load_state_dict(w)
+    layer = layer.to(torch.bfloat16).cuda()
+    attach_mock_lora(layer, r=r)
+    for path, a in ad.items():
+        m = layer.get_submodule(path)
+        m.lora_A["default"].weight.data.copy_(a.A)
+        m.lora_B["default"].weight.data.copy_(a.B)
+        m.scaling["default"] = a.scaling
+    layer.train()
+    inp = make_inputs(1, 1225, 256, H, seed=43)
+    pm = inp.padding_mask
+    proj = torch.randn(inp.hidden_states.shape, generator=torch.Generator().manual_seed(44)).bfloat16()
+    x = inp.hidden_states.cuda().requires_grad_(True)
+    (out,) = layer(x, token_type_ids=inp.token_type_ids.cuda(), position_ids=inp.position_ids.cuda(),
+                   padding_mask=pm.cuda())
+    (out.float() * proj.cuda().float()).sum().backward()
+
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    wf = {k: v.float() for k, v in w.items()}
+    adf = {k: O.LoRA(v.A.float().requires_grad_(True), v.B.float().requires_grad_(True), v.scaling) for k, v in ad.items()}
+    for k in ("input_layernorm.weight", "post_attention_layernorm.weight"):
+        wf[k].requires_grad_(True)
+    xr = inp.hidden_states.float().requires_grad_(True)
+    (ref,) = O.decoder_layer(wf, xr, inp.token_type_ids, inp.position_ids, pm, num_heads=heads, lora=adf)
+    (ref * proj.float()).sum().backward()
+
+    def close(got, want, name, tol=4e-2):
+        e = float((got.float().cpu() - want).norm() / want.norm().clamp_min(1e-12))
+        assert e <= tol, (name, e)
+
+    mx, fro = _errs(out.detach().cpu()[pm], ref.detach()[pm])
+    assert mx <= MAX_REL and fro <= FRO_REL, (mx, fro)
+    close(x.grad[pm.cuda()], xr.grad[pm], "d_hidden")
+    for path, a in adf.items():
+        m = layer.get_submodule(path)
+        close(m.lora_A["default"].weight.grad, a.A.grad, path + ".lora_A")
+        close(m.lora_B["default"].weight.grad, a.B.grad, path + ".lora_B")
+    close(layer.input_layernorm.modules_to_save["default"].weight.grad, wf["input_layernorm.weight"].grad, "ln1")
+    close(layer.post_attention_layernorm.modules_to_save["default"].weight.grad,
+          wf["post_attention_layernorm.weight"].grad, "ln2")
+
+
+# ------------------------------------------------------------------------------------------ drop-in behaviour (round 2)
+def test_prefill_and_decode_under_inference_mode():
+    """The reference's evaluation drivers call generate under torch.inference_mode() (scripts/evaluate/models/
+    mmmm.py:132): inference tensors have no version counter, which the plan cache must not touch.  Prefill with
+    use_cache, get_expert_mask, masked_rms_norm and two decode steps, all inside inference_mode, equal the no_grad run."""
+    from mmmm_b200.inputs import make_inputs
+    from mmmm_b200.modeling_cogvlm import RMSNorm, get_expert_mask, masked_rms_norm
+    H, I, heads = 512, 768, 4
+    w = O.random_weights(H, I, heads, seed=51, dtype=torch.bfloat16)
+    layer = _make_layer(w, dict(hidden_size=H, intermediate_size=I, num_attention_heads=heads))
+    norm = RMSNorm(H).to(torch.bfloat16).cuda()
+    inp = make_inputs(2, 60, 20, H, ragged=True, seed=52)
+
+    def run():
+        d = inp.to("cuda")
+        pm = d.padding_mask.long().bool()                     # attention_mask.bool() computed inside the context (:539)
+        out, kv = layer(d.hidden_states, token_type_ids=d.token_type_ids, position_ids=d.position_ids, padding_mask=pm,
+                        use_cache=True)
+        vm, lm = get_expert_mask(d.token_type_ids, pm)
+        hn = masked_rms_norm(norm, out, d.token_type_ids, pm)
+        outs = [out.clone(), hn.clone(), vm.clone(), lm.clone()]
+        mask = pm
+        for step in range(2):
+            mask = torch.cat([mask, torch.ones(2, 1, dtype=torch.bool, device="cuda")], dim=1)
+            x = d.hidden_states[:, step:step + 1].contiguous()
+            p1 = d.position_ids.max(dim=1, keepdim=True).values + 1 + step
+            o, kv = layer(x, token_type_ids=torch.zeros(2, 1, dtype=torch.long, device="cuda"), position_ids=p1,
+                          padding_mask=mask, past_key_value=kv, use_cache=True)
+            outs.append(o.clone())
+        return outs
+
+    with torch.no_grad():
+        want = run()
+    with torch.inference_mode():
+        got = run()
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+
+
+def test_plain_layer_runs_with_grad_enabled():
+    """A layer without PEFT wrappers called outside torch.no_grad() (its base weights have requires_grad = True by
+    default) is plain inference, like the reference -- not the training path, and not an error."""
+    from mmmm_b200.inputs import make_inputs
+    H, I, heads = 512, 768, 4
+    w = O.random_weights(H, I, heads, seed=53, dtype=torch.bfloat16)
+    layer = _make_layer(w, dict(hidden_size=H, intermediate_size=I, num_attention_heads=heads))
+    assert any(p.requires_grad for p in layer.parameters())
+    d = make_inputs(2, 40, 12, H, seed=54).to("cuda")
+    (a,) = layer(d.hidden_states, token_type_ids=d.token_type_ids, position_ids=d.position_ids,
+                 padding_mask=d.padding_mask)
+    with torch.no_grad():
+        (b,) = layer(d.hidden_states, token_type_ids=d.token_type_ids, position_ids=d.position_ids,
+                     padding_mask=d.padding_mask)
+    assert torch.equal(a, b) and not a.requires_grad
+
+
+def test_fp32_base_weight_is_rejected_and_adapter_cast_is_cached():
+    from mmmm_b200 import modeling_cogvlm as MC
+    from mmmm_b200.inputs import make_inputs
+    H, I, heads = 512, 768, 4
+    w = O.random_weights(H, I, heads, seed=55, dtype=torch.bfloat16)
+    ad = O.random_lora(H, I, r=16, seed=56, dtype=torch.bfloat16)
+    layer = _make_layer(w, dict(hidden_size=H, intermediate_size=I, num_attention_heads=heads), lora=ad)
+    # PEFT's autocast_adapter_dtype: fp32 adapters on a bf16 base -> converted ONCE per tensor version
+    for m in layer.modules():
+        if hasattr(m, "lora_A"):
+            m.lora_A.float(), m.lora_B.float()
+    d = make_inputs(1, 30, 10, H, seed=57).to("cuda")
+    MC._cast_cache.clear()
+    _run(layer, d.hidden_states, d.token_type_ids, d.position_ids, d.padding_mask)
+    n1 = len(MC._cast_cache)
+    ptrs = {k: v[2].data_ptr() for k, v in MC._cast_cache.items()}
+    _run(layer, d.hidden_states, d.token_type_ids, d.position_ids, d.padding_mask)
+    assert len(MC._cast_cache) == n1 == 20 and ptrs == {k: v[2].data_ptr() for k, v in MC._cast_cache.items()}
+    a = layer.self_attn.vision_expert_dense.lora_A["default"].weight
+    with torch.no_grad():
+        a.mul_(2)                                             # optimiser step: version bump -> fresh copy
+    _run(layer, d.hidden_states, d.token_type_ids, d.position_ids, d.padding_mask)
+    assert torch.equal(MC._cast_cache[id(a)][2], a.detach().bfloat16())
+    layer.mlp.vision_mlp.down_proj.base_layer.weight.data = layer.mlp.vision_mlp.down_proj.base_layer.weight.data.float()
+    with pytest.raises(TypeError):
+        _run(layer, d.hidden_states, d.token_type_ids, d.position_ids, d.padding_mask)
+
+
+# ------------------------------------------------------------------------------------------ stack + static KV cache (round 2)
+def _make_decoder(H, I, heads, nl, seed):
+    from mmmm_b200.modeling_cogvlm import VexConfig, VisualExpertDecoder
+    ws = [O.random_weights(H, I, heads, seed=seed + i, dtype=torch.bfloat16) for i in range(nl)]
+    model = VisualExpertDecoder(VexConfig(hidden_size=H, intermediate_size=I, num_attention_heads=heads,
+                                          num_hidden_layers=nl))
+    sd = {f"layers.{i}.{k}": v for i, w in enumerate(ws) for k, v in w.items()}
+    norm_w = (1 + 0.1 * torch.randn(H, generator=torch.Generator().manual_seed(seed))).bfloat16()
+    sd["norm.weight"] = norm_w
+    model.load_state_dict(sd, strict=True)
+    return ws, norm_w, model.to(torch.bfloat16).cuda().eval()
+
+
+def test_sorted_stream_stack_equals_flat_layer_calls():
+    """the residual stream kept in expert-sorted order across layers (one gather, in-place residual
+    epilogues, one scatter fused into the final norm) is bit-identical to calling the drop-in layers one by one in the
+    flat [B, L, H] layout + masked_rms_norm, including the K / V every layer leaves in the cache."""
+    from mmmm_b200.inputs import make_inputs
+    from mmmm_b200.modeling_cogvlm import masked_rms_norm
+    H, I, heads, nl = 512, 768, 4, 3
+    _, _, model = _make_decoder(H, I, heads, nl, 60)
+    d = make_inputs(3, 90, 25, H, ragged=True, seed=61).to("cuda")
+    with torch.no_grad():
+        out, cache = model.llm_forward(d.hidden_states, d.token_type_ids, d.padding_mask, d.position_ids, use_cache=True)
+        h, flat_cache = d.hidden_states, []
+        for layer in model.layers:
+            h, kv = layer(h, token_type_ids=d.token_type_ids, position_ids=d.position_ids, padding_mask=d.padding_mask,
+                          use_cache=True)
+            flat_cache.append(kv)
+        want = masked_rms_norm(model.norm, h, d.token_type_ids, d.padding_mask)
+    assert torch.equal(out, want)
+    for (k, v), (k2, v2) in zip(cache, flat_cache):
+        assert torch.equal(k, k2) and torch.equal(v, v2)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_static_cache_generation_vs_oracle(graph):
+    """Generation as a system: prefill_static leaves K / V in pre-allocated buffers, decode_step appends in place
+    (device-side position counter) and -- with graph -- replays the whole 2-layer step as one CUDA graph.  Four steps
+    against the oracle's decode branch driven through its tuple cache."""
+    from mmmm_b200.inputs import make_inputs
+    H, I, heads, nl = 512, 768, 4, 2
+    ws, norm_w, model = _make_decoder(H, I, heads, nl, 70)
+    inp = make_inputs(3, 70, 20, H, ragged=True, seed=71)
+    tt, pos, pm = inp.token_type_ids, inp.position_ids, inp.padding_mask
+    d = inp.to("cuda")
+    h, cache = model.prefill_static(d.hidden_states, d.token_type_ids, d.padding_mask, d.position_ids, max_new_tokens=8)
+    # oracle prefill, layer by layer with caches
+    ref_h, ref_kv = inp.hidden_states, []
+    for w in ws:
+        ref_h, kv = O.decoder_layer(w, ref_h, tt, pos, pm, num_heads=heads, use_cache=True)
+        ref_kv.append(kv)
+    ref_h = O.masked_rms_norm(ref_h, pm, norm_w, 1e-6)
+    mx, fro = _errs(h.cpu()[pm], ref_h[pm])
+    assert mx <= 2 * MAX_REL and fro <= 2 * FRO_REL, (mx, fro)
+    g = torch.Generator().manual_seed(72)
+    mask = pm.clone()
+    next_pos = pos.max(dim=1, keepdim=True).values + 1
+    for step in range(4):
+        x = torch.randn(3, 1, H, generator=g).bfloat16()
+        mask = torch.cat([mask, torch.ones(3, 1, dtype=torch.bool)], dim=1)
+        p1 = next_pos + step
+        out = model.decode_step(x.cuda(), p1.cuda(), cache, graph=graph).clone()
+        r = x
+        for i, w in enumerate(ws):
+            r, ref_kv[i] = O.decoder_layer(w, r, torch.zeros(3, 1, dtype=torch.long), p1, mask, num_heads=heads,
+                                           use_cache=True, past_key_value=ref_kv[i])
+        r = O.rms_norm(r, norm_w, 1e-6)
+        mx, fro = _errs(out.cpu(), r)
+        assert mx <= 2 * MAX_REL and fro <= 2 * FRO_REL, (step, mx, fro)
+    assert cache.host_len == pm.shape[1] + 4 and int(cache.past_len) == cache.host_len
+    mh = mask[:, None, :].expand(3, heads, mask.shape[1])
+    for (k, v), (rk, rv) in zip(cache.views(), ref_kv):
+        for got, want in ((k, rk), (v, rv)):
+            mx, fro = _errs(got.cpu()[mh], want[mh])
+            assert mx <= 2 * MAX_REL and fro <= 2 * FRO_REL, (mx, fro)
+
+
+def test_tuple_cache_decode_appends_in_place():
+    """Through the reference's tuple-cache interface the step after a prefill appends into the prefill's buffer (no
+    torch.cat re-allocation): the returned views share storage with the incoming ones; a foreign contiguous cache
+    (e.g. after a beam-search reorder) is adopted once and then extended in place as well."""
+    from mmmm_b200.inputs import make_inputs
+    H, I, heads = 512, 768, 4
+    w = O.random_weights(H, I, heads, seed=80, dtype=torch.bfloat16)
+    layer = _make_layer(w, dict(hidden_size=H, intermediate_size=I, num_attention_heads=heads))
+    d = make_inputs(2, 40, 10, H, seed=81).to("cuda")
+    L = d.padding_mask.shape[1]
+    with torch.no_grad():
+        _, kv = layer(d.hidden_states, token_type_ids=d.token_type_ids, position_ids=d.position_ids,
+                      padding_mask=d.padding_mask, use_cache=True)
+        x = d.hidden_states[:, :1].contiguous()
+        step = lambda kv, n: layer(x, token_type_ids=torch.zeros(2, 1, dtype=torch.long, device="cuda"),
+                                   position_ids=torch.full((2, 1), 5 + n, device="cuda"),
+                                   padding_mask=torch.ones(2, L + n, dtype=torch.bool, device="cuda"),
+                                   past_key_value=kv, use_cache=True)
+        o1, kv1 = step(kv, 1)
+        assert kv1[0].shape[2] == L + 1 and kv1[0].data_ptr() == kv[0].data_ptr() and kv1[1].data_ptr() == kv[1].data_ptr()
+        assert torch.equal(kv1[0][:, :, :L], kv[0])
+        foreign = tuple(t.contiguous().clone() for t in kv)        # no headroom: adopted into a fresh buffer
+        o2, kv2 = step(foreign, 1)
+        assert torch.equal(o1, o2) and torch.equal(kv2[0], kv1[0]) and kv2[0].data_ptr() != foreign[0].data_ptr()
+        _, kv3 = step(kv2, 2)
+        assert kv3[0].data_ptr() == kv2[0].data_ptr()

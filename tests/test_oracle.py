@@ -56,7 +56,7 @@ def test_bf16_arange_quirk(golden_dir):
     assert torch.equal(cos[256], cos[257]) and torch.equal(cos[259], cos[260])
 
 
-@pytest.mark.parametrize("name", ["layer_tiny.pt", "layer_longpos.pt"])
+@pytest.mark.parametrize("name", ["layer_tiny.pt", "layer_longpos.pt", "layer_pos600.pt"])
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 def test_oracle_matches_golden_layer(golden_dir, name, prec):
     case = _load(golden_dir, name)

@@ -37,11 +37,15 @@ def bench_attention(B=8, nv=1225, nt=256, heads=32, only=None):
     res = {}
     impls = only or ("mma", "tc1", "tc2-tmem", "tc2", "tc3")
     for impl in impls:
-        os.environ["VEX_ATTN_IMPL"] = impl.split("-")[0]
         os.environ["VEX_ATTN_P"] = impl.split("-")[1] if "-" in impl else "early"
         out.zero_()
+        if impl == "tc3":
+            attend = ops.attention
+        else:  # superseded kernels: libvex_baselines.so (csrc/baselines/), not part of the product library
+            from tests.helpers import baselines
+            attend = lambda *a, _i=impl.split("-")[0]: baselines.attention(_i, *a)
         try:
-            ms = timeit(lambda: ops.attention(qkv, plan.cu_seqlens, B, L, heads, plan.token_to_sorted, out, 128 ** -0.5))
+            ms = timeit(lambda: attend(qkv, plan.cu_seqlens, B, L, heads, plan.token_to_sorted, out, 128 ** -0.5))
         except Exception as e:  # keep measuring the other implementations
             print(json.dumps({"kernel": f"attention_{impl}", "error": str(e)[:200]}))
             continue
@@ -51,7 +55,6 @@ def bench_attention(B=8, nv=1225, nt=256, heads=32, only=None):
         if impl != "mma" and impl in res and "mma" in res:
             d = (res["mma"].float() - res[impl].float()).abs().max().item()
             print(json.dumps({f"attention_mma_vs_{impl}_maxabs": d}))
-    os.environ.pop("VEX_ATTN_IMPL", None)
     os.environ.pop("VEX_ATTN_P", None)
 
 
