@@ -552,12 +552,13 @@ def run_ours(args):
 def run_train(args):
     """BASELINE config 5: LoRA (r = --lora, default 64) forward + backward of an N-layer visual-expert decoder with
     the LoRA-gradient all-reduce (NCCL) -- one step = fwd + self-checkpointed bwd + all-reduce over one batch.
-    Forward, recompute and backward all run on the native kernels (mmmm_b200/training.py)."""
+    Forward, recompute and backward all run on the native kernels (mmmm_b200/training.py); the all-reduce is issued
+    per layer from inside the backward on a side stream (training.BucketedGradReducer), so only the last layer's
+    collective is exposed.  --allreduce post times the round-1 post-backward reducer instead (A/B)."""
     import torch.distributed as dist
     from mmmm_b200 import instrument
-    from mmmm_b200.inputs import make_inputs
     from mmmm_b200.sharding import max_over_ranks
-    from mmmm_b200.training import LoraGradReducer
+    from mmmm_b200.training import BucketedGradReducer, LoraGradReducer
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -573,8 +574,10 @@ def run_train(args):
     for l in layers:
         l.recompute = bool(args.recompute)
     params = [p for l in layers for p in l.parameters() if p.requires_grad]
-    reducer = LoraGradReducer(params)
-    inp = make_inputs(b, nv, nt, H, seed=rank).to(dev)
+    overlapped = args.allreduce == "overlap"
+    reducer = BucketedGradReducer(layers) if overlapped else LoraGradReducer(params)
+    host, total_tokens = make_shard_inputs(args)
+    inp = host.to(dev)
     tokens = int(inp.padding_mask.sum())
     proj = torch.randn_like(inp.hidden_states)
     ar_ms = []
@@ -582,16 +585,22 @@ def run_train(args):
     def step():
         h = inp.hidden_states.detach().requires_grad_(True)
         x = h
+        if overlapped:
+            reducer.zero()
         for layer in layers:
             x = layer(x, token_type_ids=inp.token_type_ids, position_ids=inp.position_ids,
                       padding_mask=inp.padding_mask)[0]
         loss = (x.float() * proj.float()).mean()
-        for p in params:
-            p.grad = None
+        if not overlapped:
+            for p in params:
+                p.grad = None
         loss.backward()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        reducer.reduce()
+        if overlapped:
+            reducer.finish()   # joins the side stream: what is left of the last layer's collective
+        else:
+            reducer.reduce()
         e1.record()
         ar_ms.append((e0, e1))
         return loss
@@ -607,6 +616,7 @@ def run_train(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    lo_mark = sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -616,11 +626,28 @@ def run_train(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(lo_mark, sampler.mark()) if rank == 0 else None
     ms_step = max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
     allreduce_ms = sum(a.elapsed_time(b_) for a, b_ in ar_ms) / max(len(ar_ms), 1)
+    # cost of the collective inside the step: the same step with the process group's collectives skipped
+    ms_nocomm = None
+    if world > 1 and overlapped:
+        saved = reducer._world
+        reducer._world = lambda: 1
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            step()
+        f1.record()
+        torch.cuda.synchronize()
+        ms_nocomm = max_over_ranks(f0.elapsed_time(f1), dev) / args.steps
+        reducer._world = saved
     if rank == 0:
-        total = tokens * world
+        total = total_tokens
         seq = 1 + nv + 2 + 1 + nt
         # algorithmic FLOP of one step: forward + recompute (up to the down projection) + input-gradient GEMMs
         # (base weights frozen) + LoRA forward/dgrad/wgrad + attention forward x2 and backward (5 GEMM-equivalents
@@ -633,21 +660,143 @@ def run_train(args):
         flop = args.layers * ((g_fwd + lora_f) + rec * (g_fwd - g_down + lora_f) + (g_fwd + lora_f) + 2 * lora_f
                               + (1 + rec) * attn_f + 2.5 * attn_f)
         pk = peaks()
+        exposed = None if ms_nocomm is None else ms_step - ms_nocomm
+        busbw = None
+        if world > 1:  # ring all-reduce moves 2 (N-1)/N of the buffer per rank
+            t = (exposed if exposed and exposed > 0 else allreduce_ms) / 1e3
+            busbw = reducer.nbytes * 2 * (world - 1) / world / max(t, 1e-9) / 1e9
         emit(json.dumps({
             "metric": "visual-expert LoRA train tokens/s", "value": total / (ms_step / 1e3), "unit": "tokens/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": dict(config_dict(args, tokens), lora_r=r, lora_dropout=args.lora_dropout,
                            recompute=bool(args.recompute),
                            mode=("train: fwd + recompute + bwd + LoRA-grad allreduce" if args.recompute else
-                                 "train: fwd (activations kept in HBM) + bwd + LoRA-grad allreduce")),
+                                 "train: fwd (activations kept in HBM) + bwd + LoRA-grad allreduce"),
+                           allreduce=("per-layer NCCL AVG issued from the layer's backward on a side stream; grads are "
+                                      "views of the flat bucket" if overlapped else "post-backward, packed (round 1)")),
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
-            "allreduce_ms": allreduce_ms, "allreduce_bytes": reducer.nbytes, "trainable_params": reducer.flat.numel(),
+            "allreduce_tail_ms": allreduce_ms, "allreduce_bytes": reducer.nbytes,
+            "ms_per_step_without_collectives": ms_nocomm, "allreduce_exposed_ms": exposed,
+            "allreduce_busbw_gbs_over_exposed_time": busbw,
+            "trainable_params": (reducer.acc if overlapped else reducer.flat).numel(),
             "gpu_launches": launches, "clocks": clocks, "kernels": kernels,
             "step_tflops_per_gpu": flop / (ms_step / 1e3) / 1e12,
-            "step_frac_of_bf16_peak": flop / (ms_step / 1e3) / 1e12 / pk["bf16_tflops"], "peaks": pk,
+            "step_frac_of_bf16_peak": flop / (ms_step / 1e3) / 1e12 / pk["bf16_tflops"],
+            "step_frac_of_bf16_sustained": flop / (ms_step / 1e3) / 1e12 / (pk.get("bf16_tflops_sustained") or pk["bf16_tflops"]),
+            "peaks": pk,
             "note": "forward, recompute and backward all run on the native sm_100a kernels (K1-K9); only the "
                     "LoRA-gradient all-reduce is NCCL",
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_decode(args):
+    """generation after a prefill.  One step = ONE new token for every sample of the batch through the
+    full stack (q_len == 1: language-expert weights only, K / V appended in place by the QKV epilogue, K4d over the
+    pre-allocated cache, final norm), replayed as one CUDA graph per token (kv_cache.StaticKVCache).  HBM-bound: per
+    step every language-expert weight (404.75 MB per layer) and the live K / V of every sample are read once."""
+    import torch.distributed as dist
+    from types import SimpleNamespace
+    from mmmm_b200 import instrument
+    from mmmm_b200.kv_cache import StaticKVCache
+    from mmmm_b200.modeling_cogvlm import decoder_stack_forward
+    from mmmm_b200.plan import GLOBAL_PLAN_CACHE
+    from mmmm_b200.sharding import max_over_ranks
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nl, b, gb, nv, nt, scaling, _ = workload(args)
+    layers = [make_gpu_layer(dev, args.lora, seed=i) for i in range(nl)]
+    model = SimpleNamespace(layers=layers, norm=make_norm(dev))
+    host, _ = make_shard_inputs(args)
+    inp = host.to(dev)
+    L = inp.padding_mask.shape[1]
+    n_new = args.warmup + args.steps + 8
+    cache = StaticKVCache(nl, b, HEADS, L + n_new, dev)
+    with torch.no_grad():
+        plan = GLOBAL_PLAN_CACHE.get(inp.token_type_ids, inp.padding_mask)
+        decoder_stack_forward(layers, model.norm, inp.hidden_states, plan, inp.position_ids, use_cache=True,
+                              kv_out=cache.layers)
+    cache.start(inp.padding_mask)
+    x = torch.randn(b, 1, H, device=dev).to(torch.bfloat16)
+    x_host, out_host = x.cpu().pin_memory(), torch.empty(b, 1, H, dtype=torch.bfloat16).pin_memory()
+    pos = inp.position_ids.max(dim=1, keepdim=True).values + 1
+    state = {"i": 0}
+
+    def step():
+        out = cache.step(model, x, pos + state["i"], graph=bool(args.graph))
+        state["i"] += 1
+        return out
+
+    def step_e2e():  # host token embedding in, host hidden state out, every step (what a sampling loop on the host does)
+        x.copy_(x_host, non_blocking=True)
+        out_host.copy_(step(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    kernels = None
+    with torch.no_grad():
+        instrument.reset()
+        cache.step(model, x, pos, graph=False)       # one eager step: launch count + per-kernel times
+        launches_per_step = instrument.launches()
+        state["i"] = 1
+        kernels = instrument.profile(lambda: cache.step(model, x, pos + 1, graph=False) and None, iters=2) if rank == 0 else None
+        state["i"] = 4 if rank == 0 else 1
+        cache.host_len = L + state["i"]
+        cache.past_len.fill_(cache.host_len)
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lo = sampler.mark()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n_timed = args.steps - 2
+    for _ in range(n_timed):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop(lo, sampler.mark()) if rank == 0 else None
+    ms_step = max_over_ranks(e0.elapsed_time(e1), dev) / n_timed
+    t0 = time.perf_counter()
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3, dev) / 2
+    if rank == 0:
+        pk = peaks()
+        kv_len = L + args.warmup + args.steps // 2
+        w_bytes = nl * 2 * (H * 3 * H + H * H + 3 * H * I)           # language expert, bf16
+        kv_bytes = nl * 2 * b * kv_len * H * 2                        # K and V of every sample, once per layer
+        gbs = (w_bytes + kv_bytes) / (ms_step / 1e3) / 1e9
+        total = b * world
+        emit(json.dumps({
+            "metric": "visual-expert decode tokens/s", "value": total / (ms_step / 1e3), "unit": "tokens/s",
+            "n_gpus": world, "steps": n_timed, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"decode after a {args.workload} prefill: {nl} layers, batch {b} per GPU, ~{kv_len} cached "
+                                   f"positions per sample, 1 new token per sample per step",
+                       "layers": nl, "samples_per_gpu": b, "cuda_graph": bool(args.graph), "lora_r": args.lora,
+                       "l2": "per-step weights (12.95 GB) exceed the 126 MB L2; no flush needed"},
+            "roofline": {"kernel": "whole decode step (weight + KV streaming)", "bound": "hbm", "achieved": gbs,
+                         "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": None,
+                         "bytes_per_step": w_bytes + kv_bytes, "weight_bytes": w_bytes, "kv_bytes": kv_bytes,
+                         "peak_source": pk["source"]},
+            "kernels": kernels,
+            "e2e": {"value": total / (ms_e2e / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": b * H * 2,
+                    "d2h_bytes_per_step": b * H * 2, "ms_per_step": ms_e2e,
+                    "how": "host embedding in, graph replay, host hidden state out, synchronised every token"},
+            "gpu_launches": launches_per_step * n_timed, "launches_per_step": launches_per_step, "clocks": clocks,
+            "peaks": pk,
         }))
     if world > 1:
         dist.destroy_process_group()
@@ -781,7 +930,10 @@ def main():
     ap.add_argument("--lora-dropout", type=float, default=0.0, help="--train: lora_dropout (the reference uses 0.05)")
     ap.add_argument("--recompute", type=int, default=1, help="--train: 1 = checkpoint each layer like the reference "
                     "(save the input, recompute in backward); 0 = keep the activations in HBM (no recompute pass)")
+    ap.add_argument("--allreduce", default="overlap", choices=["overlap", "post"], help="--train: per-layer all-reduce "
+                    "overlapped with the backward (default) or the round-1 post-backward reducer")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the forward as one CUDA graph (default), 0: eager")
+    ap.add_argument("--decode", action="store_true", help="SURVEY 8(f)-2: time graphed decode steps after a prefill")
     ap.add_argument("--vision", action="store_true", help="SURVEY 8(f)-4: time the EVA2-CLIP-E vision encoder instead")
     ap.add_argument("--vision-layers", type=int, default=63)
     args = ap.parse_args()
@@ -790,6 +942,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.decode:
+        run_decode(args)
     elif args.vision:
         run_vision(args)
     elif args.train:

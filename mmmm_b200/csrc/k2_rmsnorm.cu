@@ -13,14 +13,16 @@ namespace vex {
 constexpr int K2_WARPS = 8;
 
 template <int NCHUNK>  // H = NCHUNK * 256
-__global__ void __launch_bounds__(K2_WARPS * 32, 3)
+__global__ void __launch_bounds__(K2_WARPS * 32, 2)
     k2_rmsnorm(const __nv_bfloat16* __restrict__ x, const void* __restrict__ weight, int weight_is_fp32, float eps,
                const int32_t* __restrict__ row_src, const int32_t* __restrict__ row_dst,
                const int32_t* __restrict__ n_rows_ptr, __nv_bfloat16* __restrict__ y, int rows_cap) {
   constexpr int H = NCHUNK * 256;
-  // WPR warps share one row so that a lane holds at most 8 x 16 bytes of it (32 registers): 24 warps per SM
-  // stay resident with every load of their row slice in flight (the 1-warp-per-row version needed 230
-  // registers and ran 8 warps per SM at 68 % of the HBM roofline)
+  // WPR warps share one row so that a lane holds at most 8 x 16 bytes of it (32 registers).  The NEXT row's slice is
+  // loaded into a second register set before the current row is reduced and stored (software pipelining): a warp has
+  // loads in flight during its shuffle / barrier / store phase too, and the dependent row-index -> row-data latency of
+  // the gather is hidden behind the previous row (round 1: 0.70 of the HBM roofline at c2, loads only in flight during
+  // ~40 % of a warp's iteration).
   constexpr int WPR = NCHUNK > 8 ? 2 : 1;   // warps per row
   constexpr int CPL = NCHUNK / WPR;         // 16-byte chunks per lane
   constexpr int ROWS = K2_WARPS / WPR;      // rows per CTA iteration
@@ -36,17 +38,30 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 3)
   const int warp = threadIdx.x >> 5;
   const int slot = warp / WPR, half = warp % WPR;
   const int n_rows = min(*n_rows_ptr, rows_cap);
+  const int stride = gridDim.x * ROWS;
+
+  auto load_row = [&](int r, uint4 (&dst)[CPL]) {
+    const int src = row_src ? row_src[r] : r;
+    const uint4* xp = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(src) * H) + half * CPL * 32;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) dst[i] = ld_stream(xp + i * 32 + lane);
+  };
+
+  uint4 nx[CPL];
+  {
+    const int r = blockIdx.x * ROWS + slot;
+    if (r < n_rows) load_row(r, nx);
+  }
   // trip count uniform per warp pair (both warps of a row take the pair barrier below)
-  for (int r0 = blockIdx.x * ROWS; r0 < n_rows; r0 += gridDim.x * ROWS) {
+  for (int r0 = blockIdx.x * ROWS; r0 < n_rows; r0 += stride) {
     const int r = r0 + slot;
     const bool live = r < n_rows;
     uint4 v[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) v[i] = nx[i];
+    if (r + stride < n_rows) load_row(r + stride, nx);  // prefetch: in flight during the reduction and the stores
     float ss = 0.f;
     if (live) {
-      const int src = row_src ? row_src[r] : r;
-      const uint4* xp = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(src) * H) + half * CPL * 32;
-#pragma unroll
-      for (int i = 0; i < CPL; ++i) v[i] = ld_stream(xp + i * 32 + lane);
 #pragma unroll
       for (int i = 0; i < CPL; ++i) {
         const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
@@ -98,7 +113,7 @@ extern "C" int vex_rmsnorm_gather(const void* x, const void* weight, int weight_
   if (H % 256 != 0 || H <= 0 || H > 4096) return VEX_E_UNSUPPORTED;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // persistent-ish grid: every CTA stages the weight vector once, then strides over rows
-  const int grid = std::min(vex::ceil_div(rows_cap, vex::K2_WARPS / 2), 148 * 3);
+  const int grid = std::min(vex::ceil_div(rows_cap, vex::K2_WARPS / 2), 148 * 2);
   auto xp = static_cast<const __nv_bfloat16*>(x);
   auto yp = static_cast<__nv_bfloat16*>(y);
 #define VEX_K2_CASE(NC)                                                                                        \

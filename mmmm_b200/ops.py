@@ -257,12 +257,12 @@ def grouped_gemm(a: torch.Tensor, w_vision: torch.Tensor, w_language: Optional[t
 
 
 @torch.library.custom_op("vex::grouped_gemm_fused", mutates_args=("out", "kv_k", "kv_v"))
-def grouped_gemm_fused(a: torch.Tensor, w: List[Optional[torch.Tensor]], out: torch.Tensor, counts: torch.Tensor,
-                       mode: int, row_map: Optional[torch.Tensor], residual: Optional[torch.Tensor],
-                       lora_t: List[Optional[torch.Tensor]], lora_b: List[Optional[torch.Tensor]], lora_r: int,
-                       rope: List[torch.Tensor], rope_cols: int, single_expert: bool, alpha: float,
-                       kv_k: Optional[torch.Tensor] = None, kv_v: Optional[torch.Tensor] = None, kv_seq_len: int = 0,
-                       kv_pos: Optional[torch.Tensor] = None) -> None:
+def _grouped_gemm_fused(a: torch.Tensor, w: List[Optional[torch.Tensor]], out: torch.Tensor, counts: torch.Tensor,
+                        mode: int, row_map: Optional[torch.Tensor], residual: Optional[torch.Tensor],
+                        lora_t: List[Optional[torch.Tensor]], lora_b: List[Optional[torch.Tensor]], lora_r: int,
+                        rope: List[torch.Tensor], rope_cols: int, single_expert: bool, alpha: float,
+                        kv_k: Optional[torch.Tensor], kv_v: Optional[torch.Tensor], kv_seq_len: int,
+                        kv_pos: Optional[torch.Tensor]) -> None:
     """K3 with a fused epilogue (``mode`` = EPI_*), LoRA K-extension and scatter; see ``grouped_gemm_raw``.
     ``kv_k`` / ``kv_v`` [B, heads, capacity, 128]: KV-cache second output of EPI_ROPE (prefill: ``kv_seq_len`` = L;
     decode: 1 and ``kv_pos`` = device counter of cached positions)."""
@@ -270,6 +270,14 @@ def grouped_gemm_fused(a: torch.Tensor, w: List[Optional[torch.Tensor]], out: to
                      lora_r=lora_r, rope=tuple(rope) if len(rope) else None, rope_cols=rope_cols,
                      single_expert=single_expert, alpha=alpha,
                      kv=None if kv_k is None else (kv_k, kv_v, kv_seq_len, kv_pos))
+
+
+def grouped_gemm_fused(a, w, out, counts, mode, row_map, residual, lora_t, lora_b, lora_r, rope, rope_cols,
+                       single_expert, alpha, kv_k=None, kv_v=None, kv_seq_len=0, kv_pos=None) -> None:
+    """``vex::grouped_gemm_fused`` with the KV-cache arguments defaulted (the registered op takes every argument
+    positionally: torch.library tracks mutated arguments by position)."""
+    _grouped_gemm_fused(a, w, out, counts, mode, row_map, residual, lora_t, lora_b, lora_r, rope, rope_cols,
+                        single_expert, alpha, kv_k, kv_v, kv_seq_len, kv_pos)
 
 
 @torch.library.custom_op("vex::grouped_gemm_dgrad", mutates_args=("out",))
@@ -682,6 +690,6 @@ def lora_wgrad(x: torch.Tensor, y: torch.Tensor, out_vision: Optional[torch.Tens
     _lib.check(rc, "vex_lora_wgrad")
 
 
-for _op in (attention_decode_cache, advance_counter, kv_clear_padded, linear_bias_act, attention_blockdiag, layernorm, patchify, maxpool_tokens, scatter_rows, label_rows, lm_head_ce_forward, lm_head_ce_backward, dropout_rows, attention_train, attention_backward, lora_wgrad, gather_rows, silu_mul_backward, rmsnorm_backward, grouped_gemm_dgrad, attention_decode, partition, rmsnorm_gather, silu_mul, residual_scatter, copy_padded_rows, grouped_gemm, grouped_gemm_fused,
+for _op in (attention_decode_cache, advance_counter, kv_clear_padded, linear_bias_act, attention_blockdiag, layernorm, patchify, maxpool_tokens, scatter_rows, label_rows, lm_head_ce_forward, lm_head_ce_backward, dropout_rows, attention_train, attention_backward, lora_wgrad, gather_rows, silu_mul_backward, rmsnorm_backward, grouped_gemm_dgrad, attention_decode, partition, rmsnorm_gather, silu_mul, residual_scatter, copy_padded_rows, grouped_gemm, _grouped_gemm_fused,
             attention):
     _op.register_fake(lambda *a, **k: None)

@@ -554,8 +554,17 @@ def test_k4_attention_vs_oracle(lens, impl, monkeypatch):
 
 def _baseline_attention(impl):
     """The superseded attention kernels live in libvex_baselines.so (csrc/baselines/), outside the product library."""
-    from tests.helpers import baselines
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "vex_test_baselines", os.path.join(os.path.dirname(os.path.abspath(__file__)), "helpers", "baselines.py"))
+    baselines = _BASELINES.setdefault("mod", importlib.util.module_from_spec(spec))
+    if not hasattr(baselines, "attention"):
+        spec.loader.exec_module(baselines)
     return lambda *a: baselines.attention(impl, *a)
+
+
+_BASELINES = {}
 
 
 @pytest.mark.parametrize("impl", ["tc3", "tc2"])

@@ -52,6 +52,27 @@ def _worker(rank, world, port, tmp):
         red.reduce()
         mean = sum(range(1, world + 1)) / world
         assert torch.equal(ps[0].grad, torch.full((3, 4), mean)) and torch.equal(ps[1].grad, torch.arange(5.0) * mean)
+        # the overlapped variant: kernels accumulate into a layer's segment of the flat fp32 buffer, the segment is
+        # all-reduced when the layer's backward is done, p.grad is a bucket view (no pack / unpack)
+        from mmmm_b200.training import BucketedGradReducer
+        for dtype in (torch.float32, torch.bfloat16):
+            mods = [torch.nn.Linear(3, 5).to(dtype), torch.nn.Linear(2, 2, bias=False).to(dtype)]
+            mods[0].bias.requires_grad_(False)
+            br = BucketedGradReducer(mods)
+            assert br.comm_dtype == dtype and br.acc.dtype == torch.float32
+            for step in range(2):
+                br.zero()
+                for li in (1, 0):                                   # backward order
+                    for p in mods[li].parameters():
+                        if p.requires_grad:
+                            br.accumulator(p).add_(float(rank + 1) * (li + 1))   # what K8 / K7 would accumulate
+                    br.layer_done(mods[li])
+                br.finish()
+                for li in (0, 1):
+                    wt = mods[li].weight
+                    assert wt.grad.dtype == dtype and torch.equal(wt.grad, torch.full_like(wt, mean * (li + 1)))
+                    assert wt.grad.data_ptr() == br.comm[br.slots[id(wt)][0]:].data_ptr()   # a view, not a copy
+                assert mods[0].bias.grad is None and not br.owns(mods[0].bias)
         dist.barrier()
         if rank == 0:
             (full,) = O.decoder_layer(w, inp.hidden_states, inp.token_type_ids, inp.position_ids, inp.padding_mask,

@@ -42,7 +42,8 @@ def bench_attention(B=8, nv=1225, nt=256, heads=32, only=None):
         if impl == "tc3":
             attend = ops.attention
         else:  # superseded kernels: libvex_baselines.so (csrc/baselines/), not part of the product library
-            from tests.helpers import baselines
+            sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "helpers"))
+            import baselines
             attend = lambda *a, _i=impl.split("-")[0]: baselines.attention(_i, *a)
         try:
             ms = timeit(lambda: attend(qkv, plan.cu_seqlens, B, L, heads, plan.token_to_sorted, out, 128 ** -0.5))
