@@ -746,7 +746,7 @@ def run_decode(args):
         cache.step(model, x, pos, graph=False)       # one eager step: launch count + per-kernel times
         launches_per_step = instrument.launches()
         state["i"] = 1
-        kernels = instrument.profile(lambda: cache.step(model, x, pos + 1, graph=False) and None, iters=2) if rank == 0 else None
+        kernels = instrument.profile(lambda: (cache.step(model, x, pos + 1, graph=False), None)[1], iters=2) if rank == 0 else None
         state["i"] = 4 if rank == 0 else 1
         cache.host_len = L + state["i"]
         cache.past_len.fill_(cache.host_len)

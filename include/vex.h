@@ -188,6 +188,15 @@ typedef struct vexGemmArgs {
 
 int vex_grouped_gemm(const vexGemmArgs* args, vexStream stream);
 
+/* K12 -- the skinny form of vex_grouped_gemm for a decode step (q_len == 1): rows_cap <= 32 live rows
+ * (= the batch; `counts` is not read), single_expert = 1 (get_expert_mask's L == 1 rule :67: every token goes to the
+ * language expert), forward form only.  HBM-bound by design: the weights stream from global memory straight into
+ * mma.sync fragments, 16 output features per CTA, K interleaved over 8 warps.  Modes VEX_EPI_PLAIN / RESIDUAL / SWIGLU /
+ * ROPE (with the KV-cache append, kv_seq_len = 1) and the LoRA K-extension (lora_r % 32 == 0); row_map, bias, act are
+ * not supported (VEX_E_UNSUPPORTED -- callers fall back to vex_grouped_gemm).  K % 32 == 0, N % 16 == 0 (N % 128 == 0
+ * for ROPE); position_ids is indexed by batch row. */
+int vex_decode_gemm(const vexGemmArgs* args, vexStream stream);
+
 /* K4 -- causal block-diagonal (varlen) flash attention over the token-order QKV buffer.
  * Replaces attention_fn's prefill branch (:106-128): per sample, token i attends to tokens j <= i of
  * the same sample (causality by token rank, not position_ids), scale = 128^-0.5, fp32 softmax.

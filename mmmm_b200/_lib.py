@@ -23,7 +23,7 @@ SYMBOLS = [
     "vex_attention", "vex_attention_decode", "vex_gather_rows", "vex_silu_mul_backward", "vex_rmsnorm_backward",
     "vex_lora_wgrad", "vex_attention_lse", "vex_attention_backward", "vex_dropout_rows", "vex_label_rows", "vex_ce_reduce",
     "vex_attention_blockdiag", "vex_layernorm", "vex_patchify", "vex_maxpool_tokens", "vex_scatter_rows",
-    "vex_attention_decode_cache", "vex_advance_counter", "vex_kv_clear_padded",
+    "vex_attention_decode_cache", "vex_advance_counter", "vex_kv_clear_padded", "vex_decode_gemm",
 ]
 
 
@@ -85,6 +85,7 @@ def lib() -> C.CDLL:
         L.vex_residual_scatter.argtypes = [p, p, p, p, p, i32, i32, p]
         L.vex_copy_padded_rows.argtypes = [p, p, p, i32, i32, p]
         L.vex_grouped_gemm.argtypes = [C.POINTER(GemmArgs), p]
+        L.vex_decode_gemm.argtypes = [C.POINTER(GemmArgs), p]
         L.vex_attention.argtypes = [p, p, i32, i32, i32, p, p, f32, p]
         L.vex_attention_decode.argtypes = [p, i64, p, p, p, p, i32, i32, i32, f32, p]
         L.vex_gather_rows.argtypes = [p, p, p, p, i32, i32, p]

@@ -1,0 +1,317 @@
+// K12 -- skinny GEMM of the decode step (q_len == 1): out[b, n] = sum_k x[b, k] * W[n, k] for a batch of at most 32
+// rows -- the five nn.Linear calls of a generation step through the LANGUAGE expert (get_expert_mask's L == 1 rule,
+// modeling_cogvlm.py:67; Linears :244-245, :278-279, MLP.forward :54-56) with the same fused epilogues as K3: rotary +
+// KV-cache append (:188-193, :258-262), residual add (:321, :330), SiLU-gate (:55), LoRA K-extension.
+//
+// This is an HBM-BOUND kernel (every weight is read once per token; 404.75 MB per layer), not a tensor-throughput one:
+// a 128 x 256 tcgen05 tile over 8 live rows leaves most SMs idle for the small-N projections (dense / down: 16 tiles),
+// which is what round 2 measured for the decode step on K3 (1.8 TB/s).  Design for bandwidth instead:
+//   * one CTA (8 warps) per group of 16 output features (and their partner tile: up_proj for SwiGLU, column j + 64
+//     for rotary), 256 ... 768 CTAs per projection -- every SM streams;
+//   * the K dimension is interleaved over the 8 warps in 32-element chunks; a thread loads 16 bytes (8 consecutive k)
+//     of weight row g and of row g + 8 straight from global memory into the A fragment of mma.sync.m16n8k16 -- the k
+//     order inside a chunk is permuted identically for the B fragment, so no shuffle / shared-memory staging of the
+//     weights is needed and every load is a full 16-byte vector (4 chunks = 8 loads per thread in flight);
+//   * the batch is the N dimension of the MMA (n8 tiles, 1 ... 4 of them); x is read through the read-only path
+//     (L1-resident: 8 x 4096 x 2 B = 64 KB, shared by every CTA on the SM);
+//   * partial sums of the 8 warps are reduced through shared memory, then 16 x B outputs take the epilogue.
+// mma.sync is used on purpose: the math is 0.1 % of the tensor peak, the operand path (global -> registers) is what
+// matters, and tcgen05 would force the weights through shared memory.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace vex {
+
+constexpr int DG_THREADS = 256;
+constexpr int DG_WARPS = 8;
+constexpr int DG_UNROLL = 4;  // 32-element k chunks per load batch
+
+struct DecGemm {
+  const __nv_bfloat16* x;     // [B, K]
+  const __nv_bfloat16* w[2];  // [N, K]; w[1] = up_proj (SWIGLU) or nullptr
+  const __nv_bfloat16* lt[2];  // LoRA T = s * x . A^T  [B, r] per half, or nullptr
+  const __nv_bfloat16* lb[2];  // lora_B [N, r] per half
+  __nv_bfloat16* out;
+  const __nv_bfloat16* residual;
+  const __nv_bfloat16* rope_cos;
+  const __nv_bfloat16* rope_sin;
+  const int64_t* position_ids;
+  __nv_bfloat16* kv_k;
+  __nv_bfloat16* kv_v;
+  const int32_t* kv_pos;
+  int64_t ldx, ldw, ldt, ldo;
+  int B, N, K, mode, lora_r, rope_len, rope_cols, kv_cap;
+  float alpha;
+};
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+// accumulates  c[tile][nb] += W_tile[16, k-range] . x[nb*8 .., k-range]^T  over the chunks this warp owns
+template <int NB, int TILES>
+__device__ __forceinline__ void accumulate(float (&c)[2][NB][4], const __nv_bfloat16* const* wrow_lo,
+                                           const __nv_bfloat16* const* wrow_hi, const __nv_bfloat16* const* xrow,
+                                           const bool* xlive, int K, int warp, int t) {
+  const int nchunks = K >> 5;
+  for (int i0 = warp; i0 < nchunks; i0 += DG_WARPS * DG_UNROLL) {
+    uint4 alo[DG_UNROLL][TILES], ahi[DG_UNROLL][TILES];
+#pragma unroll
+    for (int u = 0; u < DG_UNROLL; ++u) {
+      const int i = i0 + u * DG_WARPS;
+      const int kb = (i << 5) + 8 * t;
+#pragma unroll
+      for (int tl = 0; tl < TILES; ++tl) {
+        if (i < nchunks) {
+          alo[u][tl] = ld_stream(reinterpret_cast<const uint4*>(wrow_lo[tl] + kb));
+          ahi[u][tl] = ld_stream(reinterpret_cast<const uint4*>(wrow_hi[tl] + kb));
+        } else {
+          alo[u][tl] = make_uint4(0, 0, 0, 0);
+          ahi[u][tl] = make_uint4(0, 0, 0, 0);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < DG_UNROLL; ++u) {
+      const int i = i0 + u * DG_WARPS;
+      if (i >= nchunks) break;
+      const int kb = (i << 5) + 8 * t;
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        uint4 xb = make_uint4(0, 0, 0, 0);
+        if (xlive[nb]) xb = __ldg(reinterpret_cast<const uint4*>(xrow[nb] + kb));
+#pragma unroll
+        for (int tl = 0; tl < TILES; ++tl) {
+          mma_bf16_16816(c[tl][nb], alo[u][tl].x, ahi[u][tl].x, alo[u][tl].y, ahi[u][tl].y, xb.x, xb.y);
+          mma_bf16_16816(c[tl][nb], alo[u][tl].z, ahi[u][tl].z, alo[u][tl].w, ahi[u][tl].w, xb.z, xb.w);
+        }
+      }
+    }
+  }
+}
+
+template <int NB, int TILES>
+__global__ void __launch_bounds__(DG_THREADS, 2) k12_decode_gemm(const DecGemm p) {
+  __shared__ float red[DG_WARPS][TILES][NB][32][4];   // per-warp partial fragments
+  __shared__ float fin[TILES][NB * 8][16];            // reduced [tile][batch row][feature]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int task = blockIdx.x;
+  // first output feature of the two tiles
+  int n_a, n_b;
+  if (p.mode == VEX_EPI_ROPE) {   // (j, j + 64) inside one head of 128
+    n_a = (task >> 2) * 128 + (task & 3) * 16;
+    n_b = n_a + 64;
+  } else {
+    n_a = n_b = task * 16;
+  }
+  const __nv_bfloat16* wa = p.w[0];
+  const __nv_bfloat16* wb = (p.mode == VEX_EPI_SWIGLU) ? p.w[1] : p.w[0];
+  float c[2][NB][4];
+#pragma unroll
+  for (int tl = 0; tl < 2; ++tl)
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) c[tl][nb][r] = 0.f;
+
+  const __nv_bfloat16* xrow[NB];
+  bool xlive[NB];
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) {
+    xlive[nb] = nb * 8 + g < p.B;
+    xrow[nb] = p.x + static_cast<int64_t>(min(nb * 8 + g, p.B - 1)) * p.ldx;
+  }
+  {
+    const __nv_bfloat16* lo[2] = {wa + static_cast<int64_t>(n_a + g) * p.ldw, wb + static_cast<int64_t>(n_b + g) * p.ldw};
+    const __nv_bfloat16* hi[2] = {wa + static_cast<int64_t>(n_a + g + 8) * p.ldw,
+                                  wb + static_cast<int64_t>(n_b + g + 8) * p.ldw};
+    accumulate<NB, TILES>(c, lo, hi, xrow, xlive, p.K, warp, t);
+  }
+  if (p.lora_r > 0) {  // K-extension: += T . lora_B^T  (r is a multiple of 32 here; r = 64 -> two chunks, warps 0 and 1)
+    const __nv_bfloat16* trow[NB];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) trow[nb] = p.lt[0] + static_cast<int64_t>(min(nb * 8 + g, p.B - 1)) * p.ldt;
+    const __nv_bfloat16* lo[2] = {p.lb[0] + static_cast<int64_t>(n_a + g) * p.lora_r,
+                                  (p.mode == VEX_EPI_SWIGLU ? p.lb[1] : p.lb[0]) + static_cast<int64_t>(n_b + g) * p.lora_r};
+    const __nv_bfloat16* hi[2] = {lo[0] + 8 * static_cast<int64_t>(p.lora_r), lo[1] + 8 * static_cast<int64_t>(p.lora_r)};
+    if (p.mode == VEX_EPI_SWIGLU) {
+      // gate and up have their own T: accumulate the two tiles separately
+      float cg[2][NB][4], cu[2][NB][4];
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) cg[0][nb][r] = cg[1][nb][r] = cu[0][nb][r] = cu[1][nb][r] = 0.f;
+      const __nv_bfloat16* urow[NB];
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) urow[nb] = p.lt[1] + static_cast<int64_t>(min(nb * 8 + g, p.B - 1)) * p.ldt;
+      const __nv_bfloat16* lo_g[2] = {lo[0], lo[0]};
+      const __nv_bfloat16* hi_g[2] = {hi[0], hi[0]};
+      const __nv_bfloat16* lo_u[2] = {lo[1], lo[1]};
+      const __nv_bfloat16* hi_u[2] = {hi[1], hi[1]};
+      accumulate<NB, 1>(cg, lo_g, hi_g, trow, xlive, p.lora_r, warp, t);
+      accumulate<NB, 1>(cu, lo_u, hi_u, urow, xlive, p.lora_r, warp, t);
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          c[0][nb][r] += cg[0][nb][r];
+          if (TILES == 2) c[1][nb][r] += cu[0][nb][r];
+        }
+    } else {
+      accumulate<NB, TILES>(c, lo, hi, trow, xlive, p.lora_r, warp, t);
+    }
+  }
+
+  // ---- reduce the 8 warps' fragments ----
+#pragma unroll
+  for (int tl = 0; tl < TILES; ++tl)
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb)
+      *reinterpret_cast<float4*>(red[warp][tl][nb][lane]) = make_float4(c[tl][nb][0], c[tl][nb][1], c[tl][nb][2], c[tl][nb][3]);
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < TILES * NB * 128; idx += DG_THREADS) {
+    const int r = idx & 3, L = (idx >> 2) & 31, nb = (idx >> 7) % NB, tl = idx / (NB * 128);
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < DG_WARPS; ++w) s += red[w][tl][nb][L][r];
+    // fragment element -> (feature row, batch column): c0,c1 row g cols 2t,2t+1; c2,c3 row g+8
+    const int feat = (L >> 2) + ((r & 2) ? 8 : 0), brow = nb * 8 + 2 * (L & 3) + (r & 1);
+    fin[tl][brow][feat] = s;
+  }
+  __syncthreads();
+
+  // ---- epilogue: 16 features x B rows (x 2 tiles) ----
+  for (int idx = threadIdx.x; idx < p.B * 16; idx += DG_THREADS) {
+    const int b = idx >> 4, f = idx & 15;
+    const float va = fin[0][b][f];
+    const float vb = TILES == 2 ? fin[TILES - 1][b][f] : 0.f;
+    __nv_bfloat16* orow = p.out + static_cast<int64_t>(b) * p.ldo;
+    if (p.mode == VEX_EPI_PLAIN) {
+      orow[n_a + f] = __float2bfloat16_rn(va * p.alpha);
+    } else if (p.mode == VEX_EPI_RESIDUAL) {
+      const float r = __bfloat162float(p.residual[static_cast<int64_t>(b) * p.ldo + n_a + f]);
+      orow[n_a + f] = __float2bfloat16_rn(bf16r(va) + r);   // Linear output -> bf16, then the eager bf16 add
+    } else if (p.mode == VEX_EPI_SWIGLU) {
+      const float gt = bf16r(va), up = bf16r(vb);
+      orow[n_a + f] = __float2bfloat16_rn(bf16r(silu_f(gt)) * up);
+    } else {  // VEX_EPI_ROPE
+      float o1, o2;
+      if (n_a < p.rope_cols) {
+        const int64_t pz = p.position_ids[b];
+        const int pos = static_cast<int>(min(max(pz, int64_t(0)), int64_t(p.rope_len - 1)));
+        const int j = (n_a & 127) + f;  // column inside the head, < 64
+        const __nv_bfloat16* cr = p.rope_cos + static_cast<int64_t>(pos) * 128;
+        const __nv_bfloat16* sr = p.rope_sin + static_cast<int64_t>(pos) * 128;
+        const float x1 = bf16r(va), x2 = bf16r(vb);
+        o1 = bf16r(x1 * __bfloat162float(cr[j])) - bf16r(x2 * __bfloat162float(sr[j]));
+        o2 = bf16r(x2 * __bfloat162float(cr[j + 64])) + bf16r(x1 * __bfloat162float(sr[j + 64]));
+      } else {
+        o1 = va;
+        o2 = vb;
+      }
+      const __nv_bfloat16 h1 = __float2bfloat16_rn(o1), h2 = __float2bfloat16_rn(o2);
+      orow[n_a + f] = h1;
+      orow[n_b + f] = h2;
+      const int Hh = p.rope_cols >> 1;
+      if (p.kv_k != nullptr && n_a >= Hh) {  // K (post-rotary) and V heads are appended to the cache at *kv_pos
+        const bool is_v = n_a >= 2 * Hh;
+        const int head = (n_a - (is_v ? 2 * Hh : Hh)) >> 7;
+        const int l = p.kv_pos ? p.kv_pos[0] : 0;
+        if (l >= 0 && l < p.kv_cap) {
+          __nv_bfloat16* dst = (is_v ? p.kv_v : p.kv_k) +
+                               ((static_cast<int64_t>(b) * (Hh >> 7) + head) * p.kv_cap + l) * 128;
+          dst[(n_a & 127) + f] = h1;
+          dst[(n_b & 127) + f] = h2;
+        }
+      }
+    }
+  }
+}
+
+template <int NB, int TILES>
+static int launch_dg(const DecGemm& p, int tasks, cudaStream_t s) {
+  k12_decode_gemm<NB, TILES><<<tasks, DG_THREADS, 0, s>>>(p);
+  VEX_LAUNCH_CHECK();
+  return VEX_OK;
+}
+
+}  // namespace vex
+
+extern "C" int vex_decode_gemm(const vexGemmArgs* a, vexStream stream) {
+  using namespace vex;
+  if (!a || !a->a || !a->out || !a->w[0][0]) return VEX_E_INVALID;
+  if (a->rows_cap <= 0 || a->rows_cap > 32 || a->N <= 0 || a->K <= 0) return VEX_E_UNSUPPORTED;
+  if (!a->single_expert || a->w_transposed || a->bias || a->act != VEX_ACT_NONE || a->row_map) return VEX_E_UNSUPPORTED;
+  if (a->K % 32 != 0 || a->lda % 8 != 0 || a->ldw % 8 != 0 || a->N % 16 != 0) return VEX_E_UNSUPPORTED;
+  const int mode = a->mode;
+  if (mode != VEX_EPI_PLAIN && mode != VEX_EPI_RESIDUAL && mode != VEX_EPI_SWIGLU && mode != VEX_EPI_ROPE)
+    return VEX_E_UNSUPPORTED;
+  DecGemm p;
+  std::memset(&p, 0, sizeof(p));
+  p.x = static_cast<const __nv_bfloat16*>(a->a);
+  p.w[0] = static_cast<const __nv_bfloat16*>(a->w[0][0]);
+  p.w[1] = static_cast<const __nv_bfloat16*>(a->w[0][1]);
+  p.out = static_cast<__nv_bfloat16*>(a->out);
+  p.ldx = a->lda;
+  p.ldw = a->ldw;
+  p.ldo = a->ldo;
+  p.B = a->rows_cap;
+  p.N = a->N;
+  p.K = a->K;
+  p.mode = mode;
+  p.alpha = a->alpha;
+  if (mode == VEX_EPI_SWIGLU && !p.w[1]) return VEX_E_INVALID;
+  if (mode == VEX_EPI_RESIDUAL) {
+    if (!a->residual) return VEX_E_INVALID;
+    p.residual = static_cast<const __nv_bfloat16*>(a->residual);
+  }
+  if (a->lora_r > 0 && a->lora_b[0][0]) {
+    if (a->lora_r % 32 != 0 || !a->lora_t[0] || a->ldt % 8 != 0) return VEX_E_UNSUPPORTED;
+    if (mode == VEX_EPI_SWIGLU && (!a->lora_b[0][1] || !a->lora_t[1])) return VEX_E_UNSUPPORTED;
+    p.lora_r = a->lora_r;
+    p.ldt = a->ldt;
+    p.lt[0] = static_cast<const __nv_bfloat16*>(a->lora_t[0]);
+    p.lt[1] = static_cast<const __nv_bfloat16*>(a->lora_t[1]);
+    p.lb[0] = static_cast<const __nv_bfloat16*>(a->lora_b[0][0]);
+    p.lb[1] = static_cast<const __nv_bfloat16*>(a->lora_b[0][1]);
+  }
+  int tasks = a->N / 16;
+  if (mode == VEX_EPI_ROPE) {
+    if (!a->rope_cos || !a->rope_sin || !a->position_ids || a->rope_len <= 0) return VEX_E_INVALID;
+    if (a->rope_cols % 128 != 0 || a->N % 128 != 0) return VEX_E_UNSUPPORTED;
+    p.rope_cos = static_cast<const __nv_bfloat16*>(a->rope_cos);
+    p.rope_sin = static_cast<const __nv_bfloat16*>(a->rope_sin);
+    p.position_ids = a->position_ids;   // indexed by batch row (sorted_to_flat is the identity in a decode step)
+    p.rope_len = a->rope_len;
+    p.rope_cols = a->rope_cols;
+    if (a->kv_k || a->kv_v) {
+      if (!a->kv_k || !a->kv_v || a->kv_seq_len != 1 || a->kv_capacity <= 0) return VEX_E_INVALID;
+      if (a->N != 3 * (a->rope_cols / 2)) return VEX_E_UNSUPPORTED;
+      p.kv_k = static_cast<__nv_bfloat16*>(a->kv_k);
+      p.kv_v = static_cast<__nv_bfloat16*>(a->kv_v);
+      p.kv_pos = a->kv_pos;
+      p.kv_cap = a->kv_capacity;
+    }
+    tasks = a->N / 32;  // two tiles (j, j + 64) per task
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int nb = (a->rows_cap + 7) / 8;
+  const bool two = mode == VEX_EPI_SWIGLU || mode == VEX_EPI_ROPE;
+#define VEX_DG_CASE(NBV)                                                                       \
+  case NBV:                                                                                    \
+    return two ? launch_dg<NBV, 2>(p, tasks, s) : launch_dg<NBV, 1>(p, tasks, s);
+  switch (nb) {
+    VEX_DG_CASE(1) VEX_DG_CASE(2) VEX_DG_CASE(3) VEX_DG_CASE(4)
+    default:
+      return VEX_E_UNSUPPORTED;
+  }
+#undef VEX_DG_CASE
+}

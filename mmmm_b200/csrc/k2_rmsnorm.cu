@@ -30,10 +30,6 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 2)
   // weight vector staged once per CTA in shared memory (fp32): short-latency LDS in the per-row epilogue
   __shared__ __align__(16) float w_s[H];
   __shared__ float part[K2_WARPS];
-  for (int i = threadIdx.x; i < H; i += K2_WARPS * 32)
-    w_s[i] = weight_is_fp32 ? static_cast<const float*>(weight)[i]
-                            : __bfloat162float(static_cast<const __nv_bfloat16*>(weight)[i]);
-  __syncthreads();
   const int lane = lane_id();
   const int warp = threadIdx.x >> 5;
   const int slot = warp / WPR, half = warp % WPR;
@@ -50,8 +46,12 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 2)
   uint4 nx[CPL];
   {
     const int r = blockIdx.x * ROWS + slot;
-    if (r < n_rows) load_row(r, nx);
+    if (r < n_rows) load_row(r, nx);  // the first row is in flight while the weight vector is staged
   }
+  for (int i = threadIdx.x; i < H; i += K2_WARPS * 32)
+    w_s[i] = weight_is_fp32 ? static_cast<const float*>(weight)[i]
+                            : __bfloat162float(static_cast<const __nv_bfloat16*>(weight)[i]);
+  __syncthreads();
   // trip count uniform per warp pair (both warps of a row take the pair barrier below)
   for (int r0 = blockIdx.x * ROWS; r0 < n_rows; r0 += stride) {
     const int r = r0 + slot;

@@ -1017,6 +1017,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1)
   }
   tc_fence_before();
   cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  __syncthreads();     // redundant with the cluster barrier; compute-sanitizer's racecheck only models the CTA barrier as
+                       // ordering warp 2's tcgen05.alloc result (written to shared memory) before the reads below
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
 

@@ -4,56 +4,79 @@
 // Restates the generation branch of attention_fn (modeling_cogvlm.py:129-141) with its eager-bf16 rounding
 // points: the query is scaled in bf16 (`query_layer *= d ** -0.5`), scores are a bf16 einsum output, masked
 // positions become -inf, softmax runs in fp32 and is cast back to bf16 before the weighted sum over the values.
-// Cache layout is the reference's: k, v [B, heads, L, 128] (what prefill returns and torch.cat extends, :258-262).
+// Cache layout is the reference's: k, v [B, heads, capacity, 128] (what prefill returns and torch.cat extends, :258-262).
 //
-// One CTA per (head, sample), 128 threads.  Scores: one key per thread (16 x 16-byte loads of its row, fp32
-// dot product against the query held in shared memory).  Values: warp w takes keys w, w+4, ...; a lane owns
-// 4 of the 128 output dims (8-byte loads, a 256-byte row per warp instruction, coalesced).
+// Split-KV over a THREAD-BLOCK CLUSTER: the positions of one (sample, head) are split over the 1 / 2 / 4 / 8 CTAs of a
+// cluster (grid z), so that a small batch still fills the machine (8 samples x 32 heads are only 256 CTAs; round 2
+// measured 1.3 TB/s with one CTA per (sample, head)).  The softmax stays EXACT -- global max and sum are exchanged
+// through distributed shared memory before any probability is rounded to bf16 -- and the partial outputs are reduced
+// by the cluster's rank-0 CTA through DSMEM reads: no workspace in HBM, no second kernel.
+// Per CTA (256 threads): scores one key per thread (16 x 16-byte loads of its row, fp32 dot product against the query
+// held in shared memory); values: warp w takes keys w, w+8, ...; a lane owns 4 of the 128 output dims (8-byte loads,
+// a 256-byte row per warp instruction, coalesced).
+#include <cstring>
+
 #include "common.cuh"
 
 namespace vex {
 
-constexpr int DEC_THREADS = 128;
+constexpr int DEC_THREADS = 256;
+constexpr int DEC_WARPS = DEC_THREADS / 32;
+
+__device__ __forceinline__ float ld_dsmem_f32(const float* local, uint32_t rank) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(mapa_shared(smem_u32(local), rank)));
+  return v;
+}
 
 __device__ __forceinline__ float block_reduce_max(float v, float* red) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   if (lane_id() == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
-  v = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  float r = red[0];
+#pragma unroll
+  for (int i = 1; i < DEC_WARPS; ++i) r = fmaxf(r, red[i]);
   __syncthreads();
-  return v;
+  return r;
 }
 __device__ __forceinline__ float block_reduce_sum(float v, float* red) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   if (lane_id() == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
-  v = (red[0] + red[1]) + (red[2] + red[3]);
+  float r = 0.f;
+#pragma unroll
+  for (int i = 0; i < DEC_WARPS; ++i) r += red[i];
   __syncthreads();
-  return v;
+  return r;
 }
 
 // `kv_len` (device, may be null): number of cache positions already filled BEFORE this step; the step attends to
 // *kv_len + 1 positions (the current token's K / V were appended by the QKV epilogue).  Null = attend to all L.
 // Cache rows of one (sample, head) are `cap` positions apart (cap >= L: pre-allocated headroom); the mask row
-// stride is ld_mask.
+// stride is ld_mask.  `chunk_cap` = ceil(L_host / nsplit): the size of the dynamic score buffer.
 __global__ void __launch_bounds__(DEC_THREADS)
     k4_attention_decode(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k,
                         const __nv_bfloat16* __restrict__ v, const uint8_t* __restrict__ mask, int64_t ld_mask,
                         __nv_bfloat16* __restrict__ out, int heads, int L_host, int cap,
-                        const int32_t* __restrict__ kv_len, float scale) {
-  extern __shared__ float sc[];  // L scores, then probabilities
+                        const int32_t* __restrict__ kv_len, float scale, int chunk_cap) {
+  extern __shared__ float sc[];  // this CTA's scores, then exp(score - max)
   __shared__ float qs[128];
-  __shared__ float red[4];
-  __shared__ float osum[4][128];
+  __shared__ float red[DEC_WARPS];
+  __shared__ float xch[2];                  // local max, local sum: read by the peers through DSMEM
+  __shared__ float opart[128];              // this CTA's partial output: read by rank 0 through DSMEM
+  __shared__ float osum[DEC_WARPS][128];
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const uint32_t rank = blockIdx.z, nsplit = gridDim.z;  // cluster = the z extent of the grid
   const int L = kv_len ? min(max(kv_len[0] + 1, 1), L_host) : L_host;
-  qs[tid] = bf16r(__bfloat162float(q[static_cast<int64_t>(b) * ldq + h * 128 + tid]) * scale);
+  const int chunk = min((L + static_cast<int>(nsplit) - 1) / static_cast<int>(nsplit), chunk_cap);
+  const int l0 = min(static_cast<int>(rank) * chunk, L), l1 = min(l0 + chunk, L);
+  if (tid < 128) qs[tid] = bf16r(__bfloat162float(q[static_cast<int64_t>(b) * ldq + h * 128 + tid]) * scale);
   __syncthreads();
   const int64_t base = (static_cast<int64_t>(b) * heads + h) * cap;
   const uint8_t* mrow = mask + static_cast<int64_t>(b) * ld_mask;
 
   float mx = -INFINITY;
-  for (int l = tid; l < L; l += DEC_THREADS) {
+  for (int l = l0 + tid; l < l1; l += DEC_THREADS) {
     float s = -INFINITY;
     if (mrow[l]) {
       const uint4* kr = reinterpret_cast<const uint4*>(k + (base + l) * 128);
@@ -70,24 +93,35 @@ __global__ void __launch_bounds__(DEC_THREADS)
       }
       s = bf16r(acc);
     }
-    sc[l] = s;
+    sc[l - l0] = s;
     mx = fmaxf(mx, s);
   }
   mx = block_reduce_max(mx, red);
+  if (nsplit > 1) {  // exact softmax across the cluster: exchange the local maxima
+    if (tid == 0) xch[0] = mx;
+    cluster_sync_all();
+    for (uint32_t r = 0; r < nsplit; ++r) mx = fmaxf(mx, ld_dsmem_f32(&xch[0], r));
+  }
   float sum = 0.f;
-  for (int l = tid; l < L; l += DEC_THREADS) {
-    const float e = __expf(sc[l] - mx);
-    sc[l] = e;
+  for (int l = l0 + tid; l < l1; l += DEC_THREADS) {
+    const float e = __expf(sc[l - l0] - mx);
+    sc[l - l0] = e;
     sum += e;
   }
   sum = block_reduce_sum(sum, red);  // also orders the sc[] writes before the reads below
+  if (nsplit > 1) {
+    if (tid == 0) xch[1] = sum;
+    cluster_sync_all();
+    sum = 0.f;
+    for (uint32_t r = 0; r < nsplit; ++r) sum += ld_dsmem_f32(&xch[1], r);
+  }
   const float inv = 1.0f / sum;
 
   const int warp = tid >> 5, lane = tid & 31;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 4
-  for (int l = warp; l < L; l += 4) {
-    const float p = bf16r(sc[l] * inv);
+  for (int l = l0 + warp; l < l1; l += DEC_WARPS) {
+    const float p = bf16r(sc[l - l0] * inv);
     if (p != 0.f) {  // masked keys have p == 0 (their values are zeroed in the reference, :135)
       const uint2 u = *reinterpret_cast<const uint2*>(v + (base + l) * 128 + lane * 4);
       a0 = fmaf(p, bf16_lo(u.x), a0);
@@ -101,8 +135,21 @@ __global__ void __launch_bounds__(DEC_THREADS)
   osum[warp][lane * 4 + 2] = a2;
   osum[warp][lane * 4 + 3] = a3;
   __syncthreads();
-  const float o = (osum[0][tid] + osum[1][tid]) + (osum[2][tid] + osum[3][tid]);
-  out[static_cast<int64_t>(b) * heads * 128 + h * 128 + tid] = __float2bfloat16_rn(o);
+  float o = 0.f;
+  if (tid < 128) {
+#pragma unroll
+    for (int w = 0; w < DEC_WARPS; ++w) o += osum[w][tid];
+  }
+  if (nsplit > 1) {
+    if (tid < 128) opart[tid] = o;
+    cluster_sync_all();
+    if (rank == 0 && tid < 128) {
+      o = 0.f;
+      for (uint32_t r = 0; r < nsplit; ++r) o += ld_dsmem_f32(&opart[tid], r);
+    }
+  }
+  if (rank == 0 && tid < 128) out[static_cast<int64_t>(b) * heads * 128 + h * 128 + tid] = __float2bfloat16_rn(o);
+  if (nsplit > 1) cluster_sync_all();  // the peers' shared memory stays alive until rank 0 has read it
 }
 
 __global__ void k4_advance_counter(int32_t* p, int by) { if (threadIdx.x == 0) p[0] += by; }
@@ -114,19 +161,34 @@ static int launch_decode(const void* q, int64_t ldq, const void* k, const void* 
                          int64_t ld_mask, void* out, int B, int heads, int L, int cap, const int32_t* kv_len,
                          float scale, cudaStream_t s) {
   if (!q || !k || !v || !mask || !out || B <= 0 || heads <= 0 || L <= 0 || cap < L) return VEX_E_INVALID;
-  if (B > 65535 || L > DEC_MAX_L) return VEX_E_UNSUPPORTED;
+  if (B > 65535) return VEX_E_UNSUPPORTED;
+  // KV splits (= cluster size, a power of two <= 8): enough CTAs for ~4 per SM, chunks of at least 64 positions
+  int nsplit = 1;
+  while (nsplit < 8 && static_cast<int64_t>(B) * heads * nsplit < 4 * 148 && L / (2 * nsplit) >= 64) nsplit *= 2;
+  const int chunk_cap = ceil_div(L, nsplit);
+  if (chunk_cap > DEC_MAX_L) return VEX_E_UNSUPPORTED;
   static bool configured = false;
   if (!configured) {
     VEX_CUDA_TRY(cudaFuncSetAttribute(k4_attention_decode, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       DEC_MAX_L * 4));
     configured = true;
   }
-  dim3 grid(heads, B);
-  k4_attention_decode<<<grid, DEC_THREADS, L * sizeof(float), s>>>(
-      static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k),
-      static_cast<const __nv_bfloat16*>(v), mask, ld_mask, static_cast<__nv_bfloat16*>(out), heads, L, cap, kv_len,
-      scale);
-  VEX_LAUNCH_CHECK();
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(heads, B, nsplit);
+  cfg.blockDim = dim3(DEC_THREADS);
+  cfg.dynamicSmemBytes = static_cast<size_t>(chunk_cap) * sizeof(float);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = nsplit;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VEX_CUDA_TRY(cudaLaunchKernelEx(&cfg, k4_attention_decode, static_cast<const __nv_bfloat16*>(q), ldq,
+                                  static_cast<const __nv_bfloat16*>(k), static_cast<const __nv_bfloat16*>(v), mask,
+                                  ld_mask, static_cast<__nv_bfloat16*>(out), heads, L, cap, kv_len, scale, chunk_cap));
   return VEX_OK;
 }
 

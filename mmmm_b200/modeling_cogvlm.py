@@ -501,13 +501,17 @@ def _decode_constants(batch: int, device):
     return _decode_consts[key]
 
 
-def _lora_t_single(x: torch.Tensor, spec: LinearSpec, counts: torch.Tensor):
+def _lora_t_single(x: torch.Tensor, spec: LinearSpec, counts: torch.Tensor, skinny: bool = False):
     if spec.lora_A is None:
         return None, 0, None
     if spec.r % 8 or spec.r > 64:
         raise NotImplementedError(f"LoRA rank {spec.r}: the fused K-extension handles multiples of 8 up to 64")
     t = torch.empty(x.shape[0], spec.r, dtype=torch.bfloat16, device=x.device)
-    ops.grouped_gemm(x, _bf16(spec.lora_A), None, t, counts, None, float(spec.scaling))
+    if skinny and spec.r % 16 == 0:
+        ops.grouped_gemm_raw(x, [_bf16(spec.lora_A)], t, counts, ops.EPI_PLAIN, single_expert=True,
+                             alpha=float(spec.scaling), skinny=True)
+    else:
+        ops.grouped_gemm(x, _bf16(spec.lora_A), None, t, counts, None, float(spec.scaling))
     return t, spec.r, _bf16(spec.lora_B)
 
 
@@ -533,15 +537,23 @@ def decode_core(layer: "CogVLMDecoderLayer", hf: torch.Tensor, position_ids: tor
     gate_s, up_s = resolve_linear(mlp.language_mlp.gate_proj), resolve_linear(mlp.language_mlp.up_proj)
     down_s = resolve_linear(mlp.language_mlp.down_proj)
 
+    # batches of up to 32 rows take K12, the HBM-bound weight-streaming GEMM (a 128 x 256 tcgen05 tile over 8 live rows
+    # leaves most SMs idle on the small-N projections); larger batches and odd LoRA ranks stay on K3
+    skinny = B <= 32 and os.environ.get("VEX_DECODE_GEMM", "skinny") != "k3"
+
     def gemm(a, w, out, mode, spec_pair, residual=None, rope=(), rope_cols=0, kv=(None, None, 0, None)):
         t, r, lb = [None, None], 0, [None] * 4
+        sk = skinny and all(sp.r % 32 == 0 for sp in spec_pair)
         for h, sp in enumerate(spec_pair):
-            th, rh, bh = _lora_t_single(a, sp, counts)
+            th, rh, bh = _lora_t_single(a, sp, counts, sk)
             if th is not None:
                 t[h], r, lb[h] = th, rh, bh
         if len(spec_pair) == 2 and (t[0] is None) != (t[1] is None):
             raise NotImplementedError("gate_proj and up_proj adapters must come in pairs")
-        ops.grouped_gemm_fused(a, w, out, counts, mode, None, residual, t, lb, r, list(rope), rope_cols, True, 1.0, *kv)
+        if residual is None and mode == ops.EPI_RESIDUAL:
+            residual = out   # in place
+        ops.grouped_gemm_fused(a, w, out, counts, mode, None, residual, t, lb, r, list(rope), rope_cols, True, 1.0, *kv,
+                               skinny=sk)
 
     xn = new(B, H)
     ops.rmsnorm_gather(hf, ln1.weight.detach(), ln1.variance_epsilon, None, n_rows, xn)
@@ -582,14 +594,21 @@ def _cache_capacity(t: torch.Tensor) -> int:
     """Capacity (positions) of the pre-allocated buffer a [B, heads, L, 128] cache view lives in, 0 if it is not such
     a view (e.g. the contiguous result of a ``torch.cat`` / beam-search ``index_select``)."""
     B, heads, L, d = t.shape
-    if d != HEAD_DIM or t.stride(3) != 1 or t.stride(2) != HEAD_DIM or t.storage_offset() != 0:
+    if d != HEAD_DIM or t.stride(3) != 1 or t.stride(2) != HEAD_DIM:
         return 0
     cap = t.stride(1) // HEAD_DIM
     if t.stride(1) != cap * HEAD_DIM or (B > 1 and t.stride(0) != heads * cap * HEAD_DIM) or cap < L:
         return 0
-    if t.untyped_storage().nbytes() < B * heads * cap * HEAD_DIM * t.element_size():
+    room = t.untyped_storage().nbytes() // t.element_size() - t.storage_offset()
+    if room < B * heads * cap * HEAD_DIM:
         return 0
     return cap
+
+
+def _full_cache_view(t: torch.Tensor, cap: int) -> torch.Tensor:
+    B, heads = t.shape[:2]
+    return torch.as_strided(t, (B, heads, cap, HEAD_DIM), (heads * cap * HEAD_DIM, cap * HEAD_DIM, HEAD_DIM, 1),
+                            t.storage_offset())
 
 
 def visual_expert_layer_decode(layer: "CogVLMDecoderLayer", hidden_states: torch.Tensor, position_ids: torch.Tensor,
@@ -612,9 +631,7 @@ def visual_expert_layer_decode(layer: "CogVLMDecoderLayer", hidden_states: torch
         raise ValueError(f"padding_mask must cover past + current positions: expected {(B, Lkv)}")
     cap = min(_cache_capacity(past_k), _cache_capacity(past_v))
     if cap >= Lkv:
-        shape = (B, heads, cap, HEAD_DIM)
-        k_cache, v_cache = (torch.as_strided(t, shape, (heads * cap * HEAD_DIM, cap * HEAD_DIM, HEAD_DIM, 1), 0)
-                            for t in (past_k, past_v))
+        k_cache, v_cache = _full_cache_view(past_k, cap), _full_cache_view(past_v, cap)
     else:
         cap = Lkv + KV_HEADROOM
         kv = torch.empty(2, B, heads, cap, HEAD_DIM, dtype=past_k.dtype, device=past_k.device)

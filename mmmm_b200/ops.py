@@ -144,7 +144,7 @@ def grouped_gemm_raw(a: torch.Tensor, w: Sequence[Optional[torch.Tensor]], out: 
                      alpha: float = 1.0, n_out: Optional[int] = None, w_transposed: bool = False,
                      dropout_p: float = 0.0, dropout_seed: int = 0, ce: Optional[dict] = None,
                      bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
-                     kv: Optional[tuple] = None) -> None:
+                     kv: Optional[tuple] = None, skinny: bool = False) -> None:
     """K3 (vex_grouped_gemm).  ``w`` = [vision_w0, vision_w1, language_w0, language_w1] ([N, K] each; the *_w1
     entries are up_proj for SWIGLU, else None).  ``lora_b`` likewise; ``lora_t`` = [T_half0, T_half1].
     ``rope`` = (cos [S,128], sin [S,128], position_ids int64 [B*L], sorted_to_flat int32).
@@ -153,7 +153,9 @@ def grouped_gemm_raw(a: torch.Tensor, w: Sequence[Optional[torch.Tensor]], out: 
     ``bias`` (bf16 [N]) / ``act`` (ACT_GELU): nn.Linear with bias and the erf-GELU of the vision encoder's Linears
     (visual.py:84-85, :110-117), PLAIN / RESIDUAL epilogues only.
     ``kv`` = (k_cache, v_cache [B, heads, capacity, 128], seq_len, kv_pos or None): EPI_ROPE also writes the post-rotary
-    K heads and the V heads into the KV cache (vexGemmArgs.kv_k)."""
+    K heads and the V heads into the KV cache (vexGemmArgs.kv_k).
+    ``skinny``: the rows are a decode batch (<= 32, all live, single expert) -- run K12 (vex_decode_gemm), the
+    HBM-bound weight-streaming form, instead of the tcgen05 tile kernel."""
     _dev(a, "a", _BF16)
     if out is not None:
         _dev(out, "out", _BF16)
@@ -242,6 +244,13 @@ def grouped_gemm_raw(a: torch.Tensor, w: Sequence[Optional[torch.Tensor]], out: 
         args.kv_seq_len, args.kv_capacity = int(kv_seq), k_cache.shape[2]
     name = ("gemm_plain", "gemm_rope", "gemm_swiglu", "gemm_residual", "gemm_dropout_acc", "gemm_ce", "gemm_ce_bwd")[mode] + ("_n64" if N <= 64 else "") + \
         ("_dgrad" if w_transposed else "") + ("_gelu" if act == ACT_GELU else "")
+    if skinny:
+        if rope is not None and pos.numel() != rows_cap:
+            raise ValueError("skinny (decode) form: position_ids must have one entry per batch row")
+        with instrument.region("decode_" + name):
+          rc = _lib.lib().vex_decode_gemm(C.byref(args), _stream())
+        _lib.check(rc, "vex_decode_gemm")
+        return
     with instrument.region(name):
       rc = _lib.lib().vex_grouped_gemm(C.byref(args), _stream())
     _lib.check(rc, "vex_grouped_gemm")
@@ -262,22 +271,22 @@ def _grouped_gemm_fused(a: torch.Tensor, w: List[Optional[torch.Tensor]], out: t
                         lora_t: List[Optional[torch.Tensor]], lora_b: List[Optional[torch.Tensor]], lora_r: int,
                         rope: List[torch.Tensor], rope_cols: int, single_expert: bool, alpha: float,
                         kv_k: Optional[torch.Tensor], kv_v: Optional[torch.Tensor], kv_seq_len: int,
-                        kv_pos: Optional[torch.Tensor]) -> None:
+                        kv_pos: Optional[torch.Tensor], skinny: bool) -> None:
     """K3 with a fused epilogue (``mode`` = EPI_*), LoRA K-extension and scatter; see ``grouped_gemm_raw``.
     ``kv_k`` / ``kv_v`` [B, heads, capacity, 128]: KV-cache second output of EPI_ROPE (prefill: ``kv_seq_len`` = L;
     decode: 1 and ``kv_pos`` = device counter of cached positions)."""
     grouped_gemm_raw(a, w, out, counts, mode, row_map=row_map, residual=residual, lora_t=lora_t, lora_b=lora_b,
                      lora_r=lora_r, rope=tuple(rope) if len(rope) else None, rope_cols=rope_cols,
                      single_expert=single_expert, alpha=alpha,
-                     kv=None if kv_k is None else (kv_k, kv_v, kv_seq_len, kv_pos))
+                     kv=None if kv_k is None else (kv_k, kv_v, kv_seq_len, kv_pos), skinny=skinny)
 
 
 def grouped_gemm_fused(a, w, out, counts, mode, row_map, residual, lora_t, lora_b, lora_r, rope, rope_cols,
-                       single_expert, alpha, kv_k=None, kv_v=None, kv_seq_len=0, kv_pos=None) -> None:
+                       single_expert, alpha, kv_k=None, kv_v=None, kv_seq_len=0, kv_pos=None, skinny=False) -> None:
     """``vex::grouped_gemm_fused`` with the KV-cache arguments defaulted (the registered op takes every argument
     positionally: torch.library tracks mutated arguments by position)."""
     _grouped_gemm_fused(a, w, out, counts, mode, row_map, residual, lora_t, lora_b, lora_r, rope, rope_cols,
-                        single_expert, alpha, kv_k, kv_v, kv_seq_len, kv_pos)
+                        single_expert, alpha, kv_k, kv_v, kv_seq_len, kv_pos, skinny)
 
 
 @torch.library.custom_op("vex::grouped_gemm_dgrad", mutates_args=("out",))

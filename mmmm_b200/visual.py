@@ -74,12 +74,35 @@ class PatchEmbedding(nn.Module):
         super().__init__()
         self.proj = Downsample(config.in_channels, config.hidden_size, config.patch_size)
         self.pos_embed_shape = tuple(config.pos_embed_shape)
+        pt = getattr(config, "pt_pos_embed_shape", None)   # grid of the pretrained 2-D position embedding (visual.py:31)
+        self.pt_pos_embed_shape = None if pt is None else tuple(pt)
         self.cls_embedding = ParameterWrapper(NoWeightDecayParameter(torch.zeros(1, config.hidden_size)))
         self.cls_pos_embed = ParameterWrapper(NoWeightDecayParameter(torch.zeros(1, config.hidden_size)))
         self.position_embedding = ParameterWrapper(
             NoWeightDecayParameter(torch.zeros(1, config.hidden_size, *config.pos_embed_shape)))
 
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        """Same checkpoint inflation as the reference (visual.py:38-57): a pretrained 2-D EVA2-CLIP position embedding
+        ``[1 + h*w, C]`` (class row first) is split into ``cls_pos_embed`` and a ``[1, C, d, h, w]`` grid -- resampled
+        when the pretrained grid differs from ``pos_embed_shape[-2:]``, repeated along depth -- and a saved
+        modules_to_save copy of another grid size is resampled to this module's grid."""
+        key = f"{prefix}position_embedding.weight"
+        saved = f"{prefix}position_embedding.modules_to_save.default.weight"
+        if (pe := state_dict.get(key)) is not None and pe.ndim == 2:
+            cls_pe, pe = pe[0:1], pe[1:]
+            h, w = self.pt_pos_embed_shape if self.pt_pos_embed_shape is not None else self.pos_embed_shape[-2:]
+            if pe.shape[0] != h * w:
+                raise ValueError(f"{key}: {pe.shape[0]} rows do not form the pretrained {h} x {w} grid "
+                                 f"(config.pt_pos_embed_shape)")
+            pe = pe.reshape(h, w, -1).permute(2, 0, 1)[None]                        # '(h w) c -> 1 c h w'
+            if (h, w) != tuple(self.pos_embed_shape[-2:]):
+                pe = resample(pe.float(), self.pos_embed_shape[-2:]).to(pe.dtype)
+            pe = pe[:, :, None].expand(-1, -1, self.pos_embed_shape[0], -1, -1).contiguous()   # '1 c h w -> 1 c d h w'
+            del state_dict[key]
+            state_dict[f"{prefix}cls_pos_embed"] = cls_pe
+            state_dict[f"{prefix}position_embedding"] = pe
+        elif (pe := state_dict.get(saved)) is not None and tuple(pe.shape[2:]) != tuple(self.position_embedding.weight.shape[2:]):
+            state_dict[saved] = resample(pe.float(), self.position_embedding.weight.shape[2:]).to(pe.dtype)
         # ParameterWrapper.wrap (mmmm/utils.py:71-77): accept the bare-parameter spelling of the three embeddings
         for name in ("cls_embedding", "cls_pos_embed", "position_embedding"):
             if (w := state_dict.pop(prefix + name, None)) is not None:

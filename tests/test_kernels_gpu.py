@@ -665,3 +665,111 @@ def test_k9_attention_backward_vs_autograd(lens):
     untouched = torch.ones(cap, dtype=torch.bool)
     untouched[t2s[:T].long()] = False
     assert (dqkv.cpu()[untouched] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------ K12 (decode skinny GEMM) / K4d
+@pytest.mark.parametrize("B", [1, 3, 8, 19, 32])
+@pytest.mark.parametrize("r", [0, 64])
+def test_k12_decode_gemm_vs_fp32_and_k3(B, r):
+    """The weight-streaming decode GEMM (mma.sync fragments loaded straight from global memory, K permuted inside
+    32-element chunks) against fp32 matmuls with the eager-bf16 rounding points, for every epilogue the decode step uses
+    (PLAIN with alpha, RESIDUAL separate / in place, SWIGLU, ROPE + KV-cache append) with and without the LoRA
+    K-extension, and against K3 on the same inputs."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(100 + B + r)
+    H, I, heads = 512, 1408, 4
+    rnd = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).bfloat16().cuda()
+    counts = torch.tensor([B, 0, B, 1], dtype=torch.int32).cuda()
+    x = rnd(B, H)
+    lin = lambda a, w: (a.float() @ w.float().T)
+    def lora(a, A, Bm):
+        return 0 if r == 0 else (a.float() @ A.float().T).bfloat16().float() @ Bm.float().T
+    def t_of(a, A):
+        if r == 0:
+            return None
+        t = torch.empty(B, r, dtype=torch.bfloat16).cuda()
+        ops.grouped_gemm_raw(a, [A], t, counts, ops.EPI_PLAIN, single_expert=True, alpha=1.0, skinny=True)
+        torch.testing.assert_close(t.float(), (a.float() @ A.float().T), rtol=2e-2, atol=2e-2)
+        return t
+    close = lambda got, want: torch.testing.assert_close(got.float(), want.float(), rtol=2e-2, atol=2e-2)
+
+    # PLAIN with alpha
+    w = rnd(768, H, sc=0.06)
+    out = torch.zeros(B, 768, dtype=torch.bfloat16).cuda()
+    ops.grouped_gemm_raw(x, [w], out, counts, ops.EPI_PLAIN, single_expert=True, alpha=0.5, skinny=True)
+    close(out, 0.5 * lin(x, w))
+    # RESIDUAL (+ LoRA), separate and in place, vs K3
+    A, Bm = (rnd(r, H, sc=0.05), rnd(H, r, sc=0.05)) if r else (None, None)
+    wd, res = rnd(H, H, sc=0.06), rnd(B, H)
+    t = t_of(x, A)
+    kw = dict(single_expert=True, lora_t=[t, None], lora_b=[Bm, None, None, None], lora_r=r, residual=res)
+    o_s, o_k = torch.zeros(B, H, dtype=torch.bfloat16).cuda(), torch.zeros(B, H, dtype=torch.bfloat16).cuda()
+    ops.grouped_gemm_raw(x, [wd], o_s, counts, ops.EPI_RESIDUAL, skinny=True, **kw)
+    ops.grouped_gemm_raw(x, [wd], o_k, counts, ops.EPI_RESIDUAL, skinny=False, **kw)
+    want = (lin(x, wd) + lora(x, A, Bm)).bfloat16().float() + res.float()
+    close(o_s, want), close(o_s, o_k)
+    inpl = res.clone()
+    ops.grouped_gemm_raw(x, [wd], inpl, counts, ops.EPI_RESIDUAL, skinny=True, **dict(kw, residual=None))
+    assert torch.equal(inpl, o_s)
+    # SWIGLU (+ LoRA on gate and up)
+    wg, wu = rnd(I, H, sc=0.06), rnd(I, H, sc=0.06)
+    Ag, Bg, Au, Bu = (rnd(r, H, sc=0.05), rnd(I, r, sc=0.05), rnd(r, H, sc=0.05), rnd(I, r, sc=0.05)) if r else [None] * 4
+    tg, tu = t_of(x, Ag), t_of(x, Au)
+    act = torch.zeros(B, I, dtype=torch.bfloat16).cuda()
+    ops.grouped_gemm_raw(x, [wg, wu], act, counts, ops.EPI_SWIGLU, single_expert=True, lora_t=[tg, tu],
+                         lora_b=[Bg, Bu, None, None], lora_r=r, skinny=True)
+    gt = (lin(x, wg) + lora(x, Ag, Bg)).bfloat16().float()
+    up = (lin(x, wu) + lora(x, Au, Bu)).bfloat16().float()
+    close(act, torch.nn.functional.silu(gt).bfloat16().float() * up)
+    # ROPE + KV append at a device-side position
+    wq = rnd(3 * H, H, sc=0.06)
+    cos, sin = O.rotary_tables(O.default_inv_freq(128).bfloat16(), 600)
+    pos = torch.randint(0, 600, (B,), generator=g)
+    cap, at = 40, 17
+    kc = torch.zeros(B, heads, cap, 128, dtype=torch.bfloat16).cuda()
+    vc = torch.zeros_like(kc)
+    kv_pos = torch.tensor([at], dtype=torch.int32).cuda()
+    ident = torch.arange(B, dtype=torch.int32).cuda()
+    qkv = torch.zeros(B, 3 * H, dtype=torch.bfloat16).cuda()
+    Aq, Bq = (rnd(r, H, sc=0.05), rnd(3 * H, r, sc=0.05)) if r else (None, None)
+    tq = t_of(x, Aq)
+    ops.grouped_gemm_raw(x, [wq], qkv, counts, ops.EPI_ROPE, single_expert=True, lora_t=[tq, None],
+                         lora_b=[Bq, None, None, None], lora_r=r,
+                         rope=(cos.cuda().contiguous(), sin.cuda().contiguous(), pos.cuda(), ident), rope_cols=2 * H,
+                         kv=(kc, vc, 1, kv_pos), skinny=True)
+    l3 = (lin(x, wq) + lora(x, Aq, Bq)).bfloat16().cpu()
+    q, k, v = l3.split(H, dim=-1)
+    qh, kh = q.view(1, B, heads, 128).permute(0, 2, 1, 3), k.view(1, B, heads, 128).permute(0, 2, 1, 3)
+    qr, kr = O.apply_rotary(qh, kh, cos, sin, pos[None])
+    want = torch.cat([qr.permute(0, 2, 1, 3).reshape(B, H), kr.permute(0, 2, 1, 3).reshape(B, H), v], dim=-1)
+    close(qkv.cpu(), want)
+    assert torch.equal(kc[:, :, at].reshape(B, H), qkv[:, H:2 * H]) and torch.equal(vc[:, :, at].reshape(B, H), qkv[:, 2 * H:])
+    kc[:, :, at] = 0
+    vc[:, :, at] = 0
+    assert not kc.any() and not vc.any()          # nothing else in the cache was touched
+
+
+@pytest.mark.parametrize("B,L,cap", [(1, 700, 800), (2, 63, 64), (8, 1500, 1600), (40, 130, 130), (3, 4100, 4200)])
+def test_k4d_cluster_split_decode_attention_vs_oracle(B, L, cap):
+    """Decode attention over the pre-allocated cache with the positions of one (sample, head) split over a thread-block
+    cluster (1 / 2 / 4 / 8 CTAs, exact softmax through distributed shared memory) against the oracle's generation
+    branch; the device-side length counter selects the live prefix of the cache."""
+    ops = _ops()
+    heads = 4
+    g = torch.Generator().manual_seed(B * 1000 + L)
+    q = torch.randn(B, heads, 1, 128, generator=g).bfloat16()
+    k = torch.randn(B, heads, L, 128, generator=g).bfloat16()
+    v = torch.randn(B, heads, L, 128, generator=g).bfloat16()
+    mask = torch.rand(B, L, generator=g) > 0.2
+    mask[:, -1] = True
+    want = O.attention_decode(q, k, v, mask)                     # [B, heads, 1, 128]
+    kc = torch.full((B, heads, cap, 128), float("nan"), dtype=torch.bfloat16)
+    vc = torch.full((B, heads, cap, 128), float("nan"), dtype=torch.bfloat16)
+    kc[:, :, :L], vc[:, :, :L] = k, v
+    mfull = torch.ones(B, cap, dtype=torch.bool)
+    mfull[:, :L] = mask
+    out = torch.zeros(B, heads * 128, dtype=torch.bfloat16).cuda()
+    kv_len = torch.tensor([L - 1], dtype=torch.int32).cuda()      # positions cached before this step
+    ops.attention_decode_cache(q.reshape(B, heads * 128).cuda(), kc.cuda(), vc.cuda(), mfull.cuda(), kv_len, out,
+                               128 ** -0.5)
+    torch.testing.assert_close(out.cpu().float(), want.reshape(B, heads * 128).float(), rtol=2e-2, atol=2e-2)

@@ -165,8 +165,11 @@ def test_error_behaviour_on_gpu():
             layer(h.cpu(), ids.cpu(), ids.cpu(), pm.cpu())
         out = layer(h, ids, ids, attention_mask=pm)   # BASELINE's name for the 4th argument
         assert out[0].shape == h.shape
-    with pytest.raises(NotImplementedError):           # base weights are frozen under PEFT: full fine-tuning is
-        layer(h, ids, ids, pm)                         # not what the fused training path implements
+    (plain,) = layer(h, ids, ids, pm)                  # grad mode on, nothing differentiable involved: plain inference
+    assert not plain.requires_grad
+    with pytest.raises(NotImplementedError):           # base weights are frozen under PEFT: full fine-tuning (a
+        layer(h.clone().requires_grad_(True), ids, ids, pm)   # differentiable input + trainable base weights) is not
+                                                       # what the fused training path implements
 
 
 @pytest.mark.parametrize("ragged", [False, True])
@@ -691,8 +694,11 @@ def test_training_step_full_width_r64_vs_oracle_autograd():
         e = float((got.float().cpu() - want).norm() / want.norm().clamp_min(1e-12))
         assert e <= tol, (name, e)
 
+    # the oracle runs in FP32 here (autograd reference); at this width the reference's own bf16 run is 6.9e-2 max-rel /
+    # 1.2e-2 rel-Frobenius away from its fp32 run (SURVEY 8(c) calibration), so the forward is held to that envelope --
+    # the bf16-vs-bf16 forward bar at this shape is test_c2_one_sample_full_width_vs_oracle[64]
     mx, fro = _errs(out.detach().cpu()[pm], ref.detach()[pm])
-    assert mx <= MAX_REL and fro <= FRO_REL, (mx, fro)
+    assert mx <= 1.5 * 6.9e-2 and fro <= 1.5 * 1.2e-2, (mx, fro)
     close(x.grad[pm.cuda()], xr.grad[pm], "d_hidden")
     for path, a in adf.items():
         m = layer.get_submodule(path)

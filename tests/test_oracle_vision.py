@@ -158,3 +158,41 @@ def test_cpu_tensors_raise():
         model(img, [(4, 8, 8)], [(1, 1, 1)])
     with pytest.raises(ValueError, match="head_dim"):
         _tiny_model(hidden_size=512, num_heads=2)
+
+
+def test_patch_embedding_checkpoint_inflation_matches_reference():
+    """PatchEmbedding._load_from_state_dict (visual.py:38-57): a pretrained 2-D EVA2-CLIP position embedding
+    [1 + h*w, C] is split / resampled / repeated along depth on load.  Checked against the live reference module when
+    /root/reference exists (same state dict in, same parameters out), and structurally everywhere."""
+    g = torch.Generator().manual_seed(3)
+    C = 256
+    pt = torch.randn(1 + 3 * 3, C, generator=g)                    # pretrained 3 x 3 grid + class row
+    model = _tiny_model(pt_pos_embed_shape=(3, 3))
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    sd["patch_embedding.position_embedding.weight"] = pt.clone()
+    del sd["patch_embedding.cls_pos_embed.weight"]
+    model.load_state_dict(sd)
+    pe = model.patch_embedding.position_embedding.weight
+    assert pe.shape == (1, C, 2, 4, 4)
+    assert torch.equal(model.patch_embedding.cls_pos_embed.weight, pt[0:1])
+    assert torch.equal(pe[:, :, 0], pe[:, :, 1])                    # repeated along depth
+    # same grid: no resampling, pure reshape
+    same = _tiny_model(pt_pos_embed_shape=(4, 4))
+    pt4 = torch.randn(1 + 16, C, generator=g)
+    sd4 = {k: v.clone() for k, v in same.state_dict().items()}
+    sd4["patch_embedding.position_embedding.weight"] = pt4.clone()
+    del sd4["patch_embedding.cls_pos_embed.weight"]
+    same.load_state_dict(sd4)
+    assert torch.equal(same.patch_embedding.position_embedding.weight[0, :, 0], pt4[1:].reshape(4, 4, C).permute(2, 0, 1))
+    if RL.reference_available():
+        cfg = OV.VisionConfig(hidden_size=256, num_heads=2, intermediate_size=256, num_hidden_layers=2,
+                              patch_size=(4, 8, 8), pos_embed_shape=(2, 4, 4), lm_hidden_size=256,
+                              lm_intermediate_size=256)
+        ref = RL.make_reference_vision(cfg, OV.random_vision_weights(cfg, seed=1))
+        ref.patch_embedding.pt_pos_embed_shape = (3, 3)
+        rsd = {k: v.clone() for k, v in ref.state_dict().items()}
+        rsd["patch_embedding.position_embedding.weight"] = pt.clone()
+        del rsd["patch_embedding.cls_pos_embed.weight"]
+        ref.load_state_dict(rsd)
+        assert torch.equal(ref.patch_embedding.position_embedding.weight, pe)
+        assert torch.equal(ref.patch_embedding.cls_pos_embed.weight, model.patch_embedding.cls_pos_embed.weight)

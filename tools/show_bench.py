@@ -18,6 +18,6 @@ for f in sys.argv[1:]:
         print("   e2e:", {k: v for k, v in d["e2e"].items() if k != "how"})
     if d.get("roofline"):
         r = d["roofline"]
-        print(f"   roofline: {r['achieved']:.1f} {r['unit']} frac {r['frac']:.3f} ms/launch {r['ms_per_launch']:.4f} traffic {r['traffic']}")
+        print(f"   roofline: {r['achieved']:.1f} {r['unit']} frac {r['frac']:.3f} ms/launch {r.get('ms_per_launch', 0):.4f} traffic {r['traffic']}")
     for k, v in sorted((d.get("kernels") or {}).items(), key=lambda kv: -kv[1]["ms"]):
         print(f"      {k:20s} {v['ms']:.4f} ms  x{v['calls_per_step']}")
