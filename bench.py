@@ -452,12 +452,17 @@ def run_ours(args):
             t0 = time.perf_counter()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             instrument.reset()
+            ranged = sampler is not None and os.environ.get("VEX_PROFILER_RANGE") == "1"
+            if ranged:  # `ncu --profile-from-start off`: the launch list covers exactly the timed region
+                torch.cuda.cudart().cudaProfilerStart()
             e0.record()
             for _ in range(steps):
                 fn()
             e1.record()
             launches = instrument.launches()
             barrier()
+            if ranged:
+                torch.cuda.cudart().cudaProfilerStop()
             wall_ms = (time.perf_counter() - t0) * 1e3
             if sampler is not None:
                 marks["hi"] = sampler.mark()

@@ -192,9 +192,9 @@ int vex_grouped_gemm(const vexGemmArgs* args, vexStream stream);
  * (= the batch; `counts` is not read), single_expert = 1 (get_expert_mask's L == 1 rule :67: every token goes to the
  * language expert), forward form only.  HBM-bound by design: the weights stream from global memory straight into
  * mma.sync fragments, 16 output features per CTA, K interleaved over 8 warps.  Modes VEX_EPI_PLAIN / RESIDUAL / SWIGLU /
- * ROPE (with the KV-cache append, kv_seq_len = 1) and the LoRA K-extension (lora_r % 32 == 0); row_map, bias, act are
- * not supported (VEX_E_UNSUPPORTED -- callers fall back to vex_grouped_gemm).  K % 32 == 0, N % 16 == 0 (N % 128 == 0
- * for ROPE); position_ids is indexed by batch row. */
+ * ROPE (with the KV-cache append, kv_seq_len = 1) and the LoRA K-extension (lora_r % 64 == 0); row_map, bias, act are
+ * not supported (VEX_E_UNSUPPORTED -- callers fall back to vex_grouped_gemm).  K % 64 == 0, N % 16 == 0 (N % 128 == 0
+ * for ROPE), operands 32-byte aligned (256-bit loads); position_ids is indexed by batch row. */
 int vex_decode_gemm(const vexGemmArgs* args, vexStream stream);
 
 /* K4 -- causal block-diagonal (varlen) flash attention over the token-order QKV buffer.

@@ -130,6 +130,29 @@ __device__ __forceinline__ uint4 ld_stream(const void* p) {
                : "l"(p));
   return r;
 }
+// 256-bit loads (sm_100: LDG.256): a thread moves 32 bytes, so 4 threads cover one 128-byte line and an 8-row x 128-byte
+// access pattern costs ONE line request per row.  The L1 miss path tracks 128-byte lines: with 16-byte loads the same
+// pattern occupies twice the line slots per byte and the decode kernels measured half the bandwidth of a fully
+// coalesced stream (round 2, profiles/r2_decode_*.md).
+struct alignas(32) U32x8 {
+  uint32_t v[8];
+};
+__device__ __forceinline__ U32x8 ld_stream_256(const void* p) {  // streaming: read-only path, no L1 allocation
+  U32x8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+                 "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ U32x8 ld_cached_256(const void* p) {  // reused data (L1-resident)
+  U32x8 r;
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+                 "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
 __device__ __forceinline__ void st_stream(void* p, const uint4& v) {
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
                "r"(v.w)

@@ -8,10 +8,11 @@
 // which is what round 2 measured for the decode step on K3 (1.8 TB/s).  Design for bandwidth instead:
 //   * one CTA (8 warps) per group of 16 output features (and their partner tile: up_proj for SwiGLU, column j + 64
 //     for rotary), 256 ... 768 CTAs per projection -- every SM streams;
-//   * the K dimension is interleaved over the 8 warps in 32-element chunks; a thread loads 16 bytes (8 consecutive k)
-//     of weight row g and of row g + 8 straight from global memory into the A fragment of mma.sync.m16n8k16 -- the k
-//     order inside a chunk is permuted identically for the B fragment, so no shuffle / shared-memory staging of the
-//     weights is needed and every load is a full 16-byte vector (4 chunks = 8 loads per thread in flight);
+//   * the K dimension is interleaved over the 8 warps in 64-element chunks; a thread loads 32 bytes (16 consecutive k,
+//     one LDG.256) of weight row g and of row g + 8 straight from global memory into the A fragments of four
+//     mma.sync.m16n8k16 steps -- the k order inside a chunk is permuted identically for the B fragment, so no shuffle /
+//     shared-memory staging of the weights is needed, 4 threads cover one full 128-byte line of a row, and the next
+//     chunk is in flight while the current one is multiplied (double-buffered registers);
 //   * the batch is the N dimension of the MMA (n8 tiles, 1 ... 4 of them); x is read through the read-only path
 //     (L1-resident: 8 x 4096 x 2 B = 64 KB, shared by every CTA on the SM);
 //   * partial sums of the 8 warps are reduced through shared memory, then 16 x B outputs take the epilogue.
@@ -25,7 +26,6 @@ namespace vex {
 
 constexpr int DG_THREADS = 256;
 constexpr int DG_WARPS = 8;
-constexpr int DG_UNROLL = 4;  // 32-element k chunks per load batch
 
 struct DecGemm {
   const __nv_bfloat16* x;     // [B, K]
@@ -55,45 +55,64 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
-// accumulates  c[tile][nb] += W_tile[16, k-range] . x[nb*8 .., k-range]^T  over the chunks this warp owns
+// One 64-element k chunk of this thread's fragments: 32 bytes (16 consecutive k) of weight rows g and g + 8 per tile.
+template <int TILES>
+struct WFrag {
+  U32x8 lo[TILES], hi[TILES];
+};
+
+template <int TILES>
+__device__ __forceinline__ void load_w(WFrag<TILES>& f, const __nv_bfloat16* const* wrow_lo,
+                                       const __nv_bfloat16* const* wrow_hi, int kb) {
+#pragma unroll
+  for (int tl = 0; tl < TILES; ++tl) {
+    f.lo[tl] = ld_stream_256(wrow_lo[tl] + kb);
+    f.hi[tl] = ld_stream_256(wrow_hi[tl] + kb);
+  }
+}
+
+// c[tile][nb] += W_tile[16, chunk] . x[nb*8 .., chunk]^T.  The 16 k of a thread are consumed as four m16n8k16 steps
+// (step j: register pair 2j, 2j + 1); the B fragment takes the same 16 k of x row g, so the k permutation cancels.
+template <int NB, int TILES>
+__device__ __forceinline__ void mma_chunk(float (&c)[2][NB][4], const WFrag<TILES>& f, const __nv_bfloat16* const* xrow,
+                                          const bool* xlive, int kb) {
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) {
+    U32x8 xb;
+    if (xlive[nb]) {
+      xb = ld_cached_256(xrow[nb] + kb);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xb.v[j] = 0u;
+    }
+#pragma unroll
+    for (int tl = 0; tl < TILES; ++tl)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        mma_bf16_16816(c[tl][nb], f.lo[tl].v[2 * j], f.hi[tl].v[2 * j], f.lo[tl].v[2 * j + 1], f.hi[tl].v[2 * j + 1],
+                       xb.v[2 * j], xb.v[2 * j + 1]);
+  }
+}
+
+// accumulates over the 64-element chunks this warp owns (chunk i = warp, warp + 8, ...), software-pipelined: the next
+// chunk's weight loads are issued before the current chunk's MMAs, so every warp has loads in flight all the time
 template <int NB, int TILES>
 __device__ __forceinline__ void accumulate(float (&c)[2][NB][4], const __nv_bfloat16* const* wrow_lo,
                                            const __nv_bfloat16* const* wrow_hi, const __nv_bfloat16* const* xrow,
                                            const bool* xlive, int K, int warp, int t) {
-  const int nchunks = K >> 5;
-  for (int i0 = warp; i0 < nchunks; i0 += DG_WARPS * DG_UNROLL) {
-    uint4 alo[DG_UNROLL][TILES], ahi[DG_UNROLL][TILES];
-#pragma unroll
-    for (int u = 0; u < DG_UNROLL; ++u) {
-      const int i = i0 + u * DG_WARPS;
-      const int kb = (i << 5) + 8 * t;
-#pragma unroll
-      for (int tl = 0; tl < TILES; ++tl) {
-        if (i < nchunks) {
-          alo[u][tl] = ld_stream(reinterpret_cast<const uint4*>(wrow_lo[tl] + kb));
-          ahi[u][tl] = ld_stream(reinterpret_cast<const uint4*>(wrow_hi[tl] + kb));
-        } else {
-          alo[u][tl] = make_uint4(0, 0, 0, 0);
-          ahi[u][tl] = make_uint4(0, 0, 0, 0);
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < DG_UNROLL; ++u) {
-      const int i = i0 + u * DG_WARPS;
-      if (i >= nchunks) break;
-      const int kb = (i << 5) + 8 * t;
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb) {
-        uint4 xb = make_uint4(0, 0, 0, 0);
-        if (xlive[nb]) xb = __ldg(reinterpret_cast<const uint4*>(xrow[nb] + kb));
-#pragma unroll
-        for (int tl = 0; tl < TILES; ++tl) {
-          mma_bf16_16816(c[tl][nb], alo[u][tl].x, ahi[u][tl].x, alo[u][tl].y, ahi[u][tl].y, xb.x, xb.y);
-          mma_bf16_16816(c[tl][nb], alo[u][tl].z, ahi[u][tl].z, alo[u][tl].w, ahi[u][tl].w, xb.z, xb.w);
-        }
-      }
-    }
+  const int nchunks = K >> 6;
+  WFrag<TILES> f0, f1;
+  int i = warp;
+  if (i < nchunks) load_w<TILES>(f0, wrow_lo, wrow_hi, (i << 6) + 16 * t);
+  while (i < nchunks) {
+    const int i1 = i + DG_WARPS;
+    if (i1 < nchunks) load_w<TILES>(f1, wrow_lo, wrow_hi, (i1 << 6) + 16 * t);
+    mma_chunk<NB, TILES>(c, f0, xrow, xlive, (i << 6) + 16 * t);
+    if (i1 >= nchunks) break;
+    const int i2 = i1 + DG_WARPS;
+    if (i2 < nchunks) load_w<TILES>(f0, wrow_lo, wrow_hi, (i2 << 6) + 16 * t);
+    mma_chunk<NB, TILES>(c, f1, xrow, xlive, (i1 << 6) + 16 * t);
+    i = i2;
   }
 }
 
@@ -135,7 +154,7 @@ __global__ void __launch_bounds__(DG_THREADS, 2) k12_decode_gemm(const DecGemm p
                                   wb + static_cast<int64_t>(n_b + g + 8) * p.ldw};
     accumulate<NB, TILES>(c, lo, hi, xrow, xlive, p.K, warp, t);
   }
-  if (p.lora_r > 0) {  // K-extension: += T . lora_B^T  (r is a multiple of 32 here; r = 64 -> two chunks, warps 0 and 1)
+  if (p.lora_r > 0) {  // K-extension: += T . lora_B^T  (r is a multiple of 64 here; r = 64 -> one chunk, warp 0)
     const __nv_bfloat16* trow[NB];
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) trow[nb] = p.lt[0] + static_cast<int64_t>(min(nb * 8 + g, p.B - 1)) * p.ldt;
@@ -250,7 +269,9 @@ extern "C" int vex_decode_gemm(const vexGemmArgs* a, vexStream stream) {
   if (!a || !a->a || !a->out || !a->w[0][0]) return VEX_E_INVALID;
   if (a->rows_cap <= 0 || a->rows_cap > 32 || a->N <= 0 || a->K <= 0) return VEX_E_UNSUPPORTED;
   if (!a->single_expert || a->w_transposed || a->bias || a->act != VEX_ACT_NONE || a->row_map) return VEX_E_UNSUPPORTED;
-  if (a->K % 32 != 0 || a->lda % 8 != 0 || a->ldw % 8 != 0 || a->N % 16 != 0) return VEX_E_UNSUPPORTED;
+  if (a->K % 64 != 0 || a->lda % 16 != 0 || a->ldw % 16 != 0 || a->N % 16 != 0) return VEX_E_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(a->a) | reinterpret_cast<uintptr_t>(a->w[0][0]) | reinterpret_cast<uintptr_t>(a->w[0][1])) & 31)
+    return VEX_E_UNSUPPORTED;  // 256-bit loads
   const int mode = a->mode;
   if (mode != VEX_EPI_PLAIN && mode != VEX_EPI_RESIDUAL && mode != VEX_EPI_SWIGLU && mode != VEX_EPI_ROPE)
     return VEX_E_UNSUPPORTED;
@@ -274,7 +295,10 @@ extern "C" int vex_decode_gemm(const vexGemmArgs* a, vexStream stream) {
     p.residual = static_cast<const __nv_bfloat16*>(a->residual);
   }
   if (a->lora_r > 0 && a->lora_b[0][0]) {
-    if (a->lora_r % 32 != 0 || !a->lora_t[0] || a->ldt % 8 != 0) return VEX_E_UNSUPPORTED;
+    if (a->lora_r % 64 != 0 || !a->lora_t[0] || a->ldt % 16 != 0) return VEX_E_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(a->lora_t[0]) | reinterpret_cast<uintptr_t>(a->lora_t[1]) |
+         reinterpret_cast<uintptr_t>(a->lora_b[0][0]) | reinterpret_cast<uintptr_t>(a->lora_b[0][1])) & 31)
+      return VEX_E_UNSUPPORTED;
     if (mode == VEX_EPI_SWIGLU && (!a->lora_b[0][1] || !a->lora_t[1])) return VEX_E_UNSUPPORTED;
     p.lora_r = a->lora_r;
     p.ldt = a->ldt;

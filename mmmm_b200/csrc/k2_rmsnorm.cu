@@ -48,9 +48,41 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 2)
     const int r = blockIdx.x * ROWS + slot;
     if (r < n_rows) load_row(r, nx);  // the first row is in flight while the weight vector is staged
   }
-  for (int i = threadIdx.x; i < H; i += K2_WARPS * 32)
-    w_s[i] = weight_is_fp32 ? static_cast<const float*>(weight)[i]
-                            : __bfloat162float(static_cast<const __nv_bfloat16*>(weight)[i]);
+  // Weight staging with every load issued up front (16-byte vectors, fully unrolled).  The scalar one-element-per-trip
+  // loop this replaces was a chain of up to 16 dependent-latency round trips (~12 us: the whole duration of the
+  // 8-row decode launch, and a quarter of the 42 us prefill launch at c2 -- ncu, profiles/r2_decode_ncu.md).
+  if (weight_is_fp32) {
+    constexpr int NV = (H / 4 + K2_WARPS * 32 - 1) / (K2_WARPS * 32);  // float4 per thread
+    float4 wv[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int i = threadIdx.x + j * K2_WARPS * 32;
+      if (i < H / 4) wv[j] = __ldg(static_cast<const float4*>(weight) + i);
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int i = threadIdx.x + j * K2_WARPS * 32;
+      if (i < H / 4) *reinterpret_cast<float4*>(&w_s[4 * i]) = wv[j];
+    }
+  } else {
+    constexpr int NV = (H / 8 + K2_WARPS * 32 - 1) / (K2_WARPS * 32);  // uint4 (8 bf16) per thread
+    uint4 wv[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int i = threadIdx.x + j * K2_WARPS * 32;
+      if (i < H / 8) wv[j] = __ldg(static_cast<const uint4*>(weight) + i);
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int i = threadIdx.x + j * K2_WARPS * 32;
+      if (i < H / 8) {
+        *reinterpret_cast<float4*>(&w_s[8 * i]) =
+            make_float4(bf16_lo(wv[j].x), bf16_hi(wv[j].x), bf16_lo(wv[j].y), bf16_hi(wv[j].y));
+        *reinterpret_cast<float4*>(&w_s[8 * i + 4]) =
+            make_float4(bf16_lo(wv[j].z), bf16_hi(wv[j].z), bf16_lo(wv[j].w), bf16_hi(wv[j].w));
+      }
+    }
+  }
   __syncthreads();
   // trip count uniform per warp pair (both warps of a row take the pair barrier below)
   for (int r0 = blockIdx.x * ROWS; r0 < n_rows; r0 += stride) {
@@ -110,6 +142,7 @@ extern "C" int vex_rmsnorm_gather(const void* x, const void* weight, int weight_
                                   const int32_t* row_src, const int32_t* row_dst, const int32_t* n_rows, void* y,
                                   int rows_cap, int H, vexStream stream) {
   if (!x || !weight || !n_rows || !y || rows_cap <= 0) return VEX_E_INVALID;
+  if (reinterpret_cast<uintptr_t>(weight) & 15) return VEX_E_INVALID;  // staged with 16-byte loads
   if (H % 256 != 0 || H <= 0 || H > 4096) return VEX_E_UNSUPPORTED;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // persistent-ish grid: every CTA stages the weight vector once, then strides over rows

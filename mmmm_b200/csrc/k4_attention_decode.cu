@@ -11,9 +11,9 @@
 // measured 1.3 TB/s with one CTA per (sample, head)).  The softmax stays EXACT -- global max and sum are exchanged
 // through distributed shared memory before any probability is rounded to bf16 -- and the partial outputs are reduced
 // by the cluster's rank-0 CTA through DSMEM reads: no workspace in HBM, no second kernel.
-// Per CTA (256 threads): scores one key per thread (16 x 16-byte loads of its row, fp32 dot product against the query
-// held in shared memory); values: warp w takes keys w, w+8, ...; a lane owns 4 of the 128 output dims (8-byte loads,
-// a 256-byte row per warp instruction, coalesced).
+// Per CTA (256 threads): both passes read the cache with LDG.256, 8 lanes per 256-byte row (two full 128-byte lines),
+// 4 rows per warp instruction; a lane owns 16 of the 128 dims (scores: shuffle-reduced inside the 8-lane group; values:
+// the 4 groups of a warp are folded with shuffles, the 8 warps through shared memory).
 #include <cstring>
 
 #include "common.cuh"
@@ -75,26 +75,43 @@ __global__ void __launch_bounds__(DEC_THREADS)
   const int64_t base = (static_cast<int64_t>(b) * heads + h) * cap;
   const uint8_t* mrow = mask + static_cast<int64_t>(b) * ld_mask;
 
+  // scores: 8 lanes per key row (LDG.256 each: a 256-byte row = two full 128-byte lines per 8 lanes, 4 rows per warp
+  // instruction), 16 dims per lane, 3-step shuffle reduction inside the lane group
+  const int warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 3, sub = lane & 7;
+  float qreg[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) qreg[j] = qs[sub * 16 + j];
   float mx = -INFINITY;
-  for (int l = l0 + tid; l < l1; l += DEC_THREADS) {
-    float s = -INFINITY;
-    if (mrow[l]) {
-      const uint4* kr = reinterpret_cast<const uint4*>(k + (base + l) * 128);
+  constexpr int SU = 4;  // key rows in flight per lane group
+  for (int lb = l0 + warp * 4; lb < l1; lb += DEC_WARPS * 4 * SU) {
+    U32x8 u[SU];
+    bool in[SU], live[SU];
+#pragma unroll
+    for (int i = 0; i < SU; ++i) {
+      const int l = lb + i * DEC_WARPS * 4 + grp;
+      in[i] = l < l1;
+      live[i] = in[i] && mrow[l];
+      if (live[i]) u[i] = ld_stream_256(k + (base + l) * 128 + sub * 16);
+    }
+#pragma unroll
+    for (int i = 0; i < SU; ++i) {
+      const int l = lb + i * DEC_WARPS * 4 + grp;
       float acc = 0.f;
+      if (live[i]) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const uint4 u = ld_stream(kr + i);
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          acc = fmaf(qs[i * 8 + 2 * j], bf16_lo(w[j]), acc);
-          acc = fmaf(qs[i * 8 + 2 * j + 1], bf16_hi(w[j]), acc);
+        for (int j = 0; j < 8; ++j) {
+          acc = fmaf(qreg[2 * j], bf16_lo(u[i].v[j]), acc);
+          acc = fmaf(qreg[2 * j + 1], bf16_hi(u[i].v[j]), acc);
         }
       }
-      s = bf16r(acc);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      const float sv = live[i] ? bf16r(acc) : -INFINITY;
+      if (in[i] && sub == 0) sc[l - l0] = sv;
+      if (in[i]) mx = fmaxf(mx, sv);
     }
-    sc[l - l0] = s;
-    mx = fmaxf(mx, s);
   }
   mx = block_reduce_max(mx, red);
   if (nsplit > 1) {  // exact softmax across the cluster: exchange the local maxima
@@ -117,23 +134,40 @@ __global__ void __launch_bounds__(DEC_THREADS)
   }
   const float inv = 1.0f / sum;
 
-  const int warp = tid >> 5, lane = tid & 31;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
-  for (int l = l0 + warp; l < l1; l += DEC_WARPS) {
-    const float p = bf16r(sc[l - l0] * inv);
-    if (p != 0.f) {  // masked keys have p == 0 (their values are zeroed in the reference, :135)
-      const uint2 u = *reinterpret_cast<const uint2*>(v + (base + l) * 128 + lane * 4);
-      a0 = fmaf(p, bf16_lo(u.x), a0);
-      a1 = fmaf(p, bf16_hi(u.x), a1);
-      a2 = fmaf(p, bf16_lo(u.y), a2);
-      a3 = fmaf(p, bf16_hi(u.y), a3);
+  // values: same access shape -- lane group `grp` takes keys lb + grp, a lane owns 16 of the 128 output dims
+  float a[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) a[j] = 0.f;
+  for (int lb = l0 + warp * 4; lb < l1; lb += DEC_WARPS * 4 * SU) {
+    U32x8 u[SU];
+    float pr[SU];
+#pragma unroll
+    for (int i = 0; i < SU; ++i) {
+      const int l = lb + i * DEC_WARPS * 4 + grp;
+      pr[i] = l < l1 ? bf16r(sc[l - l0] * inv) : 0.f;
+      // masked keys have p == 0 (their values are zeroed in the reference, :135): their rows are not read
+      if (pr[i] != 0.f) u[i] = ld_stream_256(v + (base + l) * 128 + sub * 16);
+    }
+#pragma unroll
+    for (int i = 0; i < SU; ++i) {
+      if (pr[i] != 0.f) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a[2 * j] = fmaf(pr[i], bf16_lo(u[i].v[j]), a[2 * j]);
+          a[2 * j + 1] = fmaf(pr[i], bf16_hi(u[i].v[j]), a[2 * j + 1]);
+        }
+      }
     }
   }
-  osum[warp][lane * 4 + 0] = a0;
-  osum[warp][lane * 4 + 1] = a1;
-  osum[warp][lane * 4 + 2] = a2;
-  osum[warp][lane * 4 + 3] = a3;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {  // fold the 4 lane groups of the warp
+    a[j] += __shfl_xor_sync(0xffffffffu, a[j], 8);
+    a[j] += __shfl_xor_sync(0xffffffffu, a[j], 16);
+  }
+  if (grp == 0) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) osum[warp][sub * 16 + j] = a[j];
+  }
   __syncthreads();
   float o = 0.f;
   if (tid < 128) {

@@ -543,7 +543,7 @@ def decode_core(layer: "CogVLMDecoderLayer", hf: torch.Tensor, position_ids: tor
 
     def gemm(a, w, out, mode, spec_pair, residual=None, rope=(), rope_cols=0, kv=(None, None, 0, None)):
         t, r, lb = [None, None], 0, [None] * 4
-        sk = skinny and all(sp.r % 32 == 0 for sp in spec_pair)
+        sk = skinny and all(sp.r % 64 == 0 for sp in spec_pair)
         for h, sp in enumerate(spec_pair):
             th, rh, bh = _lora_t_single(a, sp, counts, sk)
             if th is not None:

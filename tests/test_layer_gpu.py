@@ -687,12 +687,19 @@ def test_training_step_full_width_r64_vs_oracle_autograd():
     for k in ("input_layernorm.weight", "post_attention_layernorm.weight"):
         wf[k].requires_grad_(True)
     xr = inp.hidden_states.float().requires_grad_(True)
-    (ref,) = O.decoder_layer(wf, xr, inp.token_type_ids, inp.position_ids, pm, num_heads=heads, lora=adf)
+    # the fp32 oracle gets the rotary table a bf16-true run really uses (built in bf16 from the bf16 inv_freq, SURVEY
+    # section 0 quirk 2): the text tokens sit at positions 5 ... 260, where a table built in fp32 differs by tenths of a
+    # radian in the fast dimensions -- with an fp32-built table this test measured 8-10 % on exactly the four
+    # language-expert attention adapters and < 4 % everywhere else, i.e. it was measuring the table, not the kernels
+    table = O.rotary_tables(w["self_attn.rotary_emb.inv_freq"], int(inp.position_ids.max()) + 1)
+    (ref,) = O.decoder_layer(wf, xr, inp.token_type_ids, inp.position_ids, pm, num_heads=heads, lora=adf,
+                             cos_sin=table)
     (ref * proj.float()).sum().backward()
 
+    errs = {}
+
     def close(got, want, name, tol=4e-2):
-        e = float((got.float().cpu() - want).norm() / want.norm().clamp_min(1e-12))
-        assert e <= tol, (name, e)
+        errs[name] = float((got.float().cpu() - want).norm() / want.norm().clamp_min(1e-12))
 
     # the oracle runs in FP32 here (autograd reference); at this width the reference's own bf16 run is 6.9e-2 max-rel /
     # 1.2e-2 rel-Frobenius away from its fp32 run (SURVEY 8(c) calibration), so the forward is held to that envelope --
@@ -707,6 +714,8 @@ def test_training_step_full_width_r64_vs_oracle_autograd():
     close(layer.input_layernorm.modules_to_save["default"].weight.grad, wf["input_layernorm.weight"].grad, "ln1")
     close(layer.post_attention_layernorm.modules_to_save["default"].weight.grad,
           wf["post_attention_layernorm.weight"].grad, "ln2")
+    bad = {k: v for k, v in errs.items() if v > 4e-2}
+    assert not bad, (bad, {k: round(v, 4) for k, v in errs.items()}, (mx, fro))
 
 
 # ------------------------------------------------------------------------------------------ drop-in behaviour (round 2)
