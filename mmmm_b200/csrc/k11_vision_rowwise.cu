@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(K11_WARPS * 32, NCHUNK <= 8 ? 2 : 1)  // <= 12
   constexpr int H = NCHUNK * 256;
   __shared__ __align__(16) float w_s[H];
   __shared__ __align__(16) float b_s[H];
+#pragma unroll  // exactly H / 256 trips: unrolled so that all the (independent) loads are in flight at once
   for (int i = threadIdx.x; i < H; i += K11_WARPS * 32) {
     w_s[i] = __bfloat162float(weight[i]);
     b_s[i] = bias ? __bfloat162float(bias[i]) : 0.f;

@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(K7_WARPS * 32, NCHUNK >= 8 ? 1 : 2)
   __shared__ __align__(16) float w_s[H];
   __shared__ __align__(16) float dw_s[H];
   __shared__ float part[K7_WARPS][2];
+#pragma unroll  // exactly H / 256 trips: unrolled so that all the (independent) loads are in flight at once
   for (int i = threadIdx.x; i < H; i += K7_WARPS * 32) {
     w_s[i] = weight_is_fp32 ? static_cast<const float*>(weight)[i]
                             : __bfloat162float(static_cast<const __nv_bfloat16*>(weight)[i]);
