@@ -580,7 +580,7 @@ def run_train(args):
         l.recompute = bool(args.recompute)
     params = [p for l in layers for p in l.parameters() if p.requires_grad]
     overlapped = args.allreduce == "overlap"
-    reducer = BucketedGradReducer(layers) if overlapped else LoraGradReducer(params)
+    reducer = BucketedGradReducer(layers, layers_per_collective=args.ar_group or None) if overlapped else LoraGradReducer(params)
     host, total_tokens = make_shard_inputs(args)
     inp = host.to(dev)
     tokens = int(inp.padding_mask.sum())
@@ -678,8 +678,9 @@ def run_train(args):
                            recompute=bool(args.recompute),
                            mode=("train: fwd + recompute + bwd + LoRA-grad allreduce" if args.recompute else
                                  "train: fwd (activations kept in HBM) + bwd + LoRA-grad allreduce"),
-                           allreduce=("per-layer NCCL AVG issued from the layer's backward on a side stream; grads are "
-                                      "views of the flat bucket" if overlapped else "post-backward, packed (round 1)")),
+                           allreduce=((f"bucket views, NCCL AVG per {args.ar_group} layer(s) on a side stream during the "
+                                       f"backward" if args.ar_group else "bucket views, ONE NCCL AVG over the flat "
+                                       "bucket after the backward") if overlapped else "post-backward, packed (round 1)")),
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
             "allreduce_tail_ms": allreduce_ms, "allreduce_bytes": reducer.nbytes,
             "ms_per_step_without_collectives": ms_nocomm, "allreduce_exposed_ms": exposed,
@@ -935,8 +936,10 @@ def main():
     ap.add_argument("--lora-dropout", type=float, default=0.0, help="--train: lora_dropout (the reference uses 0.05)")
     ap.add_argument("--recompute", type=int, default=1, help="--train: 1 = checkpoint each layer like the reference "
                     "(save the input, recompute in backward); 0 = keep the activations in HBM (no recompute pass)")
-    ap.add_argument("--allreduce", default="overlap", choices=["overlap", "post"], help="--train: per-layer all-reduce "
-                    "overlapped with the backward (default) or the round-1 post-backward reducer")
+    ap.add_argument("--allreduce", default="overlap", choices=["overlap", "post"], help="--train: bucket-view reducer "
+                    "(default; gradients accumulate straight into the flat bucket) or the round-1 pack / unpack reducer")
+    ap.add_argument("--ar-group", type=int, default=0, help="--train: layers per NCCL collective, issued on a side stream "
+                    "during the backward (0 = ONE collective over the whole bucket after the backward, the default)")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the forward as one CUDA graph (default), 0: eager")
     ap.add_argument("--decode", action="store_true", help="SURVEY 8(f)-2: time graphed decode steps after a prefill")
     ap.add_argument("--vision", action="store_true", help="SURVEY 8(f)-4: time the EVA2-CLIP-E vision encoder instead")

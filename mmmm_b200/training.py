@@ -160,7 +160,7 @@ def layer_backward(layer, plan, position_ids: torch.Tensor, hidden_states: torch
     ops.copy_padded_rows(dof, plan.flat_to_sorted, d_hidden.view(cap, H))   # padded rows: identity path only
     ops.rmsnorm_backward(dxn1, hf, s2f, ln1.weight.detach(), ln1.variance_epsilon, dh1, None, d_hidden.view(cap, H), s2f,
                          sink.buffer(ln1.weight), n_valid)
-    if reducer is not None:  # this layer's gradients are complete: its all-reduce starts now, on the side stream
+    if reducer is not None:  # this layer's gradients are complete: cast its segment, maybe hand a layer group to NCCL
         reducer.layer_done(layer)
     return d_hidden, sink.result()
 
@@ -227,30 +227,35 @@ def layer_forward_train(layer, hidden_states: torch.Tensor, plan, position_ids: 
 # LoRA-gradient all-reduce (the only collective of the path)
 # --------------------------------------------------------------------------------------------------
 class BucketedGradReducer:
-    """Data-parallel averaging of the trainable gradients (LoRA A / B + modules_to_save norm copies), overlapped with
-    the backward -- the role of DDP's bucketed reducer in the reference (conf/phase-vlm/fit.yaml:11-15,
-    ``gradient_as_bucket_view``), restricted to the adapter tensors.
+    """Data-parallel averaging of the trainable gradients (LoRA A / B + modules_to_save norm copies) -- the role of
+    DDP's bucketed reducer in the reference (conf/phase-vlm/fit.yaml:11-15, ``gradient_as_bucket_view``), restricted to
+    the adapter tensors.
 
     * ONE flat fp32 accumulation buffer, laid out layer by layer.  The backward kernels (K8 weight gradients, K7 norm
       gradients: fp32 atomics) accumulate straight into a layer's segment -- no per-step gradient tensors, no pack.
-    * When a layer's backward finishes (``layer_done``, called from the layer's autograd node) its segment is
-      all-reduced (NCCL AVG) on a side stream while the backward of the next layer runs: one collective per layer,
-      ~18 MB at r = 64, issued 32 times per step.  bf16 parameters are reduced in bf16 (one cast of the segment,
-      half the bytes on the wire -- what DDP moves for bf16 params); fp32 parameters are reduced in place.
     * ``p.grad`` of every trainable tensor is a VIEW into the flat communication buffer (bucket view): no unpack.
-    * ``finish()`` makes the caller's stream wait for the outstanding collectives; ``zero()`` clears the accumulators
-      for the next step (gradient accumulation over micro-batches = call ``zero()`` once per optimiser step).
+      bf16 parameters are reduced in bf16 (each layer's segment is cast once, right after its backward: half the bytes
+      on the wire, what DDP moves for bf16 params); fp32 parameters are reduced in place.
+    * Collectives are NCCL ``AVG`` over contiguous ranges of ``layers_per_collective`` layers, issued on a side stream
+      as soon as the range's last layer has finished its backward; ``finish()`` reduces whatever is left and joins.
 
-    Only the last layer's collective (layer 0, the end of the backward) is exposed."""
+    How many collectives: the forward / backward kernels of this path are PERSISTENT with one CTA per SM and a static
+    tile assignment, so a concurrently resident NCCL kernel does not "fill gaps" -- the SMs it occupies delay the CTAs
+    of the next GEMM and stretch that whole launch.  Measured on 2 B200 (round 2, 32 layers, 573 MB): one collective
+    per layer (32 per step) cost 58 ms of step time; one collective over the whole bucket after the backward costs about
+    the wire time.  The default is therefore ONE collective (``layers_per_collective = None``) and the knob is kept for
+    A/B runs (``bench.py --train --ar-group G``)."""
 
-    def __init__(self, layers, process_group=None):
+    def __init__(self, layers, process_group=None, layers_per_collective: Optional[int] = None):
         self.group = process_group
         self.layers = list(layers)
+        self.per = layers_per_collective if layers_per_collective and layers_per_collective > 0 else len(self.layers)
         self.segments: Dict[int, Tuple[int, int]] = {}   # id(layer) -> [lo, hi) in elements
+        self.index: Dict[int, int] = {}                  # id(layer) -> position in self.layers
         self.slots: Dict[int, Tuple[int, int]] = {}      # id(param) -> [lo, hi)
         self.params: List[torch.Tensor] = []
         off = 0
-        for layer in self.layers:
+        for i, layer in enumerate(self.layers):
             lo = off
             for p in trainable_tensors(layer):
                 if id(p) in self.slots:
@@ -259,6 +264,7 @@ class BucketedGradReducer:
                 self.params.append(p)
                 off += (p.numel() + 3) // 4 * 4          # keep every slot 16-byte aligned
             self.segments[id(layer)] = (lo, off)
+            self.index[id(layer)] = i
             layer._vex_grad_reducer = self
         dev = self.params[0].device if self.params else "cpu"
         self.acc = torch.zeros(off, dtype=torch.float32, device=dev)
@@ -271,6 +277,8 @@ class BucketedGradReducer:
             lo, hi = self.slots[id(p)]
             src = self.comm if p.dtype == self.comm_dtype else None
             self._views[id(p)] = None if src is None else src[lo:hi].view_as(p)
+        self._done = set()       # layer positions whose backward has finished this step
+        self._reduced = set()    # group numbers already handed to NCCL this step
         self._pending = False
 
     @property
@@ -290,32 +298,55 @@ class BucketedGradReducer:
             return 1
         return dist.get_world_size(self.group)
 
-    def layer_done(self, layer) -> None:
+    def _group_range(self, g: int) -> Tuple[int, int, range]:
+        members = range(g * self.per, min((g + 1) * self.per, len(self.layers)))
+        lo = self.segments[id(self.layers[members[0]])][0]
+        hi = self.segments[id(self.layers[members[-1]])][1]
+        return lo, hi, members
+
+    def _reduce_range(self, lo: int, hi: int, side: bool) -> None:
         import torch.distributed as dist
-        lo, hi = self.segments[id(layer)]
-        if hi == lo:
-            return
         world = self._world()
-        if self.stream is None:  # CPU (gloo tests): synchronous
-            if self.comm is not self.acc:
-                self.comm[lo:hi].copy_(self.acc[lo:hi])
-            if world > 1:
-                dist.all_reduce(self.comm[lo:hi], group=self.group)
-                self.comm[lo:hi].div_(world)
+        if world == 1 or hi == lo:
             return
-        self.stream.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self.stream):
-            if self.comm is not self.acc:
-                self.comm[lo:hi].copy_(self.acc[lo:hi])
-            if world > 1:
+        if self.stream is None:  # CPU (gloo tests): synchronous, gloo has no AVG
+            dist.all_reduce(self.comm[lo:hi], group=self.group)
+            self.comm[lo:hi].div_(world)
+            return
+        if side:
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
                 dist.all_reduce(self.comm[lo:hi], op=dist.ReduceOp.AVG, group=self.group)
-        self._pending = True
+            self._pending = True
+        else:
+            dist.all_reduce(self.comm[lo:hi], op=dist.ReduceOp.AVG, group=self.group)
+
+    def layer_done(self, layer) -> None:
+        """Called from the layer's autograd node when its gradients are complete."""
+        lo, hi = self.segments[id(layer)]
+        if hi > lo and self.comm is not self.acc:
+            self.comm[lo:hi].copy_(self.acc[lo:hi])      # one cast of the segment, in stream order behind the backward
+        i = self.index[id(layer)]
+        self._done.add(i)
+        g = i // self.per
+        glo, ghi, members = self._group_range(g)
+        n_groups = (len(self.layers) + self.per - 1) // self.per
+        if n_groups > 1 and g not in self._reduced and all(m in self._done for m in members):
+            self._reduce_range(glo, ghi, side=True)      # overlaps the backward of the layers below
+            self._reduced.add(g)
 
     def finish(self) -> None:
-        """Joins the side stream and publishes the gradients (``p.grad`` = bucket views)."""
+        """Reduces what has not been reduced yet, joins the side stream and publishes ``p.grad`` (bucket views)."""
+        n_groups = (len(self.layers) + self.per - 1) // self.per
+        for g in range(n_groups):
+            if g not in self._reduced:
+                lo, hi, _ = self._group_range(g)
+                self._reduce_range(lo, hi, side=False)
         if self.stream is not None and self._pending:
             torch.cuda.current_stream().wait_stream(self.stream)
             self._pending = False
+        self._done.clear()
+        self._reduced.clear()
         for p in self.params:
             v = self._views[id(p)]
             if v is None:  # mixed dtypes: this parameter is not in the communication dtype
