@@ -580,7 +580,7 @@ def run_train(args):
         l.recompute = bool(args.recompute)
     params = [p for l in layers for p in l.parameters() if p.requires_grad]
     overlapped = args.allreduce == "overlap"
-    reducer = BucketedGradReducer(layers, layers_per_collective=args.ar_group or None) if overlapped else LoraGradReducer(params)
+    reducer = BucketedGradReducer(layers, layers_per_collective=args.ar_group) if overlapped else LoraGradReducer(params)
     host, total_tokens = make_shard_inputs(args)
     inp = host.to(dev)
     tokens = int(inp.padding_mask.sum())
@@ -938,8 +938,8 @@ def main():
                     "(save the input, recompute in backward); 0 = keep the activations in HBM (no recompute pass)")
     ap.add_argument("--allreduce", default="overlap", choices=["overlap", "post"], help="--train: bucket-view reducer "
                     "(default; gradients accumulate straight into the flat bucket) or the round-1 pack / unpack reducer")
-    ap.add_argument("--ar-group", type=int, default=0, help="--train: layers per NCCL collective, issued on a side stream "
-                    "during the backward (0 = ONE collective over the whole bucket after the backward, the default)")
+    ap.add_argument("--ar-group", type=int, default=8, help="--train: layers per NCCL collective, issued on a side stream "
+                    "during the backward (default 8; 0 = ONE collective over the whole bucket after the backward)")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the forward as one CUDA graph (default), 0: eager")
     ap.add_argument("--decode", action="store_true", help="SURVEY 8(f)-2: time graphed decode steps after a prefill")
     ap.add_argument("--vision", action="store_true", help="SURVEY 8(f)-4: time the EVA2-CLIP-E vision encoder instead")

@@ -94,25 +94,31 @@ __device__ __forceinline__ void mma_chunk(float (&c)[2][NB][4], const WFrag<TILE
   }
 }
 
-// accumulates over the 64-element chunks this warp owns (chunk i = warp, warp + 8, ...), software-pipelined: the next
-// chunk's weight loads are issued before the current chunk's MMAs, so every warp has loads in flight all the time
+// accumulates over the 64-element chunks this warp owns (chunk i = warp, warp + 8, ...), software-pipelined through a
+// ring of NBUF register fragments: NBUF - 1 chunks are in flight while one is multiplied, so a warp always has loads
+// outstanding.  One-tile launches (dense / down: only 256 CTAs, < 2 per SM) run 4 deep, two-tile launches 2 deep
+// (a fragment is 16 registers per tile; batches above 16 rows keep 2 for their extra accumulators).
 template <int NB, int TILES>
 __device__ __forceinline__ void accumulate(float (&c)[2][NB][4], const __nv_bfloat16* const* wrow_lo,
                                            const __nv_bfloat16* const* wrow_hi, const __nv_bfloat16* const* xrow,
                                            const bool* xlive, int K, int warp, int t) {
+  constexpr int NBUF = (TILES == 1 && NB <= 2) ? 4 : 2;
   const int nchunks = K >> 6;
-  WFrag<TILES> f0, f1;
-  int i = warp;
-  if (i < nchunks) load_w<TILES>(f0, wrow_lo, wrow_hi, (i << 6) + 16 * t);
-  while (i < nchunks) {
-    const int i1 = i + DG_WARPS;
-    if (i1 < nchunks) load_w<TILES>(f1, wrow_lo, wrow_hi, (i1 << 6) + 16 * t);
-    mma_chunk<NB, TILES>(c, f0, xrow, xlive, (i << 6) + 16 * t);
-    if (i1 >= nchunks) break;
-    const int i2 = i1 + DG_WARPS;
-    if (i2 < nchunks) load_w<TILES>(f0, wrow_lo, wrow_hi, (i2 << 6) + 16 * t);
-    mma_chunk<NB, TILES>(c, f1, xrow, xlive, (i1 << 6) + 16 * t);
-    i = i2;
+  WFrag<TILES> f[NBUF];
+#pragma unroll
+  for (int b = 0; b < NBUF - 1; ++b) {
+    const int ip = warp + b * DG_WARPS;
+    if (ip < nchunks) load_w<TILES>(f[b], wrow_lo, wrow_hi, (ip << 6) + 16 * t);
+  }
+  for (int i = warp; i < nchunks; i += DG_WARPS * NBUF) {
+#pragma unroll
+    for (int b = 0; b < NBUF; ++b) {
+      const int ic = i + b * DG_WARPS;                  // chunk multiplied now: lives in f[b]
+      if (ic >= nchunks) break;
+      const int ip = ic + (NBUF - 1) * DG_WARPS;        // chunk prefetched into the slot consumed one step ago
+      if (ip < nchunks) load_w<TILES>(f[(b + NBUF - 1) % NBUF], wrow_lo, wrow_hi, (ip << 6) + 16 * t);
+      mma_chunk<NB, TILES>(c, f[b], xrow, xlive, (ic << 6) + 16 * t);
+    }
   }
 }
 

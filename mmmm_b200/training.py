@@ -238,18 +238,20 @@ class BucketedGradReducer:
       on the wire, what DDP moves for bf16 params); fp32 parameters are reduced in place.
     * Collectives are NCCL ``AVG`` over contiguous ranges of ``layers_per_collective`` layers, issued on a side stream
       as soon as the range's last layer has finished its backward; ``finish()`` reduces whatever is left and joins.
-
     How many collectives: the forward / backward kernels of this path are PERSISTENT with one CTA per SM and a static
     tile assignment, so a concurrently resident NCCL kernel does not "fill gaps" -- the SMs it occupies delay the CTAs
-    of the next GEMM and stretch that whole launch.  Measured on 2 B200 (round 2, 32 layers, 573 MB): one collective
-    per layer (32 per step) cost 58 ms of step time; one collective over the whole bucket after the backward costs about
-    the wire time.  The default is therefore ONE collective (``layers_per_collective = None``) and the knob is kept for
-    A/B runs (``bench.py --train --ar-group G``)."""
+    of the next GEMM and stretch that whole launch, and every collective also costs a cast + two stream joins.
+    Measured on 2 B200 (round 2, 32 layers, r = 64, 573 MB of bf16 gradients, ~445 ms step): one collective per LAYER
+    (32 per step) cost tens of ms of step time; groups of 8 layers (4 collectives, 143 MB each, the first three hidden
+    behind the backward of the layers below) and one collective over the whole bucket both land within +-2 ms of the
+    step without any collective (profiles/r2_train_allreduce.md).  Default: 8 layers per collective, the layer-group
+    scheme of SURVEY 8(e); ``layers_per_collective=0`` = one collective after the backward."""
 
-    def __init__(self, layers, process_group=None, layers_per_collective: Optional[int] = None):
+    def __init__(self, layers, process_group=None, layers_per_collective: Optional[int] = 8):
         self.group = process_group
         self.layers = list(layers)
         self.per = layers_per_collective if layers_per_collective and layers_per_collective > 0 else len(self.layers)
+        self.per = max(1, min(self.per, len(self.layers)))
         self.segments: Dict[int, Tuple[int, int]] = {}   # id(layer) -> [lo, hi) in elements
         self.index: Dict[int, int] = {}                  # id(layer) -> position in self.layers
         self.slots: Dict[int, Tuple[int, int]] = {}      # id(param) -> [lo, hi)

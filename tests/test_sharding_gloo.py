@@ -55,7 +55,7 @@ def _worker(rank, world, port, tmp):
         # the overlapped variant: kernels accumulate into a layer's segment of the flat fp32 buffer, the segment is
         # all-reduced when the layer's backward is done, p.grad is a bucket view (no pack / unpack)
         from mmmm_b200.training import BucketedGradReducer
-        for dtype, per in ((torch.float32, None), (torch.bfloat16, None), (torch.bfloat16, 1)):
+        for dtype, per in ((torch.float32, 0), (torch.bfloat16, 8), (torch.bfloat16, 1)):
             mods = [torch.nn.Linear(3, 5).to(dtype), torch.nn.Linear(2, 2, bias=False).to(dtype)]
             mods[0].bias.requires_grad_(False)
             br = BucketedGradReducer(mods, layers_per_collective=per)   # one collective at the end / one per layer
