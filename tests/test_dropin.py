@@ -129,3 +129,32 @@ def test_rotary_module_keeps_reference_table_semantics():
     assert torch.equal(cos[256], cos[257])
     c3, s3 = rot(torch.zeros(1, dtype=torch.bfloat16), seq_len=10)  # reference forward signature
     assert c3.shape == (10, 1, 128)
+
+
+def test_plan_cache_key_tolerates_inference_tensors():
+    """Inference tensors (torch.inference_mode -- how scripts/evaluate/models/mmmm.py:132 calls generate) have no
+    version counter; the plan-cache key must not touch `_version` on them."""
+    import torch
+    from mmmm_b200.plan import _version_of
+    a = torch.zeros(2, 3, dtype=torch.long)
+    v0 = _version_of(a)
+    a.add_(1)
+    assert _version_of(a) != v0                       # normal tensors: in-place edits invalidate the plan
+    with torch.inference_mode():
+        b = torch.zeros(2, 3, dtype=torch.long)
+    key = _version_of(b)                              # would raise "Inference tensors do not track version counter"
+    assert key[0] == "inference" and key == _version_of(b)
+
+
+def test_kv_cache_view_capacity_detection():
+    """Tuple-cache decode appends in place only into views of a buffer with room left (modeling_cogvlm._cache_capacity)."""
+    import torch
+    from mmmm_b200.modeling_cogvlm import _cache_capacity, _full_cache_view
+    kv = torch.zeros(2, 3, 4, 10, 128)                # [k|v, B, heads, capacity, 128]
+    k, v = kv[0][:, :, :7], kv[1][:, :, :7]
+    assert _cache_capacity(k) == 10 and _cache_capacity(v) == 10           # v starts at a storage offset
+    full = _full_cache_view(v, 10)
+    assert full.shape == (3, 4, 10, 128) and full.data_ptr() == kv[1].data_ptr()
+    assert _cache_capacity(k.contiguous()) == 7                             # exactly full: no room -> re-allocate
+    assert _cache_capacity(torch.zeros(3, 4, 7, 64)) == 0                   # wrong head_dim
+    assert _cache_capacity(kv[0].transpose(1, 2)[:, :, :3]) == 0            # not the cache layout
