@@ -721,16 +721,19 @@ __device__ __forceinline__ void store_grad_row_early(uint32_t taddr, bool rope, 
 //   g  : 64-row steps so far (q / s / p rings, 2 deep)         it : valid items so far (resident operands, accumulators)
 // =============================================================================================
 constexpr int K9P_SCHED = 2;
-constexpr int K9P_MAXQ = 4;
+constexpr int K9P_MAXQ = 5;
 // Ring depth of the streamed 64-row tiles.  A slot is only free again when the step's LAST MMAs (dV / dK resp. dQ, which
 // read the tile as an MN-major B operand) have completed, so with 2 slots the load of step g + 2 could not start before
 // step g was completely done and every step paid a full TMA latency (~2 000 cycles against 1 024 cycles of tensor work:
 // ncu showed the tensor pipe 29 % active whatever the softmax arrangement).  dK/dV: 3 slots (shared memory is then full:
 // 226 KB); dQ: 4.
-constexpr int K9P_NQ_A = 3;
-constexpr int K9P_NQ_B = 4;
-constexpr int ABA_SMEM_P = ABA_SMEM + (K9P_NQ_A - 2) * 2 * AB_T64;
-constexpr int ABB_SMEM_P = ABB_SMEM + (K9P_NQ_B - 2) * 2 * AB_T64;
+// P^T / dS^T (dK/dV) and dS (dQ) live in TMEM, written by the softmax thread of the row with tcgen05.st over the first
+// 32 columns of the S / dP buffer it has just read (A operand of tcgen05.mma from TMEM): the 2 x 32 KB (2 x 16 KB) of
+// shared memory they used go to the ring -- 5 slots for both kernels (3 / 4 with P / dS in shared memory).
+constexpr int K9P_NQ_A = 5;
+constexpr int K9P_NQ_B = 5;
+constexpr int ABA_SMEM_P = ABA_SMEM - 4 * AB_P + (K9P_NQ_A - 2) * 2 * AB_T64;
+constexpr int ABB_SMEM_P = ABB_SMEM - 2 * AB_P + (K9P_NQ_B - 2) * 2 * AB_T64;
 static_assert(ABA_SMEM_P <= 232448 && ABB_SMEM_P <= 232448, "shared memory per CTA");
 constexpr int K9P_READERS = 9;  // MMA warp + 8 softmax warps (lane 0 arrives)
 constexpr int K9P_NCOUNTERS = 2048;
@@ -749,7 +752,7 @@ struct BarsP {
   K9Item item[K9P_SCHED];
   uint32_t tmem_base;
 };
-static_assert(sizeof(BarsP) <= 256, "barrier block");
+static_assert(sizeof(BarsP) <= 256, "barrier block");  // the layouts reserve 256 bytes behind the last tile
 
 // `reverse`: block index counted from the end of the group (dQ: the LAST query block is the heaviest, take it first)
 __device__ __forceinline__ void k9p_decode(int it, int nblk, int heads, const int32_t* __restrict__ cu_seqlens,
@@ -825,9 +828,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
   constexpr int NQ = K9P_NQ_A;
   uint8_t* sQ = smem + 2 * AB_T128;              // NQ stages of AB_T64
   uint8_t* sdO = sQ + NQ * AB_T64;               // NQ stages
-  uint8_t* sP = sdO + NQ * AB_T64;               // 2 stages of AB_P
-  uint8_t* sdS = sP + 2 * AB_P;                  // 2 stages
-  float* sStat = reinterpret_cast<float*>(sdS + 2 * AB_P);  // [2][128]: lse (64) | delta (64) of the step's queries
+  float* sStat = reinterpret_cast<float*>(sdO + NQ * AB_T64);  // [2][128]: lse (64) | delta (64) of a group's step
   BarsP* bars = reinterpret_cast<BarsP*>(sStat + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -882,8 +883,6 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     const uint64_t ddOk0 = umma_desc_kmajor_sw128(smem_u32(sdO));
     const uint64_t dQm0 = umma_desc_mnmajor_sw128(smem_u32(sQ), AB_T64 / 2, 1024);
     const uint64_t ddOm0 = umma_desc_mnmajor_sw128(smem_u32(sdO), AB_T64 / 2, 1024);
-    const uint64_t dPk0 = umma_desc_kmajor_sw128(smem_u32(sP));
-    const uint64_t ddSk0 = umma_desc_kmajor_sw128(smem_u32(sdS));
     auto issue_s = [&](int gg) {  // S^T = K Q^T and dP^T = V dO^T of global step gg into the S / dP buffer gg & 1
       const int st = gg & 1, sq = gg % NQ;
       mbar_wait(&bars->q_full[sq], (gg / NQ) & 1);
@@ -927,15 +926,14 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
         tc_fence_after();
         if (elect_one_sync()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_ss(tdV, (dPk0 + static_cast<uint64_t>(st * (AB_P >> 4))) + static_cast<uint64_t>((kk * 32) >> 4), (ddOm0 + static_cast<uint64_t>(sq * (AB_T64 >> 4))) + static_cast<uint64_t>((kk * 2048) >> 4),
+          for (int kk = 0; kk < 4; ++kk)  // A = P^T from TMEM: 16 queries = 8 packed columns per K step
+            umma_ts(tdV, tS + st * 64 + kk * 8, (ddOm0 + static_cast<uint64_t>(sq * (AB_T64 >> 4))) + static_cast<uint64_t>((kk * 2048) >> 4),
                     idesc_acc, (s > 0) || (kk > 0));
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_ss(tdK, (ddSk0 + static_cast<uint64_t>(st * (AB_P >> 4))) + static_cast<uint64_t>((kk * 32) >> 4), (dQm0 + static_cast<uint64_t>(sq * (AB_T64 >> 4))) + static_cast<uint64_t>((kk * 2048) >> 4),
+          for (int kk = 0; kk < 4; ++kk)  // A = dS^T from TMEM
+            umma_ts(tdK, tdP + st * 64 + kk * 8, (dQm0 + static_cast<uint64_t>(sq * (AB_T64 >> 4))) + static_cast<uint64_t>((kk * 2048) >> 4),
                     idesc_acc, (s > 0) || (kk > 0));
           umma_commit(&bars->q_empty[sq]);
-          umma_commit(&bars->p_empty[st]);
         }
         __syncwarp();
       }
@@ -1044,13 +1042,11 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
             }
           }
         }
-        mbar_wait(&bars->p_empty[st], ph ^ 1);  // the MMAs of step gs - 2 have finished reading this P / dS buffer
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          store_row_half(smem_u32(sP + st * AB_P), c, hf, pk[hf]);
-          store_row_half(smem_u32(sdS + st * AB_P), c, hf, dk[hf]);
-        }
-        fence_proxy_async_smem();
+        // P^T / dS^T of this key row -> the first 32 columns of the S / dP buffer just read (lane-private rows: no other
+        // thread touches them; the next S / dP into this buffer is issued behind the MMAs that read P / dS, in pipe order)
+        tmem_st_32x32b_x32(tS + lane_sel + st * 64, *reinterpret_cast<uint32_t(*)[32]>(&pk[0][0]));
+        tmem_st_32x32b_x32(tdP + lane_sel + st * 64, *reinterpret_cast<uint32_t(*)[32]>(&dk[0][0]));
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->p_full[st]);
@@ -1095,8 +1091,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
   constexpr int NQ = K9P_NQ_B;
   uint8_t* sK = smem + 2 * AB_T128;  // NQ stages of AB_T64
   uint8_t* sV = sK + NQ * AB_T64;    // NQ stages
-  uint8_t* sdS = sV + NQ * AB_T64;   // 2 stages of AB_P
-  BarsP* bars = reinterpret_cast<BarsP*>(sdS + 2 * AB_P);
+  BarsP* bars = reinterpret_cast<BarsP*>(sV + NQ * AB_T64);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) k9p_init(bars);
@@ -1148,7 +1143,6 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     const uint64_t dKk0 = umma_desc_kmajor_sw128(smem_u32(sK));
     const uint64_t dVk0 = umma_desc_kmajor_sw128(smem_u32(sV));
     const uint64_t dKm0 = umma_desc_mnmajor_sw128(smem_u32(sK), AB_T64 / 2, 1024);
-    const uint64_t ddSk0 = umma_desc_kmajor_sw128(smem_u32(sdS));
     auto issue_s = [&](int gg) {
       const int st = gg & 1, sq = gg % NQ;
       mbar_wait(&bars->q_full[sq], (gg / NQ) & 1);
@@ -1192,11 +1186,10 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
         tc_fence_after();
         if (elect_one_sync()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_ss(tdQ, (ddSk0 + static_cast<uint64_t>(st * (AB_P >> 4))) + static_cast<uint64_t>((kk * 32) >> 4), (dKm0 + static_cast<uint64_t>(sq * (AB_T64 >> 4))) + static_cast<uint64_t>((kk * 2048) >> 4),
+          for (int kk = 0; kk < 4; ++kk)  // A = dS from TMEM: 16 keys = 8 packed columns per K step
+            umma_ts(tdQ, tdP + st * 64 + kk * 8, (dKm0 + static_cast<uint64_t>(sq * (AB_T64 >> 4))) + static_cast<uint64_t>((kk * 2048) >> 4),
                     idesc_acc, (s > 0) || (kk > 0));
           umma_commit(&bars->q_empty[sq]);
-          umma_commit(&bars->p_empty[st]);
         }
         __syncwarp();
       }
@@ -1266,10 +1259,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
             }
           }
         }
-        mbar_wait(&bars->p_empty[st], ph ^ 1);
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) store_row_half(smem_u32(sdS + st * AB_P), c, hf, dk[hf]);
-        fence_proxy_async_smem();
+        tmem_st_32x32b_x32(tdP + lane_sel + st * 64, *reinterpret_cast<uint32_t(*)[32]>(&dk[0][0]));  // dS over dP
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->p_full[st]);
