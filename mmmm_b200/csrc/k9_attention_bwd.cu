@@ -746,7 +746,7 @@ struct K9Item {  // valid: 1 = work, 0 = block past the sample's end, -1 = work 
 struct BarsP {
   uint64_t res_full, res_empty;                       // resident operands (K,V / Q,dO) of the item
   uint64_t q_full[K9P_MAXQ], q_empty[K9P_MAXQ];       // streamed 64-row tiles (ring of NQ stages)
-  uint64_t s_full[2], p_full[2], p_empty[2];
+  uint64_t s_full[3], p_full[3];                      // S / dP buffers in TMEM: 2 (dK/dV) or 3 (dQ)
   uint64_t acc_full, acc_empty;
   uint64_t sched_full[K9P_SCHED], sched_empty[K9P_SCHED];
   K9Item item[K9P_SCHED];
@@ -801,10 +801,9 @@ __device__ __forceinline__ void k9p_init(BarsP* bars) {
     mbar_init(&bars->q_full[i], 1);
     mbar_init(&bars->q_empty[i], 1);
   }
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 3; ++i) {
     mbar_init(&bars->s_full[i], 1);
-    mbar_init(&bars->p_full[i], 4);   // the four warps of the softmax group that owns buffer i
-    mbar_init(&bars->p_empty[i], 1);
+    mbar_init(&bars->p_full[i], 4);   // the four warps of the softmax group that handles the step
   }
   mbar_init(&bars->acc_full, 1);
   mbar_init(&bars->acc_empty, 8);
@@ -1105,7 +1104,11 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
-  const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256;
+  // dQ uses 384 of the 512 TMEM columns with two S / dP buffers: the spare 128 hold a THIRD buffer, so S / dP of step
+  // g + 2 can be issued while step g is still in its softmax (with two buffers the chain S -> softmax -> dQ MMA -> next S
+  // is serial per buffer and each softmax group waits ~800 cycles for its next S)
+  constexpr int NS = 3;
+  const uint32_t tS = tmem, tdP = tmem + NS * 64, tdQ = tmem + 2 * NS * 64;
 
   if (warp == 0 && lane == 0) {
     // =============================== scheduler + TMA producer ===============================
@@ -1144,7 +1147,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     const uint64_t dVk0 = umma_desc_kmajor_sw128(smem_u32(sV));
     const uint64_t dKm0 = umma_desc_mnmajor_sw128(smem_u32(sK), AB_T64 / 2, 1024);
     auto issue_s = [&](int gg) {
-      const int st = gg & 1, sq = gg % NQ;
+      const int st = gg % NS, sq = gg % NQ;
       mbar_wait(&bars->q_full[sq], (gg / NQ) & 1);
       tc_fence_after();
       if (elect_one_sync()) {
@@ -1167,21 +1170,18 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
       if (w.valid == 0) continue;
       const int n_steps = min((w.len + 63) / 64, 2 * w.blk + 2);
       mbar_wait(&bars->res_full, it & 1);
-      issue_s(g);
-      if (n_steps == 1) {
-        if (elect_one_sync()) umma_commit(&bars->res_empty);
-        __syncwarp();
-      }
+      const int g_end = g + n_steps;
+      int issued = g;  // next step whose S / dP has not been issued yet; runs up to NS - 1 steps ahead of the dQ MMAs
       for (int s = 0; s < n_steps; ++s, ++g) {
-        if (s + 1 < n_steps) {
-          issue_s(g + 1);
-          if (s + 2 == n_steps) {
+        while (issued < g_end && issued < g + NS) {
+          issue_s(issued);
+          if (++issued == g_end) {  // the item's last S / dP is on its way: Q and dO may be overwritten once it completes
             if (elect_one_sync()) umma_commit(&bars->res_empty);
             __syncwarp();
           }
         }
-        const int st = g & 1, sq = g % NQ;
-        mbar_wait(&bars->p_full[st], (g >> 1) & 1);
+        const int st = g % NS, sq = g % NQ;
+        mbar_wait(&bars->p_full[st], (g / NS) & 1);
         if (s == 0 && it > 0) mbar_wait(&bars->acc_empty, (it - 1) & 1);
         tc_fence_after();
         if (elect_one_sync()) {
@@ -1228,8 +1228,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
       }
       for (int s = ((g & 1) == grp) ? 0 : 1; s < n_steps; s += 2) {
         const int gs = g + s;
-        const int st = grp;
-        const uint32_t ph = (gs >> 1) & 1;
+        const int st = gs % NS;
+        const uint32_t ph = (gs / NS) & 1;
         mbar_wait(&bars->s_full[st], ph);
         tc_fence_after();
         const bool interior = (s * 64 + 63 <= q0) && (q0 + 128 <= len);
