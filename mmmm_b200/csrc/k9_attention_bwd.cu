@@ -182,7 +182,7 @@ __device__ __forceinline__ void store_grad_row(uint32_t taddr, bool rope, const 
 
 #ifdef VEX_ATTN_TRACE
 // timing experiment build (tools/attn_trace.py k9): cycle stamps of CTA (0, 0, 0) of the dK/dV kernel
-__device__ long long* g_k9_trace = nullptr;  // [64 steps][8 stamps], row 63 = CTA-level stamps
+__device__ long long* g_k9_trace = nullptr;  // grid kernel: [64 steps][8 stamps], row 63 = CTA-level stamps; dq_p: [256][16]
 extern "C" int vex_debug_k9_trace(long long* buf) {
   return cudaMemcpyToSymbol(g_k9_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -1;
 }
@@ -1093,6 +1093,19 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
   BarsP* bars = reinterpret_cast<BarsP*>(sV + NQ * AB_T64);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef VEX_ATTN_TRACE
+  // timing experiment build (tools/k9_trace.py): stamps of CTA 0 -- row = global step (< 256); columns 0..5 softmax warp 4
+  // (group 0: even steps), 8..11 MMA warp, 12 producer
+  long long* trc = (blockIdx.x == 0 && (threadIdx.x == 128 || threadIdx.x == 32 || threadIdx.x == 0)) ? g_k9_trace : nullptr;
+#define K9P_TRACE(row, col)                                                 \
+  do {                                                                      \
+    if (trc && (row) < 256) trc[(row) * 16 + (col)] = clock64();           \
+  } while (0)
+#else
+#define K9P_TRACE(row, col) \
+  do {                      \
+  } while (0)
+#endif
   if (threadIdx.x == 0) k9p_init(bars);
   if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
   if (warp == 0 && lane == 0) {
@@ -1130,6 +1143,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
         const int st = g % NQ;
         const int row = w.seq0 + s * 64;
         mbar_wait(&bars->q_empty[st], ((g / NQ) & 1) ^ 1);
+        K9P_TRACE(g, 12);
         mbar_arrive_expect_tx(&bars->q_full[st], 2 * AB_T64);
         tma_load_2d(sK + st * AB_T64, &tm_qkv64, &bars->q_full[st], colk, row);
         tma_load_2d(sK + st * AB_T64 + AB_T64 / 2, &tm_qkv64, &bars->q_full[st], colk + 64, row);
@@ -1173,6 +1187,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
       const int g_end = g + n_steps;
       int issued = g;  // next step whose S / dP has not been issued yet; runs up to NS - 1 steps ahead of the dQ MMAs
       for (int s = 0; s < n_steps; ++s, ++g) {
+        K9P_TRACE(g, 8);
         while (issued < g_end && issued < g + NS) {
           issue_s(issued);
           if (++issued == g_end) {  // the item's last S / dP is on its way: Q and dO may be overwritten once it completes
@@ -1181,8 +1196,10 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
           }
         }
         const int st = g % NS, sq = g % NQ;
+        K9P_TRACE(g, 9);
         mbar_wait(&bars->p_full[st], (g / NS) & 1);
         if (s == 0 && it > 0) mbar_wait(&bars->acc_empty, (it - 1) & 1);
+        K9P_TRACE(g, 10);
         tc_fence_after();
         if (elect_one_sync()) {
 #pragma unroll
@@ -1192,6 +1209,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
           umma_commit(&bars->q_empty[sq]);
         }
         __syncwarp();
+        K9P_TRACE(g, 11);
       }
       if (elect_one_sync()) umma_commit(&bars->acc_full);
       __syncwarp();
@@ -1230,8 +1248,10 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
         const int gs = g + s;
         const int st = gs % NS;
         const uint32_t ph = (gs / NS) & 1;
+        K9P_TRACE(gs, 0);
         mbar_wait(&bars->s_full[st], ph);
         tc_fence_after();
+        K9P_TRACE(gs, 1);
         const bool interior = (s * 64 + 63 <= q0) && (q0 + 128 <= len);
         uint32_t dk[2][16];
 #pragma unroll
@@ -1258,13 +1278,17 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
                                          k1 ? p1 * (__uint_as_float(draw[j + 1]) - dl) : 0.f);
             }
           }
+          K9P_TRACE(gs, 2 + hf);
         }
         tmem_st_32x32b_x32(tdP + lane_sel + st * 64, *reinterpret_cast<uint32_t(*)[32]>(&dk[0][0]));  // dS over dP
         tmem_st_wait();
+        K9P_TRACE(gs, 4);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->p_full[st]);
+        K9P_TRACE(gs, 5);
       }
+      K9P_TRACE(g + n_steps - 1, 6);   // item end (before the epilogue)
       g += n_steps;
       // ---- epilogue: dQ * scale through the rotary transpose -> dqkv[token_to_sorted[tok]] ----
       mbar_wait(&bars->acc_full, it & 1);
@@ -1276,6 +1300,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
                                 __syncwarp();
                                 if (lane == 0) mbar_arrive(&bars->acc_empty);
                               });
+      K9P_TRACE(g - 1, 7);             // epilogue done
       ++it;
     }
   }

@@ -56,6 +56,8 @@ def run():
     Lb.vex_debug_k9_trace.argtypes = [ctypes.c_void_p]
     assert Lb.vex_debug_k9_trace(0) == 0
     print(f"attention backward (delta + dkdv + dq): {timeit(call) * 1e3:.1f} us")
+    if os.environ.get("VEX_K9_IMPL", "persistent") != "grid":
+        return run_persistent(Lb, call)
     buf = torch.zeros(64 * 8, dtype=torch.int64, device="cuda")
     assert Lb.vex_debug_k9_trace(buf.data_ptr()) == 0
     call()
@@ -71,6 +73,26 @@ def run():
         if r[5] == 0:
             break
         print(f"  {s:2d} @ {r[0] - t0:7d} | " + " ".join(f"{r[i + 1] - r[i]:7d}" for i in range(5)) + f" | {r[5] - r[0]:6d}")
+
+
+def run_persistent(Lb, call):
+    """Stamps of CTA 0 of the persistent dQ kernel (k9_attn_bwd_dq_p): softmax warp 4 (group 0: even global steps), the MMA
+    warp and the producer thread, per global step."""
+    import torch
+    buf = torch.zeros(256 * 16, dtype=torch.int64, device="cuda")
+    assert Lb.vex_debug_k9_trace(buf.data_ptr()) == 0
+    call()
+    torch.cuda.synchronize()
+    t = buf.cpu().view(256, 16)
+    rows = [g for g in range(256) if int(t[g, 8]) or int(t[g, 0])]
+    t0 = min(int(v) for v in t[rows][:, [0, 8]].flatten() if int(v))
+    print("dQ persistent, CTA 0.  softmax (group 0, even steps): wait_S  pass0  pass1  st+wait  arrive | MMA: issueS  wait_P  issue_dQ | producer slot-free @")
+    for g in rows[:80]:
+        r = [int(v) for v in t[g]]
+        sm = "   ".join(f"{r[i + 1] - r[i]:6d}" for i in range(5)) if r[0] else " " * 42
+        mma = "   ".join(f"{r[i + 1] - r[i]:6d}" for i in range(8, 11)) if r[8] else ""
+        print(f"  g={g:3d} sm@{(r[0] - t0) if r[0] else 0:8d} | {sm} | mma@{(r[8] - t0) if r[8] else 0:8d} {mma} | prod@{(r[12] - t0) if r[12] else 0:8d}"
+              + (f"  ITEM END, epilogue {r[7] - r[6]}" if r[6] and r[7] else ""))
 
 
 if __name__ == "__main__":
