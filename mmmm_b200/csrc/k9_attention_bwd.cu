@@ -112,6 +112,12 @@ __device__ __forceinline__ void store_row_half(uint32_t tile, int row, int half,
   }
 }
 
+__device__ __forceinline__ uint4 ld_shared_v4_k9(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int n) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
@@ -706,6 +712,33 @@ __device__ __forceinline__ void store_grad_row_early(uint32_t taddr, bool rope, 
   }
 }
 
+// One 8-column slice (and its + 64 partner slice) of a drained gradient row: rotary transpose with the row's table
+// entries and two 16-byte stores.  `lo` / `hi` hold the row's packed bf16 pairs of columns [32 q, 32 q + 32) and
+// [64 + 32 q, ...); CH selects the slice statically (no dynamic register indexing).
+template <int CH>
+__device__ __forceinline__ void flush_rope_chunk(const uint32_t (&lo)[16], const uint32_t (&hi)[16],
+                                                 const __nv_bfloat16* cos_row, const __nv_bfloat16* sin_row,
+                                                 __nv_bfloat16* dst, int q) {
+  const int col = q * 32 + CH * 8;
+  const uint4 c_lo = __ldg(reinterpret_cast<const uint4*>(cos_row + col));
+  const uint4 s_hi = __ldg(reinterpret_cast<const uint4*>(sin_row + 64 + col));
+  const uint4 c_hi = __ldg(reinterpret_cast<const uint4*>(cos_row + 64 + col));
+  const uint4 s_lo = __ldg(reinterpret_cast<const uint4*>(sin_row + col));
+  const uint32_t cl[4] = {c_lo.x, c_lo.y, c_lo.z, c_lo.w}, sh[4] = {s_hi.x, s_hi.y, s_hi.z, s_hi.w};
+  const uint32_t chh[4] = {c_hi.x, c_hi.y, c_hi.z, c_hi.w}, sl[4] = {s_lo.x, s_lo.y, s_lo.z, s_lo.w};
+  uint32_t o_lo[4], o_hi[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t x = lo[CH * 4 + i], y = hi[CH * 4 + i];
+    o_lo[i] = pack_bf16(bf16_lo(x) * bf16_lo(cl[i]) + bf16_lo(y) * bf16_lo(sh[i]),
+                        bf16_hi(x) * bf16_hi(cl[i]) + bf16_hi(y) * bf16_hi(sh[i]));
+    o_hi[i] = pack_bf16(bf16_lo(y) * bf16_lo(chh[i]) - bf16_lo(x) * bf16_lo(sl[i]),
+                        bf16_hi(y) * bf16_hi(chh[i]) - bf16_hi(x) * bf16_hi(sl[i]));
+  }
+  *reinterpret_cast<uint4*>(dst + col) = make_uint4(o_lo[0], o_lo[1], o_lo[2], o_lo[3]);
+  *reinterpret_cast<uint4*>(dst + 64 + col) = make_uint4(o_hi[0], o_hi[1], o_hi[2], o_hi[3]);
+}
+
 // =============================================================================================
 // Persistent variants (round 2).  Same math, same buffers, same roles as the two kernels above; what changes is the
 // life cycle: ONE CTA per SM pulls (sample, head, block) items from a per-launch atomic counter and keeps its
@@ -748,6 +781,7 @@ struct BarsP {
   uint64_t q_full[K9P_MAXQ], q_empty[K9P_MAXQ];       // streamed 64-row tiles (ring of NQ stages)
   uint64_t s_full[3], p_full[3];                      // S / dP buffers in TMEM: 2 (dK/dV) or 3 (dQ)
   uint64_t acc_full, acc_empty;
+  uint64_t a_ready;                                   // dQ: the item's Q / dO rows have been copied into TMEM
   uint64_t sched_full[K9P_SCHED], sched_empty[K9P_SCHED];
   K9Item item[K9P_SCHED];
   uint32_t tmem_base;
@@ -794,9 +828,10 @@ __device__ __forceinline__ K9Item k9p_publish(BarsP* bars, int& n_fetch, unsigne
   return w;
 }
 
-__device__ __forceinline__ void k9p_init(BarsP* bars) {
+__device__ __forceinline__ void k9p_init(BarsP* bars, int res_empty_count) {
   mbar_init(&bars->res_full, 1);
-  mbar_init(&bars->res_empty, 1);
+  mbar_init(&bars->res_empty, res_empty_count);  // dK/dV: one tcgen05.commit; dQ: the 8 softmax warps (TMEM copy done)
+  mbar_init(&bars->a_ready, 8);
   for (int i = 0; i < K9P_MAXQ; ++i) {
     mbar_init(&bars->q_full[i], 1);
     mbar_init(&bars->q_empty[i], 1);
@@ -831,7 +866,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
   BarsP* bars = reinterpret_cast<BarsP*>(sStat + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) k9p_init(bars);
+  if (threadIdx.x == 0) k9p_init(bars, 1);
   if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_qkv128);
@@ -1106,7 +1141,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
   do {                      \
   } while (0)
 #endif
-  if (threadIdx.x == 0) k9p_init(bars);
+  if (threadIdx.x == 0) k9p_init(bars, 8);
   if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_qkv128);
@@ -1117,11 +1152,13 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
-  // dQ uses 384 of the 512 TMEM columns with two S / dP buffers: the spare 128 hold a THIRD buffer, so S / dP of step
-  // g + 2 can be issued while step g is still in its softmax (with two buffers the chain S -> softmax -> dQ MMA -> next S
-  // is serial per buffer and each softmax group waits ~800 cycles for its next S)
-  constexpr int NS = 3;
-  const uint32_t tS = tmem, tdP = tmem + NS * 64, tdQ = tmem + 2 * NS * 64;
+  // TMEM: S / dP double-buffered (2 x 64 + 2 x 64), dQ accumulator (128), and the item's Q and dO rows as TMEM-RESIDENT A
+  // OPERANDS (64 + 64 packed columns).  With A from shared memory an N = 64 MMA reads 6 KB per instruction and issues at
+  // ~68 cycles instead of 32 (cycle trace, profiles/r2_k9_attention_bwd.md: the steady state was operand-bandwidth
+  // bound); with Q / dO in TMEM it reads the 2 KB K / V slice only.  (A third S / dP buffer in these columns was
+  // measured first: no change.)
+  constexpr int NS = 2;
+  const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256, tQ = tmem + 384, tdO = tmem + 448;
 
   if (warp == 0 && lane == 0) {
     // =============================== scheduler + TMA producer ===============================
@@ -1156,7 +1193,6 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     // =============================== MMA issuer ===============================
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
     constexpr uint32_t idesc_acc = umma_idesc_bf16(128, 128, 0, 1);
-    const uint64_t dQ = umma_desc_kmajor_sw128(smem_u32(sQ)), ddO = umma_desc_kmajor_sw128(smem_u32(sdO));
     const uint64_t dKk0 = umma_desc_kmajor_sw128(smem_u32(sK));
     const uint64_t dVk0 = umma_desc_kmajor_sw128(smem_u32(sV));
     const uint64_t dKm0 = umma_desc_mnmajor_sw128(smem_u32(sK), AB_T64 / 2, 1024);
@@ -1167,11 +1203,11 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
       if (elect_one_sync()) {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_ss(tS + st * 64, dQ + static_cast<uint64_t>(((kk >> 2) * (AB_T128 / 2) + (kk & 3) * 32) >> 4),
+          umma_ts(tS + st * 64, tQ + kk * 8,   // A = Q rows from TMEM: 16 d = 8 packed columns per K step
                   (dKk0 + static_cast<uint64_t>(sq * (AB_T64 >> 4))) + static_cast<uint64_t>(((kk >> 2) * (AB_T64 / 2) + (kk & 3) * 32) >> 4), idesc_s, kk > 0);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_ss(tdP + st * 64, ddO + static_cast<uint64_t>(((kk >> 2) * (AB_T128 / 2) + (kk & 3) * 32) >> 4),
+          umma_ts(tdP + st * 64, tdO + kk * 8,
                   (dVk0 + static_cast<uint64_t>(sq * (AB_T64 >> 4))) + static_cast<uint64_t>(((kk >> 2) * (AB_T64 / 2) + (kk & 3) * 32) >> 4), idesc_s, kk > 0);
         umma_commit(&bars->s_full[st]);
       }
@@ -1183,17 +1219,15 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
       if (!k9p_next_item(bars, n_fetch, lane, w)) break;
       if (w.valid == 0) continue;
       const int n_steps = min((w.len + 63) / 64, 2 * w.blk + 2);
-      mbar_wait(&bars->res_full, it & 1);
+      mbar_wait(&bars->a_ready, it & 1);  // Q / dO of this item are in TMEM
+      tc_fence_after();
       const int g_end = g + n_steps;
       int issued = g;  // next step whose S / dP has not been issued yet; runs up to NS - 1 steps ahead of the dQ MMAs
       for (int s = 0; s < n_steps; ++s, ++g) {
         K9P_TRACE(g, 8);
         while (issued < g_end && issued < g + NS) {
           issue_s(issued);
-          if (++issued == g_end) {  // the item's last S / dP is on its way: Q and dO may be overwritten once it completes
-            if (elect_one_sync()) umma_commit(&bars->res_empty);
-            __syncwarp();
-          }
+          ++issued;
         }
         const int st = g % NS, sq = g % NQ;
         K9P_TRACE(g, 9);
@@ -1225,6 +1259,22 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     const int half = grp;              // epilogue: which 32 + 32 columns of dQ this thread stores
     const int c = ew * 32 + lane;
     const uint32_t lane_sel = static_cast<uint32_t>(ew * 32) << 16;
+    // DEFERRED EPILOGUE: the previous item's dQ row sits in packed registers (drained from TMEM right after its last
+    // step, accumulator released at once); its rotary transpose and stores are done one 8-column slice at a time in
+    // front of the s_full waits of the NEXT item's steps, where these warps idle anyway (cycle trace: ~1 400 cycles per
+    // step) -- the ~7 000-cycle store phase no longer delays the next item's first dS.
+    uint32_t pend_lo[16], pend_hi[16];
+    const __nv_bfloat16* pend_cos = nullptr;
+    const __nv_bfloat16* pend_sin = nullptr;
+    __nv_bfloat16* pend_dst = nullptr;
+    int pend_ch = 4;  // next slice to flush; 4 = nothing pending
+    auto flush_one = [&]() {
+      if (pend_ch == 0) flush_rope_chunk<0>(pend_lo, pend_hi, pend_cos, pend_sin, pend_dst, half);
+      else if (pend_ch == 1) flush_rope_chunk<1>(pend_lo, pend_hi, pend_cos, pend_sin, pend_dst, half);
+      else if (pend_ch == 2) flush_rope_chunk<2>(pend_lo, pend_hi, pend_cos, pend_sin, pend_dst, half);
+      else if (pend_ch == 3) flush_rope_chunk<3>(pend_lo, pend_hi, pend_cos, pend_sin, pend_dst, half);
+      if (pend_ch < 4) ++pend_ch;
+    };
     int n_fetch = 0, it = 0, g = 0;
     for (;;) {
       K9Item w;
@@ -1244,11 +1294,39 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
         const int64_t pz = __ldg(p.position_ids + (p.token_to_flat ? __ldg(p.token_to_flat + tok) : tok));
         pos = static_cast<int>(min(max(pz, int64_t(0)), int64_t(p.rope_len - 1)));
       }
+      {
+        // this thread's row of Q (group 0) / dO (group 1): shared memory (TMA's SWIZZLE_128B K-major layout) -> TMEM.
+        // All MMAs of the previous item are complete (its epilogue waited for acc_full), so tQ / tdO are free.
+        mbar_wait(&bars->res_full, it & 1);
+        const uint32_t src = smem_u32(grp == 0 ? sQ : sdO) + c * 128;
+        uint32_t rowv[64];
+#pragma unroll
+        for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const uint4 v4 = ld_shared_v4_k9(src + a2 * (AB_T128 / 2) + ((ch ^ (c & 7)) << 4));
+            rowv[a2 * 32 + ch * 4 + 0] = v4.x;
+            rowv[a2 * 32 + ch * 4 + 1] = v4.y;
+            rowv[a2 * 32 + ch * 4 + 2] = v4.z;
+            rowv[a2 * 32 + ch * 4 + 3] = v4.w;
+          }
+        const uint32_t ta = (grp == 0 ? tQ : tdO) + lane_sel;
+        tmem_st_32x32b_x32(ta, *reinterpret_cast<uint32_t(*)[32]>(&rowv[0]));
+        tmem_st_32x32b_x32(ta + 32, *reinterpret_cast<uint32_t(*)[32]>(&rowv[32]));
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&bars->a_ready);    // the MMA warp may issue the item's S / dP
+          mbar_arrive(&bars->res_empty);  // ... and the producer may load the next item's Q / dO
+        }
+      }
       for (int s = ((g & 1) == grp) ? 0 : 1; s < n_steps; s += 2) {
         const int gs = g + s;
         const int st = gs % NS;
         const uint32_t ph = (gs / NS) & 1;
         K9P_TRACE(gs, 0);
+        flush_one();  // one slice of the previous item's deferred stores (no warp-level sync inside: rows may diverge)
         mbar_wait(&bars->s_full[st], ph);
         tc_fence_after();
         K9P_TRACE(gs, 1);
@@ -1290,19 +1368,32 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
       }
       K9P_TRACE(g + n_steps - 1, 6);   // item end (before the epilogue)
       g += n_steps;
-      // ---- epilogue: dQ * scale through the rotary transpose -> dqkv[token_to_sorted[tok]] ----
+      // ---- epilogue, first half: what is left of the previous item's stores, then drain this item's dQ row ----
+      while (pend_ch < 4) flush_one();
       mbar_wait(&bars->acc_full, it & 1);
       tc_fence_after();
-      store_grad_row_early<1>(tdQ + lane_sel, true, p.rope_cos + static_cast<int64_t>(pos) * 128,
-                              p.rope_sin + static_cast<int64_t>(pos) * 128, p.scale,
-                              p.dqkv + static_cast<int64_t>(dst) * (3 * H) + w.h * 128, valid, half, [&]() {
-                                tc_fence_before();
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive(&bars->acc_empty);
-                              });
-      K9P_TRACE(g - 1, 7);             // epilogue done
+      {
+        uint32_t a[32], b2[32];
+        tmem_ld_32x32b_x32(tdQ + lane_sel + half * 32, a);
+        tmem_ld_32x32b_x32(tdQ + lane_sel + 64 + half * 32, b2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          pend_lo[i] = pack_bf16(__uint_as_float(a[2 * i]) * p.scale, __uint_as_float(a[2 * i + 1]) * p.scale);
+          pend_hi[i] = pack_bf16(__uint_as_float(b2[2 * i]) * p.scale, __uint_as_float(b2[2 * i + 1]) * p.scale);
+        }
+      }
+      tc_fence_before();   // the accumulator is in registers: the next item's first dQ MMAs may overwrite it
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acc_empty);
+      pend_cos = p.rope_cos + static_cast<int64_t>(pos) * 128;
+      pend_sin = p.rope_sin + static_cast<int64_t>(pos) * 128;
+      pend_dst = p.dqkv + static_cast<int64_t>(dst) * (3 * H) + w.h * 128;
+      pend_ch = valid ? 0 : 4;   // NOTE: per-thread (rows past the sample's end store nothing)
+      K9P_TRACE(g - 1, 7);             // epilogue (drain) done
       ++it;
     }
+    while (pend_ch < 4) flush_one();   // the last item's stores
   }
 
   tc_fence_before();
