@@ -145,8 +145,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
     }
   } else {
     // =============================== epilogue: TMEM -> fp32 atomics ===============================
+    // A thread holds one feature row f (TMEM lane) x 32 rank columns.  out[r, F] (transpose_out): lanes = consecutive f
+    // -> every atomic instruction covers one contiguous 128-byte line.  out[F, r]: the same mapping would touch 32 rows
+    // 256 bytes apart per instruction (32 sectors: the dB launches ran 1.5 x slower than the dA launches of the same
+    // size, ncu round 2), so the 32 x 32 block is transposed through shared memory (the pipeline stages are dead once
+    // acc_full has fired) and written with lanes along the rank.
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int f = f0 + q * 32 + lane;
+    float* tile = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);  // [32 f][33]: conflict-free both ways
     mbar_wait(acc_full, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -154,15 +160,25 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
       uint32_t v[32];
       tmem_ld_32x32b_x32(tmem + (static_cast<uint32_t>(q * 32) << 16) + half * 32, v);
       tmem_ld_wait();
-      if (f < F) {
+      if (transpose_out) {
+        if (f < F) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = half * 32 + j;
-          if (col < r) {
-            float* dst = transpose_out ? out + static_cast<int64_t>(col) * ldo + f : out + static_cast<int64_t>(f) * ldo + col;
-            atomicAdd(dst, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; ++j) {
+            const int col = half * 32 + j;
+            if (col < r) atomicAdd(out + static_cast<int64_t>(col) * ldo + f, __uint_as_float(v[j]));
           }
         }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        const int col = half * 32 + lane;
+#pragma unroll 4
+        for (int ff = 0; ff < 32; ++ff) {
+          const int frow = f0 + q * 32 + ff;
+          if (frow < F && col < r) atomicAdd(out + static_cast<int64_t>(frow) * ldo + col, tile[ff * 33 + lane]);
+        }
+        __syncwarp();
       }
     }
   }
