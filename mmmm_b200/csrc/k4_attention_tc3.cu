@@ -58,6 +58,7 @@ constexpr int A3_REGS_SOFTMAX = 224, A3_REGS_OTHER = 56;
 constexpr int A3_EXP_BATCH = 32;
 constexpr int A3_EMU = 4;  // pairs out of every 8 whose exp2 runs on the FMA pipe
 constexpr int A3_SCHED = 4;                                // scheduler ring depth
+constexpr int A3_TAIL_WAVES = 3;                           // waves merged into the final heaviest-first wave
 constexpr int A3_SCHED_READERS = 10;                       // 2 issuer warps + 8 softmax warps (lane 0 arrives)
 constexpr int A3_NCOUNTERS = 1024;                         // work counters, one per launch in flight (round-robin)
 constexpr int A3_TILES = 2 + A3_KV_SLOTS + 2;              // Q_A, Q_B, K/V ring, P_A, P_B
@@ -85,8 +86,18 @@ __device__ unsigned int g_a3_counters[A3_NCOUNTERS];
 __device__ __forceinline__ bool a3_decode(int item, int heads, int nqp, int n_groups, int wave_groups,
                                           const int32_t* __restrict__ cu_seqlens, int causal, A3Item& it) {
   const int per_wave = wave_groups * nqp;
-  const int wave = item / per_wave, r = item % per_wave;
-  const int gw = min(wave_groups, n_groups - wave * wave_groups);  // groups in this wave (the last one may be short)
+  // the last A3_TAIL_WAVES waves form ONE wave: heaviest pair first over all of its groups, so the kernel ends on the
+  // one-block items instead of on a few CTAs finishing 12-block items while the others idle (greedy hand-out model,
+  // profiles/r2_k4_schedule.md: 0.89 -> 0.98 schedule efficiency at c2, 0.83 -> 0.96 for a two-sample c4 shard); its
+  // K / V working set (3 x 148 / nqp groups, 57 MB at c2) still fits L2
+  const int n_waves = (n_groups + wave_groups - 1) / wave_groups;
+  const int tail_wave = max(0, n_waves - A3_TAIL_WAVES);
+  int wave = item / per_wave, r = item % per_wave, gw = wave_groups;
+  if (wave >= tail_wave) {
+    wave = tail_wave;
+    r = item - tail_wave * per_wave;
+    gw = n_groups - tail_wave * wave_groups;
+  }
   const int g = wave * wave_groups + r % gw, qp = nqp - 1 - r / gw;
   const int b = g / heads;
   it.h = g % heads;
