@@ -22,6 +22,7 @@
 // issues); warp 2 TMEM allocation; warps 4..7 / 8..11 softmax + epilogue of tile A / B, one thread per query row.
 #include <cuda.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
@@ -83,7 +84,7 @@ __device__ unsigned int g_a3_counters[A3_NCOUNTERS];
 // per CTA and wave); inside a wave the items are ordered heaviest pair first across the wave's groups, so the groups of a
 // wave are in flight together (K / V shared through L2) and the last wave drains longest-first.  False when the pair
 // lies past the sample's end.
-__device__ __forceinline__ bool a3_decode(int item, int heads, int nqp, int n_groups, int wave_groups,
+__device__ __forceinline__ bool a3_decode(int item, int heads, int nqp, int n_groups, int wave_groups, int tail_waves,
                                           const int32_t* __restrict__ cu_seqlens, int causal, A3Item& it) {
   const int per_wave = wave_groups * nqp;
   // the last A3_TAIL_WAVES waves form ONE wave: heaviest pair first over all of its groups, so the kernel ends on the
@@ -91,7 +92,7 @@ __device__ __forceinline__ bool a3_decode(int item, int heads, int nqp, int n_gr
   // profiles/r2_k4_schedule.md: 0.89 -> 0.98 schedule efficiency at c2, 0.83 -> 0.96 for a two-sample c4 shard); its
   // K / V working set (3 x 148 / nqp groups, 57 MB at c2) still fits L2
   const int n_waves = (n_groups + wave_groups - 1) / wave_groups;
-  const int tail_wave = max(0, n_waves - A3_TAIL_WAVES);
+  const int tail_wave = max(0, n_waves - tail_waves);
   int wave = item / per_wave, r = item % per_wave, gw = wave_groups;
   if (wave >= tail_wave) {
     wave = tail_wave;
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1)
     k4_attention_tc3(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* __restrict__ cu_seqlens, int heads, int B,
                      int nqp, const int32_t* __restrict__ out_row_map, __nv_bfloat16* __restrict__ out,
                      float scale_log2, float* __restrict__ lse, int rows_cap, int causal,
-                     unsigned int* __restrict__ work_counter, int wave_groups) {
+                     unsigned int* __restrict__ work_counter, int wave_groups, int tail_waves) {
   const int H = heads * A3_D;
   const int n_groups = B * heads, n_items = nqp * n_groups;
 
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1)
         A3Item it;
         it.valid = -1;
         if (fetched < static_cast<unsigned int>(n_items))
-          a3_decode(static_cast<int>(fetched), heads, nqp, n_groups, wave_groups, cu_seqlens, causal, it);
+          a3_decode(static_cast<int>(fetched), heads, nqp, n_groups, wave_groups, tail_waves, cu_seqlens, causal, it);
         bars->sched_item[slot_s] = it;
         mbar_arrive(&bars->sched_full[slot_s]);  // release: the item is visible to whoever observes the phase
         ++n_fetch;
@@ -578,6 +579,15 @@ int launch_attention_tc3(const void* qkv, const int32_t* cu_seqlens, int B, int 
   std::memset(&tm, 0, sizeof(tm));
   int rc = make_tmap_2d(&tm, qkv, rows_cap, 3 * static_cast<uint64_t>(H), 3 * static_cast<uint64_t>(H), 128);
   if (rc != VEX_OK) return rc;
+  // schedule knobs (tuning only): waves merged into the final heaviest-first wave, wave size in units of the SM count
+  static const int tail_waves = [] {
+    const char* e = std::getenv("VEX_K4_TAIL_WAVES");
+    return e ? std::max(1, std::atoi(e)) : A3_TAIL_WAVES;
+  }();
+  static const int wave_mult = [] {
+    const char* e = std::getenv("VEX_K4_WAVE_MULT");
+    return e ? std::max(1, std::atoi(e)) : 1;
+  }();
   const int nqp = ceil_div(max_len_cap, 2 * A3_BQ);
   const int64_t n_items = static_cast<int64_t>(nqp) * B * heads;
   if (n_items > 0x7fffffff - 65536) return VEX_E_UNSUPPORTED;
@@ -591,7 +601,7 @@ int launch_attention_tc3(const void* qkv, const int32_t* cu_seqlens, int B, int 
   k4_attention_tc3<<<grid, A3_THREADS, A3_SMEM, s>>>(tm, cu_seqlens, heads, B, nqp, out_row_map,
                                                      static_cast<__nv_bfloat16*>(out),
                                                      scale * 1.4426950408889634f, lse, rows_cap, causal, counter,
-                                                     max(1, ceil_div(sm_count, nqp)));
+                                                     max(1, ceil_div(sm_count * wave_mult, nqp)), tail_waves);
   VEX_LAUNCH_CHECK();
   return VEX_OK;
 }
