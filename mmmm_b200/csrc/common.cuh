@@ -7,6 +7,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+#include <utility>
+
 #include "../../include/vex.h"
 
 namespace vex {
@@ -153,6 +156,71 @@ __device__ __forceinline__ U32x8 ld_cached_256(const void* p) {  // reused data 
                : "l"(p));
   return r;
 }
+// coherent variants (no .nc): for data the PREVIOUS kernel of a programmatic-dependent-launch chain wrote while this
+// grid was already resident (read after pdl_wait(); the non-coherent path must only see data that is constant for the
+// lifetime of the grid)
+__device__ __forceinline__ U32x8 ld_coherent_256(const void* p) {
+  U32x8 r;
+  asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+                 "=r"(r.v[7])
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ U32x8 ld_coherent_stream_256(const void* p) {
+  U32x8 r;
+  asm volatile("ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+                 "=r"(r.v[7])
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ uint4 ld_coherent_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): the kernels of the decode step are 12 - 50 us long, so launch latency, ramp-up
+// and tail are a third of their time.  A kernel launched through launch_pdl() may become resident while its
+// predecessor in the stream is still running: it calls pdl_trigger() first thing (its own successor may be scheduled),
+// issues whatever does not depend on the predecessor (weight prefetch), and calls pdl_wait() before it reads anything
+// an earlier kernel wrote or writes anything an earlier kernel reads (the wait returns once the predecessor grid has
+// completed and its memory operations are visible; completion is transitive along the chain).  Both instructions are
+// no-ops in a grid that was launched normally.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline bool pdl_enabled() {  // VEX_PDL=0: plain launches (A/B timing, debugging)
+  static const bool on = [] {
+    const char* e = std::getenv("VEX_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 __device__ __forceinline__ void st_stream(void* p, const uint4& v) {
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
                "r"(v.w)

@@ -80,7 +80,7 @@ __device__ __forceinline__ void mma_chunk(float (&c)[2][NB][4], const WFrag<TILE
   for (int nb = 0; nb < NB; ++nb) {
     U32x8 xb;
     if (xlive[nb]) {
-      xb = ld_cached_256(xrow[nb] + kb);
+      xb = ld_coherent_256(xrow[nb] + kb);  // L1-resident; written by the previous kernel of the PDL chain
     } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) xb.v[j] = 0u;
@@ -101,7 +101,7 @@ __device__ __forceinline__ void mma_chunk(float (&c)[2][NB][4], const WFrag<TILE
 template <int NB, int TILES>
 __device__ __forceinline__ void accumulate(float (&c)[2][NB][4], const __nv_bfloat16* const* wrow_lo,
                                            const __nv_bfloat16* const* wrow_hi, const __nv_bfloat16* const* xrow,
-                                           const bool* xlive, int K, int warp, int t) {
+                                           const bool* xlive, int K, int warp, int t, bool wait_after_prefetch = false) {
   constexpr int NBUF = (TILES == 1 && NB <= 2) ? 4 : 2;
   const int nchunks = K >> 6;
   WFrag<TILES> f[NBUF];
@@ -110,6 +110,8 @@ __device__ __forceinline__ void accumulate(float (&c)[2][NB][4], const __nv_bflo
     const int ip = warp + b * DG_WARPS;
     if (ip < nchunks) load_w<TILES>(f[b], wrow_lo, wrow_hi, (ip << 6) + 16 * t);
   }
+  // the first weight fragments are in flight; x (and everything the epilogue touches) belongs to the previous kernel
+  if (wait_after_prefetch) pdl_wait();
   for (int i = warp; i < nchunks; i += DG_WARPS * NBUF) {
 #pragma unroll
     for (int b = 0; b < NBUF; ++b) {
@@ -126,6 +128,7 @@ template <int NB, int TILES>
 __global__ void __launch_bounds__(DG_THREADS, 2) k12_decode_gemm(const DecGemm p) {
   __shared__ float red[DG_WARPS][TILES][NB][32][4];   // per-warp partial fragments
   __shared__ float fin[TILES][NB * 8][16];            // reduced [tile][batch row][feature]
+  pdl_trigger();  // the next kernel of the step may be scheduled: its weight prefetch overlaps this kernel's stream
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int task = blockIdx.x;
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(DG_THREADS, 2) k12_decode_gemm(const DecGemm p
     const __nv_bfloat16* lo[2] = {wa + static_cast<int64_t>(n_a + g) * p.ldw, wb + static_cast<int64_t>(n_b + g) * p.ldw};
     const __nv_bfloat16* hi[2] = {wa + static_cast<int64_t>(n_a + g + 8) * p.ldw,
                                   wb + static_cast<int64_t>(n_b + g + 8) * p.ldw};
-    accumulate<NB, TILES>(c, lo, hi, xrow, xlive, p.K, warp, t);
+    accumulate<NB, TILES>(c, lo, hi, xrow, xlive, p.K, warp, t, /*wait_after_prefetch=*/true);
   }
   if (p.lora_r > 0) {  // K-extension: += T . lora_B^T  (r is a multiple of 64 here; r = 64 -> one chunk, warp 0)
     const __nv_bfloat16* trow[NB];
@@ -263,8 +266,7 @@ __global__ void __launch_bounds__(DG_THREADS, 2) k12_decode_gemm(const DecGemm p
 
 template <int NB, int TILES>
 static int launch_dg(const DecGemm& p, int tasks, cudaStream_t s) {
-  k12_decode_gemm<NB, TILES><<<tasks, DG_THREADS, 0, s>>>(p);
-  VEX_LAUNCH_CHECK();
+  VEX_CUDA_TRY(launch_pdl(k12_decode_gemm<NB, TILES>, dim3(tasks), dim3(DG_THREADS), 0, s, p));
   return VEX_OK;
 }
 

@@ -33,6 +33,29 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 2)
   const int lane = lane_id();
   const int warp = threadIdx.x >> 5;
   const int slot = warp / WPR, half = warp % WPR;
+  pdl_trigger();
+  // Weight staging with every load issued up front (16-byte vectors, fully unrolled).  The scalar one-element-per-trip
+  // loop this replaces was a chain of up to 16 dependent-latency round trips (~12 us: the whole duration of the
+  // 8-row decode launch, and a quarter of the 42 us prefill launch at c2 -- ncu, profiles/r2_decode_ncu.md).  The weight
+  // is a constant: its loads are issued BEFORE the dependency wait of a programmatic dependent launch.
+  constexpr int NVF = (H / 4 + K2_WARPS * 32 - 1) / (K2_WARPS * 32);  // float4 per thread
+  constexpr int NVB = (H / 8 + K2_WARPS * 32 - 1) / (K2_WARPS * 32);  // uint4 (8 bf16) per thread
+  float4 wf[NVF];
+  uint4 wb[NVB];
+  if (weight_is_fp32) {
+#pragma unroll
+    for (int j = 0; j < NVF; ++j) {
+      const int i = threadIdx.x + j * K2_WARPS * 32;
+      if (i < H / 4) wf[j] = __ldg(static_cast<const float4*>(weight) + i);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NVB; ++j) {
+      const int i = threadIdx.x + j * K2_WARPS * 32;
+      if (i < H / 8) wb[j] = __ldg(static_cast<const uint4*>(weight) + i);
+    }
+  }
+  pdl_wait();  // rows, row maps and the row count come from earlier kernels
   const int n_rows = min(*n_rows_ptr, rows_cap);
   const int stride = gridDim.x * ROWS;
 
@@ -40,7 +63,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 2)
     const int src = row_src ? row_src[r] : r;
     const uint4* xp = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(src) * H) + half * CPL * 32;
 #pragma unroll
-    for (int i = 0; i < CPL; ++i) dst[i] = ld_stream(xp + i * 32 + lane);
+    for (int i = 0; i < CPL; ++i) dst[i] = ld_coherent_stream(xp + i * 32 + lane);
   };
 
   uint4 nx[CPL];
@@ -48,38 +71,21 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 2)
     const int r = blockIdx.x * ROWS + slot;
     if (r < n_rows) load_row(r, nx);  // the first row is in flight while the weight vector is staged
   }
-  // Weight staging with every load issued up front (16-byte vectors, fully unrolled).  The scalar one-element-per-trip
-  // loop this replaces was a chain of up to 16 dependent-latency round trips (~12 us: the whole duration of the
-  // 8-row decode launch, and a quarter of the 42 us prefill launch at c2 -- ncu, profiles/r2_decode_ncu.md).
   if (weight_is_fp32) {
-    constexpr int NV = (H / 4 + K2_WARPS * 32 - 1) / (K2_WARPS * 32);  // float4 per thread
-    float4 wv[NV];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
+    for (int j = 0; j < NVF; ++j) {
       const int i = threadIdx.x + j * K2_WARPS * 32;
-      if (i < H / 4) wv[j] = __ldg(static_cast<const float4*>(weight) + i);
-    }
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int i = threadIdx.x + j * K2_WARPS * 32;
-      if (i < H / 4) *reinterpret_cast<float4*>(&w_s[4 * i]) = wv[j];
+      if (i < H / 4) *reinterpret_cast<float4*>(&w_s[4 * i]) = wf[j];
     }
   } else {
-    constexpr int NV = (H / 8 + K2_WARPS * 32 - 1) / (K2_WARPS * 32);  // uint4 (8 bf16) per thread
-    uint4 wv[NV];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int i = threadIdx.x + j * K2_WARPS * 32;
-      if (i < H / 8) wv[j] = __ldg(static_cast<const uint4*>(weight) + i);
-    }
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
+    for (int j = 0; j < NVB; ++j) {
       const int i = threadIdx.x + j * K2_WARPS * 32;
       if (i < H / 8) {
         *reinterpret_cast<float4*>(&w_s[8 * i]) =
-            make_float4(bf16_lo(wv[j].x), bf16_hi(wv[j].x), bf16_lo(wv[j].y), bf16_hi(wv[j].y));
+            make_float4(bf16_lo(wb[j].x), bf16_hi(wb[j].x), bf16_lo(wb[j].y), bf16_hi(wb[j].y));
         *reinterpret_cast<float4*>(&w_s[8 * i + 4]) =
-            make_float4(bf16_lo(wv[j].z), bf16_hi(wv[j].z), bf16_lo(wv[j].w), bf16_hi(wv[j].w));
+            make_float4(bf16_lo(wb[j].z), bf16_hi(wb[j].z), bf16_lo(wb[j].w), bf16_hi(wb[j].w));
       }
     }
   }
@@ -151,8 +157,8 @@ extern "C" int vex_rmsnorm_gather(const void* x, const void* weight, int weight_
   auto yp = static_cast<__nv_bfloat16*>(y);
 #define VEX_K2_CASE(NC)                                                                                        \
   case NC:                                                                                                     \
-    vex::k2_rmsnorm<NC><<<grid, vex::K2_WARPS * 32, 0, s>>>(xp, weight, weight_is_fp32, eps, row_src, row_dst, \
-                                                             n_rows, yp, rows_cap);                                   \
+    VEX_CUDA_TRY(vex::launch_pdl(vex::k2_rmsnorm<NC>, dim3(grid), dim3(vex::K2_WARPS * 32), 0, s, xp, weight,    \
+                                 weight_is_fp32, eps, row_src, row_dst, n_rows, yp, rows_cap));                       \
     break;
   switch (H / 256) {
     VEX_K2_CASE(1) VEX_K2_CASE(2) VEX_K2_CASE(3) VEX_K2_CASE(4) VEX_K2_CASE(5) VEX_K2_CASE(6) VEX_K2_CASE(8)

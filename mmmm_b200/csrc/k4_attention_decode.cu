@@ -65,6 +65,9 @@ __global__ void __launch_bounds__(DEC_THREADS)
   __shared__ float xch[2];                  // local max, local sum: read by the peers through DSMEM
   __shared__ float opart[128];              // this CTA's partial output: read by rank 0 through DSMEM
   __shared__ float osum[DEC_WARPS][128];
+  // programmatic dependent launch: q and the newest cache row come from the QKV kernel right before this one
+  pdl_trigger();
+  pdl_wait();
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const uint32_t rank = blockIdx.z, nsplit = gridDim.z;  // cluster = the z extent of the grid
   const int L = kv_len ? min(max(kv_len[0] + 1, 1), L_host) : L_host;
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(DEC_THREADS)
       const int l = lb + i * DEC_WARPS * 4 + grp;
       in[i] = l < l1;
       live[i] = in[i] && mrow[l];
-      if (live[i]) u[i] = ld_stream_256(k + (base + l) * 128 + sub * 16);
+      if (live[i]) u[i] = ld_coherent_stream_256(k + (base + l) * 128 + sub * 16);
     }
 #pragma unroll
     for (int i = 0; i < SU; ++i) {
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(DEC_THREADS)
       const int l = lb + i * DEC_WARPS * 4 + grp;
       pr[i] = l < l1 ? bf16r(sc[l - l0] * inv) : 0.f;
       // masked keys have p == 0 (their values are zeroed in the reference, :135): their rows are not read
-      if (pr[i] != 0.f) u[i] = ld_stream_256(v + (base + l) * 128 + sub * 16);
+      if (pr[i] != 0.f) u[i] = ld_coherent_stream_256(v + (base + l) * 128 + sub * 16);
     }
 #pragma unroll
     for (int i = 0; i < SU; ++i) {
@@ -213,13 +216,15 @@ static int launch_decode(const void* q, int64_t ldq, const void* k, const void* 
   cfg.blockDim = dim3(DEC_THREADS);
   cfg.dynamicSmemBytes = static_cast<size_t>(chunk_cap) * sizeof(float);
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = nsplit;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   VEX_CUDA_TRY(cudaLaunchKernelEx(&cfg, k4_attention_decode, static_cast<const __nv_bfloat16*>(q), ldq,
                                   static_cast<const __nv_bfloat16*>(k), static_cast<const __nv_bfloat16*>(v), mask,
                                   ld_mask, static_cast<__nv_bfloat16*>(out), heads, L, cap, kv_len, scale, chunk_cap));
