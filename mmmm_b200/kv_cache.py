@@ -25,10 +25,24 @@ from . import ops
 HEAD_DIM = 128
 
 
+def next_position_ids(position_ids: torch.Tensor, input_ids: torch.Tensor, bop_token_id: int,
+                      eop_token_id: int) -> torch.Tensor:
+    """Position of the token a decode step is about to process, [B, 1].
+
+    The reference appends ``position_ids[:, -1:] + 1`` after every step (mmmm/models/mmmm.py:354-365) and then takes one
+    back when the token BEFORE the new one is ``<bop>`` or the new token itself is ``<eop>`` (``keep_position``,
+    :380-384): the phrase brackets share the position of their neighbour.  ``position_ids`` are the positions used so
+    far ([B, n], only the last column is read), ``input_ids`` the ids generated so far INCLUDING the token this step
+    feeds ([B, >= 2])."""
+    keep = (input_ids[:, -2] == bop_token_id) | (input_ids[:, -1] == eop_token_id)
+    return (position_ids[:, -1] + 1 - keep.to(position_ids.dtype)).unsqueeze(1)
+
+
 class StaticKVCache:
     def __init__(self, n_layers: int, batch: int, heads: int, capacity: int, device, dtype=torch.bfloat16):
         self.batch, self.heads, self.capacity = batch, heads, capacity
         kv = torch.empty(n_layers, 2, batch, heads, capacity, HEAD_DIM, dtype=dtype, device=device)
+        self._kv = kv
         self.layers = [(kv[i, 0], kv[i, 1]) for i in range(n_layers)]
         self.past_len = torch.zeros(1, dtype=torch.int32, device=device)   # device counter: positions cached
         self.mask = torch.ones(batch, capacity, dtype=torch.bool, device=device)
@@ -48,6 +62,15 @@ class StaticKVCache:
         """The reference's tuple-cache view of the current contents: per layer (k, v) [B, heads, L, 128]."""
         L = self.host_len
         return tuple((k[:, :, :L], v[:, :, :L]) for k, v in self.layers)
+
+    def reorder(self, beam_idx: torch.Tensor) -> None:
+        """Beam search: sample b continues beam ``beam_idx[b]`` -- the reference's ``_reorder_cache``
+        (modeling_cogvlm.py:782-788: ``index_select(0, beam_idx)`` on every cached k / v), done in place so that the
+        buffers a captured decode graph points at stay where they are; the mask rows move with their samples."""
+        idx = beam_idx.to(self._kv.device).long()
+        L = self.host_len
+        self._kv[:, :, :, :, :L].copy_(self._kv[:, :, :, :, :L].index_select(2, idx))
+        self.mask.copy_(self.mask.index_select(0, idx))
 
     # ------------------------------------------------------------------------------------------------------
     def _run(self, model, hidden: torch.Tensor, position_ids: torch.Tensor) -> torch.Tensor:

@@ -158,3 +158,39 @@ def test_kv_cache_view_capacity_detection():
     assert _cache_capacity(k.contiguous()) == 7                             # exactly full: no room -> re-allocate
     assert _cache_capacity(torch.zeros(3, 4, 7, 64)) == 0                   # wrong head_dim
     assert _cache_capacity(kv[0].transpose(1, 2)[:, :, :3]) == 0            # not the cache layout
+
+
+def test_next_position_ids_rule():
+    """mmmm.py:354-365 (+1 per step) and :380-384 (keep_position: the token after <bop> and an <eop> keep the previous
+    position)."""
+    from mmmm_b200.kv_cache import next_position_ids
+    BOP, EOP = 7, 8
+    pos = torch.tensor([[3, 4], [3, 4], [3, 4], [3, 4]])
+    ids = torch.tensor([[5, 6, 9],      # ordinary token                 -> 5
+                        [5, BOP, 9],    # the token right after <bop>    -> 4
+                        [5, 6, EOP],    # <eop> itself                   -> 4
+                        [5, BOP, EOP]])  # both conditions: still one back -> 4
+    # the reference, literally: cat([pos, pos[:, -1:] + 1]); pos[:, -1] -= keep; pos[:, -1:]
+    ref = torch.cat([pos, pos[:, -1:] + 1], dim=1)
+    keep = (ids[:, -2] == BOP) | (ids[:, -1] == EOP)
+    ref[:, -1] -= keep.long()
+    got = next_position_ids(pos, ids, BOP, EOP)
+    assert got.shape == (4, 1) and torch.equal(got, ref[:, -1:]) and got[:, 0].tolist() == [5, 4, 4, 4]
+
+
+def test_static_cache_reorder_matches_reference_reorder():
+    """StaticKVCache.reorder == the reference's _reorder_cache (modeling_cogvlm.py:782-788) on the tuple view, in place."""
+    from mmmm_b200.kv_cache import StaticKVCache
+    cache = StaticKVCache(n_layers=2, batch=3, heads=2, capacity=6, device="cpu", dtype=torch.float32)
+    cache._kv.copy_(torch.arange(cache._kv.numel(), dtype=torch.float32).view_as(cache._kv))
+    pm = torch.tensor([[1, 1, 1, 0], [1, 1, 0, 0], [1, 1, 1, 1]], dtype=torch.bool)
+    cache.start(pm)
+    before = tuple((k.clone(), v.clone()) for k, v in cache.views())
+    ptrs = [k.data_ptr() for k, _ in cache.layers]
+    beam = torch.tensor([2, 0, 0])
+    cache.reorder(beam)
+    want = tuple(tuple(t.index_select(0, beam) for t in layer) for layer in before)
+    for (k, v), (wk, wv) in zip(cache.views(), want):
+        assert torch.equal(k, wk) and torch.equal(v, wv)
+    assert torch.equal(cache.mask[:, :4], pm.index_select(0, beam)) and bool(cache.mask[:, 4:].all())
+    assert [k.data_ptr() for k, _ in cache.layers] == ptrs
