@@ -880,6 +880,51 @@ def test_static_cache_generation_vs_oracle(graph):
             assert mx <= 2 * MAX_REL and fro <= 2 * FRO_REL, (mx, fro)
 
 
+def test_static_cache_beam_reorder_vs_oracle():
+    """Beam search on the static cache: after one graphed step the samples are re-assigned (`cache.reorder`, the
+    reference's `_reorder_cache`, modeling_cogvlm.py:782-788) and two more graphed steps must match the oracle driven
+    through a tuple cache reordered the reference's way; positions follow the reference's keep_position rule
+    (`next_position_ids`, mmmm.py:354-384)."""
+    from mmmm_b200.inputs import make_inputs
+    from mmmm_b200.kv_cache import next_position_ids
+    H, I, heads, nl = 512, 768, 4, 2
+    ws, norm_w, model = _make_decoder(H, I, heads, nl, 90)
+    inp = make_inputs(3, 50, 12, H, ragged=True, seed=91)
+    tt, pos, pm = inp.token_type_ids, inp.position_ids, inp.padding_mask
+    d = inp.to("cuda")
+    _, cache = model.prefill_static(d.hidden_states, d.token_type_ids, d.padding_mask, d.position_ids, max_new_tokens=6)
+    ref_h, ref_kv = inp.hidden_states, []
+    for w in ws:
+        ref_h, kv = O.decoder_layer(w, ref_h, tt, pos, pm, num_heads=heads, use_cache=True)
+        ref_kv.append(kv)
+    BOP, EOP = 1001, 1002
+    ids = torch.tensor([[5, 6], [5, BOP], [5, 6]])          # sample 1: the new token follows <bop> -> position kept
+    new_tok = [torch.tensor([[9], [9], [EOP]]), torch.tensor([[9], [BOP], [9]]), torch.tensor([[9], [9], [9]])]
+    p_hist = pos.max(dim=1, keepdim=True).values            # last position used by the prefill
+    g = torch.Generator().manual_seed(92)
+    mask = pm.clone()
+    for step in range(3):
+        ids = torch.cat([ids, new_tok[step]], dim=1)
+        p1 = next_position_ids(p_hist, ids, BOP, EOP)
+        p_hist = torch.cat([p_hist, p1], dim=1)
+        x = torch.randn(3, 1, H, generator=g).bfloat16()
+        mask = torch.cat([mask, torch.ones(3, 1, dtype=torch.bool)], dim=1)
+        out = model.decode_step(x.cuda(), p1.cuda(), cache, graph=True).clone()
+        r = x
+        for i, w in enumerate(ws):
+            r, ref_kv[i] = O.decoder_layer(w, r, torch.zeros(3, 1, dtype=torch.long), p1, mask, num_heads=heads,
+                                           use_cache=True, past_key_value=ref_kv[i])
+        r = O.rms_norm(r, norm_w, 1e-6)
+        mx, fro = _errs(out.cpu(), r)
+        assert mx <= 2 * MAX_REL and fro <= 2 * FRO_REL, (step, mx, fro)
+        if step == 0:
+            beam = torch.tensor([2, 0, 0])
+            cache.reorder(beam.cuda())
+            ref_kv = [tuple(t.index_select(0, beam) for t in kv) for kv in ref_kv]
+            mask, ids, p_hist = mask.index_select(0, beam), ids.index_select(0, beam), p_hist.index_select(0, beam)
+    assert p_hist[:, 1:].tolist() != (p_hist[:, :1] + torch.arange(1, 4)).tolist()   # the rule did keep a position
+
+
 def test_tuple_cache_decode_appends_in_place():
     """Through the reference's tuple-cache interface the step after a prefill appends into the prefill's buffer (no
     torch.cat re-allocation): the returned views share storage with the incoming ones; a foreign contiguous cache
