@@ -577,7 +577,7 @@ def run_train(args):
     args.layers = n_layers
     layers = [make_gpu_layer(dev, r, seed=i, lora_dropout=args.lora_dropout).train() for i in range(args.layers)]
     for l in layers:
-        l.recompute = bool(args.recompute)
+        l.recompute = "auto" if args.recompute < 0 else bool(args.recompute)
     params = [p for l in layers for p in l.parameters() if p.requires_grad]
     overlapped = args.allreduce == "overlap"
     reducer = BucketedGradReducer(layers, layers_per_collective=args.ar_group) if overlapped else LoraGradReducer(params)
@@ -661,7 +661,10 @@ def run_train(args):
         g_down = tokens * 2 * H * I
         lora_f = tokens * 2 * r * 69888
         attn_f = b * 4 * HEADS * 128 * seq * (seq + 1) // 2
-        rec = 1 if args.recompute else 0
+        from mmmm_b200.training import KEEP_BUDGET
+        asked = KEEP_BUDGET.granted + KEEP_BUDGET.refused
+        # fraction of layer forwards that checkpointed (auto: the ones the memory budget refused to keep)
+        rec = (KEEP_BUDGET.refused / asked if asked else 1.0) if args.recompute < 0 else (1 if args.recompute else 0)
         flop = args.layers * ((g_fwd + lora_f) + rec * (g_fwd - g_down + lora_f) + (g_fwd + lora_f) + 2 * lora_f
                               + (1 + rec) * attn_f + 2.5 * attn_f)
         pk = peaks()
@@ -675,9 +678,12 @@ def run_train(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": dict(config_dict(args, tokens), lora_r=r, lora_dropout=args.lora_dropout,
-                           recompute=bool(args.recompute),
-                           mode=("train: fwd + recompute + bwd + LoRA-grad allreduce" if args.recompute else
-                                 "train: fwd (activations kept in HBM) + bwd + LoRA-grad allreduce"),
+                           recompute=("auto" if args.recompute < 0 else bool(args.recompute)),
+                           recomputed_layer_fraction=rec,
+                           mode=("train: fwd + recompute + bwd + LoRA-grad allreduce" if rec == 1 else
+                                 "train: fwd (activations kept in HBM) + bwd + LoRA-grad allreduce" if rec == 0 else
+                                 "train: fwd (activations kept while they fit) + partial recompute + bwd + LoRA-grad "
+                                 "allreduce"),
                            allreduce=((f"bucket views, NCCL AVG per {args.ar_group} layer(s) on a side stream during the "
                                        f"backward" if args.ar_group else "bucket views, ONE NCCL AVG over the flat "
                                        "bucket after the backward") if overlapped else "post-backward, packed (round 1)")),
@@ -934,8 +940,9 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="decoder layers per step (default: the workload's: 32 for c3 / c4, 1 for c2)")
     ap.add_argument("--train", action="store_true", help="config 5: LoRA fwd+bwd training step + grad all-reduce")
     ap.add_argument("--lora-dropout", type=float, default=0.0, help="--train: lora_dropout (the reference uses 0.05)")
-    ap.add_argument("--recompute", type=int, default=1, help="--train: 1 = checkpoint each layer like the reference "
-                    "(save the input, recompute in backward); 0 = keep the activations in HBM (no recompute pass)")
+    ap.add_argument("--recompute", type=int, default=-1, help="--train: 1 = checkpoint each layer like the reference "
+                    "(save the input, recompute in backward); 0 = keep the activations in HBM (no recompute pass); "
+                    "-1 (default, the product default) = keep them while they fit the memory budget, checkpoint the rest")
     ap.add_argument("--allreduce", default="overlap", choices=["overlap", "post"], help="--train: bucket-view reducer "
                     "(default; gradients accumulate straight into the flat bucket) or the round-1 pack / unpack reducer")
     ap.add_argument("--ar-group", type=int, default=8, help="--train: layers per NCCL collective, issued on a side stream "

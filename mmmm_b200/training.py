@@ -179,7 +179,13 @@ class _LayerFunction(torch.autograd.Function):
         from .modeling_cogvlm import next_dropout_seed, visual_expert_layer_forward
         ctx.dropout_seed = next_dropout_seed()  # the backward's recompute must regenerate the same LoRA dropout masks
         ctx.keep = None
-        if not recompute_default(layer):
+        mode = recompute_default(layer)
+        if mode == "auto":
+            rows = hidden_states.shape[0] * hidden_states.shape[1]
+            token = KEEP_BUDGET.take(hidden_states.device, keep_bytes_estimate(layer, rows, hidden_states.shape[2]))
+            if token is not None:
+                ctx.keep = {"continue_forward": True, "_budget": token}
+        elif not mode:
             # B200 has the HBM to keep one layer's intermediates (~1.5 GB per 8 x 1485 tokens, 47 GB for 32 layers):
             # the backward then starts from them instead of re-running the forward
             ctx.keep = {"continue_forward": True}
@@ -203,15 +209,74 @@ class _LayerFunction(torch.autograd.Function):
         return (None, None, None, d_hidden if ctx.needs_input_grad[3] else None, *tr)
 
 
-def recompute_default(layer) -> bool:
-    """True (default): save only the layer input and recompute in the backward, like the reference's always-on
-    gradient checkpointing (mmmm/models/mmmm.py:287-291).  ``layer.recompute = False`` or VEX_TRAIN_RECOMPUTE=0 keeps
-    the intermediates in HBM instead (B200-sized memory: no recompute pass, ~1.3x faster step)."""
+def recompute_default(layer):
+    """How a layer's training forward treats its intermediates: ``True`` -- save only the layer input and recompute in
+    the backward, like the reference's always-on gradient checkpointing (mmmm/models/mmmm.py:287-291); ``False`` -- keep
+    them in HBM (no recompute pass, ~1.3x faster step); ``"auto"`` (default) -- keep them while they fit (`KeepBudget`).
+    ``layer.recompute`` overrides the environment (VEX_TRAIN_RECOMPUTE = 1 | 0 | auto)."""
     import os
     flag = getattr(layer, "recompute", None)
     if flag is None:
-        return os.environ.get("VEX_TRAIN_RECOMPUTE", "1") != "0"
-    return bool(flag)
+        flag = {"1": True, "0": False}.get(os.environ.get("VEX_TRAIN_RECOMPUTE", "auto"), "auto")
+    return flag if flag == "auto" else bool(flag)
+
+
+def keep_bytes_estimate(layer, rows: int, hidden: int) -> int:
+    """Upper bound of what an activation-keeping forward leaves in HBM for the backward: per token the normed input,
+    qkv (3H), the attention context, h1 and its norm, the LoRA T rows (< H), gate / up / their product (3I), bf16."""
+    try:
+        inter = _base_weight(layer.mlp.language_mlp.down_proj).shape[1]
+    except Exception:  # a layer without the reference's module tree: assume the 7B ratio
+        inter = (hidden * 43) // 16
+    return rows * (8 * hidden + 3 * inter) * 2
+
+
+class KeepBudget:
+    """Memory-adaptive checkpointing.  B200 has the HBM to keep a 32-layer step's intermediates (47 GB at 8 x 1485
+    tokens), which the A100-era reference could not; but a longer batch may not fit, and running out of memory in layer
+    27 is not an acceptable failure mode for a drop-in.  So every layer forward asks for its estimate: granted while
+    free device memory (driver-free + the caching allocator's free blocks, read once when no layer is outstanding) minus a
+    reserve (VEX_TRAIN_KEEP_RESERVE_GB, default 10 % of the device + 8 GB for optimizer state / fragmentation) covers
+    it, and returned when the layer's backward (or the death of its autograd node) releases the activations.  Layers that
+    are refused checkpoint themselves like the reference, so a step degrades layer by layer instead of failing."""
+
+    def __init__(self):
+        self._state = {}
+        self.granted = self.refused = 0   # cumulative, for reporting (bench.py --train)
+
+    @staticmethod
+    def _available(device) -> int:
+        import os
+        free, total = torch.cuda.mem_get_info(device)
+        cached = torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+        env = os.environ.get("VEX_TRAIN_KEEP_RESERVE_GB")
+        reserve = int(float(env) * 2 ** 30) if env else total // 10 + 8 * 2 ** 30
+        return free + cached - reserve
+
+    def take(self, device, nbytes: int):
+        """A token (returned to the budget when it dies) if ``nbytes`` more may be kept on ``device``, else None."""
+        st = self._state.setdefault(torch.device(device).index or 0, {"out": 0, "avail": 0})
+        if st["out"] == 0:
+            st["avail"] = self._available(device)
+        if st["avail"] < nbytes:
+            self.refused += 1
+            return None
+        st["avail"] -= nbytes
+        st["out"] += 1
+        self.granted += 1
+        return _KeepToken(st, nbytes)
+
+
+class _KeepToken:
+    def __init__(self, st, nbytes):
+        self._st, self._n = st, nbytes
+
+    def __del__(self):
+        self._st["avail"] += self._n
+        self._st["out"] -= 1
+
+
+KEEP_BUDGET = KeepBudget()
 
 
 def layer_forward_train(layer, hidden_states: torch.Tensor, plan, position_ids: torch.Tensor) -> torch.Tensor:

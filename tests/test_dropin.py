@@ -194,3 +194,43 @@ def test_static_cache_reorder_matches_reference_reorder():
         assert torch.equal(k, wk) and torch.equal(v, wv)
     assert torch.equal(cache.mask[:, :4], pm.index_select(0, beam)) and bool(cache.mask[:, 4:].all())
     assert [k.data_ptr() for k, _ in cache.layers] == ptrs
+
+
+def test_keep_budget_policy(monkeypatch):
+    """Memory-adaptive checkpointing (training.KeepBudget): activations are kept while the device has room beyond the
+    reserve, layers past that are refused (they checkpoint like the reference, mmmm.py:287-291), and the budget comes
+    back when a layer's token dies (its backward ran or its autograd node was dropped)."""
+    import gc
+    from mmmm_b200 import training as T
+    GB = 2 ** 30
+    monkeypatch.setenv("VEX_TRAIN_KEEP_RESERVE_GB", "10")
+    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda device=None: (30 * GB, 180 * GB))
+    monkeypatch.setattr(torch.cuda, "memory_reserved", lambda device=None: 6 * GB)
+    monkeypatch.setattr(torch.cuda, "memory_allocated", lambda device=None: 4 * GB)
+    budget = T.KeepBudget()                       # available = 30 + (6 - 4) - 10 = 22 GB
+    dev = torch.device("cuda", 0)
+    tokens = [budget.take(dev, 5 * GB) for _ in range(5)]
+    assert [t is not None for t in tokens] == [True, True, True, True, False]
+    assert (budget.granted, budget.refused) == (4, 1)
+    tokens[0] = None                              # one layer's backward ran
+    gc.collect()
+    again = budget.take(dev, 5 * GB)
+    refused = budget.take(dev, 5 * GB)
+    assert again is not None and refused is None
+    del again
+    # everything released: the next request re-reads the device state
+    tokens.clear()
+    gc.collect()
+    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda device=None: (12 * GB, 180 * GB))
+    assert budget.take(dev, 5 * GB) is None       # 12 + 2 - 10 = 4 GB
+
+    class L:  # the policy switch: attribute beats environment, default is "auto"
+        pass
+    layer = L()
+    monkeypatch.delenv("VEX_TRAIN_RECOMPUTE", raising=False)
+    assert T.recompute_default(layer) == "auto"
+    monkeypatch.setenv("VEX_TRAIN_RECOMPUTE", "1")
+    assert T.recompute_default(layer) is True
+    layer.recompute = False
+    assert T.recompute_default(layer) is False
+    assert T.keep_bytes_estimate(layer, 1000, 4096) == 1000 * (8 * 4096 + 3 * 11008) * 2
