@@ -53,8 +53,9 @@ if d:
                  f"{d['value']:.0f} tok/s ({d['ms_per_step']:.2f} ms per token step, {d['launches_per_step']} launches); e2e {d['e2e']['value']:.0f} tok/s",
                  f"HBM-bound: {r['achieved']:.0f} GB/s = {100 * r['frac']:.1f} % of the measured {r['peak']:.0f} GB/s "
                  f"({r['weight_bytes'] / 1e9:.2f} GB weights + {r['kv_bytes'] / 1e9:.2f} GB K/V per step)", "r2_bench_decode.json"))
-for name, label in (("r2_bench_train32_n1.json", "c5: LoRA r = 64 training step, 32 layers, 8 x 1485 tokens, N = 1 (recompute, like the reference)"),
-                    ("r2_bench_train32_keep_n1.json", "c5, activations kept in HBM (`--recompute 0`), N = 1"),
+for name, label in (("r2_bench_train32_auto_n1.json", "**c5**: LoRA r = 64 training step, 32 layers, 8 x 1485 tokens, N = 1, default (`recompute = 'auto'`: every layer's activations fit and are kept in HBM)"),
+                    ("r2_bench_train32_n1.json", "c5, every layer checkpointed like the reference (`--recompute 1`), N = 1"),
+                    ("r2_bench_train32_partial_n1.json", "c5, auto with the budget forced down to 40 GB (`VEX_TRAIN_KEEP_RESERVE_GB=140`): 7 layers kept, 25 checkpointed"),
                     ("r2_bench_train32_n2.json", "c5, N = 2"), ("r2_bench_train32_n8.json", "c5, N = 8")):
     d = load(name)
     if d:
