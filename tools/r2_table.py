@@ -38,10 +38,12 @@ def prefill(name, label):
 
 
 prefill("r2_bench_c3_n1.json", "**c3** (default): 32 layers + final norm, global batch 64 x 1485 tokens, N = 1")
+prefill("r2_bench_c3_n1_final.json", "c3, N = 1 again on the final code of the round (another box: 1.07 GHz under the cap)")
 prefill("r2_bench_c3_n2.json", "c3, N = 2 (32 samples per GPU)")
 prefill("r2_bench_c3_n4.json", "c3, N = 4 (16 samples per GPU)")
 prefill("r2_bench_c3_n8.json", "c3, N = 8 (8 samples per GPU)")
 prefill("r2_bench_c4_n1.json", "c4: 32 layers, global batch 16 x 2564 tokens, N = 1")
+prefill("r2_bench_c4_n1_final.json", "c4, N = 1 again on the final code of the round")
 prefill("r2_bench_c4_n8.json", "c4, N = 8 (2 samples per GPU)")
 prefill("r2_bench_c2.json", "c2: ONE layer, 8 x 1485 tokens, N = 1 (burst clocks)")
 prefill("r2_bench_c2_lora64.json", "c2 + LoRA r = 64 on all ten Linears")
@@ -56,7 +58,7 @@ if d:
 for name, label in (("r2_bench_train32_auto_n1.json", "**c5**: LoRA r = 64 training step, 32 layers, 8 x 1485 tokens, N = 1, default (`recompute = 'auto'`: every layer's activations fit and are kept in HBM)"),
                     ("r2_bench_train32_n1.json", "c5, every layer checkpointed like the reference (`--recompute 1`), N = 1"),
                     ("r2_bench_train32_partial_n1.json", "c5, auto with the budget forced down to 40 GB (`VEX_TRAIN_KEEP_RESERVE_GB=140`): 7 layers kept, 25 checkpointed"),
-                    ("r2_bench_train32_n2.json", "c5, N = 2"), ("r2_bench_train32_n8.json", "c5, N = 8")):
+                    ("r2_bench_train32_n2.json", "c5, N = 2, checkpointed"), ("r2_bench_train32_n8.json", "c5, N = 8, checkpointed")):
     d = load(name)
     if d:
         ex = d.get("allreduce_exposed_ms")
