@@ -580,7 +580,8 @@ def run_train(args):
         l.recompute = "auto" if args.recompute < 0 else bool(args.recompute)
     params = [p for l in layers for p in l.parameters() if p.requires_grad]
     overlapped = args.allreduce == "overlap"
-    reducer = BucketedGradReducer(layers, layers_per_collective=args.ar_group) if overlapped else LoraGradReducer(params)
+    reducer = (BucketedGradReducer(layers, layers_per_collective=args.ar_group, tail_layers=args.ar_tail) if overlapped
+               else LoraGradReducer(params))
     host, total_tokens = make_shard_inputs(args)
     inp = host.to(dev)
     tokens = int(inp.padding_mask.sum())
@@ -684,8 +685,9 @@ def run_train(args):
                                  "train: fwd (activations kept in HBM) + bwd + LoRA-grad allreduce" if rec == 0 else
                                  "train: fwd (activations kept while they fit) + partial recompute + bwd + LoRA-grad "
                                  "allreduce"),
-                           allreduce=((f"bucket views, NCCL AVG per {args.ar_group} layer(s) on a side stream during the "
-                                       f"backward" if args.ar_group else "bucket views, ONE NCCL AVG over the flat "
+                           allreduce=((f"bucket views, NCCL AVG per {args.ar_group} layer(s) (the group of layer 0: "
+                                       f"{args.ar_tail or args.ar_group}) on a side stream during the backward"
+                                       if args.ar_group else "bucket views, ONE NCCL AVG over the flat "
                                        "bucket after the backward") if overlapped else "post-backward, packed (round 1)")),
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
             "allreduce_tail_ms": allreduce_ms, "allreduce_bytes": reducer.nbytes,
@@ -945,6 +947,8 @@ def main():
                     "-1 (default, the product default) = keep them while they fit the memory budget, checkpoint the rest")
     ap.add_argument("--allreduce", default="overlap", choices=["overlap", "post"], help="--train: bucket-view reducer "
                     "(default; gradients accumulate straight into the flat bucket) or the round-1 pack / unpack reducer")
+    ap.add_argument("--ar-tail", type=int, default=2, help="--train: layers in the group that holds layer 0 (its "
+                    "collective is the one the backward cannot hide); 0 = like the other groups")
     ap.add_argument("--ar-group", type=int, default=8, help="--train: layers per NCCL collective, issued on a side stream "
                     "during the backward (default 8; 0 = ONE collective over the whole bucket after the backward)")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the forward as one CUDA graph (default), 0: eager")

@@ -234,3 +234,17 @@ def test_keep_budget_policy(monkeypatch):
     layer.recompute = False
     assert T.recompute_default(layer) is False
     assert T.keep_bytes_estimate(layer, 1000, 4096) == 1000 * (8 * 4096 + 3 * 11008) * 2
+
+
+def test_bucketed_reducer_group_boundaries():
+    """Layer groups of the overlapped LoRA-grad all-reduce (conf/phase-vlm/fit.yaml:11-15 bucket views): the
+    group that holds layer 0 -- the last one the backward finishes, the only collective nothing can hide -- is short."""
+    from mmmm_b200.training import BucketedGradReducer
+    layers = [torch.nn.Linear(4, 4, bias=False) for _ in range(32)]
+    as_ranges = lambda r: [(g.start, g.stop) for g in r.groups]
+    assert as_ranges(BucketedGradReducer(layers)) == [(0, 2), (2, 10), (10, 18), (18, 26), (26, 32)]
+    assert as_ranges(BucketedGradReducer(layers, layers_per_collective=8, tail_layers=0)) == [(0, 8), (8, 16), (16, 24), (24, 32)]
+    assert as_ranges(BucketedGradReducer(layers, layers_per_collective=0)) == [(0, 32)]
+    assert as_ranges(BucketedGradReducer(layers[:3], layers_per_collective=1)) == [(0, 1), (1, 2), (2, 3)]
+    r = BucketedGradReducer(layers)
+    assert r.group_of[:3] == [0, 0, 1] and r.group_of[-1] == 4 and len(r.group_of) == 32

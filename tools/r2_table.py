@@ -42,9 +42,11 @@ prefill("r2_bench_c3_n1_final.json", "c3, N = 1 again on the final code of the r
 prefill("r2_bench_c3_n2.json", "c3, N = 2 (32 samples per GPU)")
 prefill("r2_bench_c3_n4.json", "c3, N = 4 (16 samples per GPU)")
 prefill("r2_bench_c3_n8.json", "c3, N = 8 (8 samples per GPU)")
+prefill("r2_bench_c3_n8_final.json", "c3, N = 8 again on the final code of the round (another box: 1.17 GHz under the cap)")
 prefill("r2_bench_c4_n1.json", "c4: 32 layers, global batch 16 x 2564 tokens, N = 1")
 prefill("r2_bench_c4_n1_final.json", "c4, N = 1 again on the final code of the round")
 prefill("r2_bench_c4_n8.json", "c4, N = 8 (2 samples per GPU)")
+prefill("r2_bench_c4_n8_final.json", "c4, N = 8 again on the final code of the round")
 prefill("r2_bench_c2.json", "c2: ONE layer, 8 x 1485 tokens, N = 1 (burst clocks)")
 prefill("r2_bench_c2_lora64.json", "c2 + LoRA r = 64 on all ten Linears")
 prefill("r2_bench_stack32_c2.json", "32-layer stack over 8 samples (= the c3 shard of one GPU at N = 8), N = 1")
@@ -56,6 +58,7 @@ if d:
                  f"HBM-bound: {r['achieved']:.0f} GB/s = {100 * r['frac']:.1f} % of the measured {r['peak']:.0f} GB/s "
                  f"({r['weight_bytes'] / 1e9:.2f} GB weights + {r['kv_bytes'] / 1e9:.2f} GB K/V per step)", "r2_bench_decode.json"))
 for name, label in (("r2_bench_train32_auto_n1.json", "**c5**: LoRA r = 64 training step, 32 layers, 8 x 1485 tokens, N = 1, default (`recompute = 'auto'`: every layer's activations fit and are kept in HBM)"),
+                    ("r2_bench_train32_auto_n8.json", "c5, default mode, N = 8 (bucketed LoRA-grad all-reduce overlapped with the backward)"),
                     ("r2_bench_train32_n1.json", "c5, every layer checkpointed like the reference (`--recompute 1`), N = 1"),
                     ("r2_bench_train32_partial_n1.json", "c5, auto with the budget forced down to 40 GB (`VEX_TRAIN_KEEP_RESERVE_GB=140`): 7 layers kept, 25 checkpointed"),
                     ("r2_bench_train32_n2.json", "c5, N = 2, checkpointed"), ("r2_bench_train32_n8.json", "c5, N = 8, checkpointed")):
