@@ -10,8 +10,11 @@
 // pulls work items (sample, head, query-tile pair) from a global atomic counter.  Items are ordered in waves of a few
 // (sample, head) groups, heaviest pair first inside a wave (a3_decode): the CTAs of the chip work on the pairs of the same
 // groups at the same time, so K / V come out of L2 (a chip-wide heaviest-first static deal read 753 MB from DRAM per c2
-// launch instead of 292 MB), the last wave drains longest-first, and the greedy hand-out balances ragged batches.  The TMA producer thread is the scheduler: it publishes each fetched item
-// through a small shared-memory ring (sched_full / sched_empty) that the issuer and softmax warps follow:
+// launch instead of 292 MB), and the greedy hand-out balances ragged batches.  The last three waves are merged into ONE
+// heaviest-first wave, so the launch ends on one-block items instead of a few CTAs finishing 12-block items while the
+// rest of the chip idles (round 2: c2 181 -> 169 us, profiles/r2_k4_schedule.md).  The TMA producer thread is the
+// scheduler: it publishes each fetched item through a small shared-memory ring (sched_full / sched_empty) that the
+// issuer and softmax warps follow:
 //   * barriers, TMEM and tensor-map prefetch are set up once per CTA;
 //   * the TMA producer runs ahead across items: the next item's Q tiles are loaded as soon as the last S of the current
 //     item has been issued (q_empty), its K/V blocks simply continue in the 3-slot ring;
