@@ -18,11 +18,14 @@
 //   * partial sums of the 8 warps are reduced through shared memory, then 16 x B outputs take the epilogue.
 // mma.sync is used on purpose: the math is 0.1 % of the tensor peak, the operand path (global -> registers) is what
 // matters, and tcgen05 would force the weights through shared memory.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
 
 namespace vex {
+
+int num_sms();
 
 constexpr int DG_THREADS = 256;
 constexpr int DG_WARPS = 8;
@@ -98,7 +101,7 @@ __device__ __forceinline__ void mma_chunk(float (&c)[2][NB][4], const WFrag<TILE
 // ring of NBUF register fragments: NBUF - 1 chunks are in flight while one is multiplied, so a warp always has loads
 // outstanding.  One-tile launches (dense / down: only 256 CTAs, < 2 per SM) run 4 deep, two-tile launches 2 deep
 // (a fragment is 16 registers per tile; batches above 16 rows keep 2 for their extra accumulators).
-template <int NB, int TILES>
+template <int NB, int TILES, int WARPS = DG_WARPS>
 __device__ __forceinline__ void accumulate(float (&c)[2][NB][4], const __nv_bfloat16* const* wrow_lo,
                                            const __nv_bfloat16* const* wrow_hi, const __nv_bfloat16* const* xrow,
                                            const bool* xlive, int K, int warp, int t, bool wait_after_prefetch = false) {
@@ -107,25 +110,28 @@ __device__ __forceinline__ void accumulate(float (&c)[2][NB][4], const __nv_bflo
   WFrag<TILES> f[NBUF];
 #pragma unroll
   for (int b = 0; b < NBUF - 1; ++b) {
-    const int ip = warp + b * DG_WARPS;
+    const int ip = warp + b * WARPS;
     if (ip < nchunks) load_w<TILES>(f[b], wrow_lo, wrow_hi, (ip << 6) + 16 * t);
   }
   // the first weight fragments are in flight; x (and everything the epilogue touches) belongs to the previous kernel
   if (wait_after_prefetch) pdl_wait();
-  for (int i = warp; i < nchunks; i += DG_WARPS * NBUF) {
+  for (int i = warp; i < nchunks; i += WARPS * NBUF) {
 #pragma unroll
     for (int b = 0; b < NBUF; ++b) {
-      const int ic = i + b * DG_WARPS;                  // chunk multiplied now: lives in f[b]
+      const int ic = i + b * WARPS;                  // chunk multiplied now: lives in f[b]
       if (ic >= nchunks) break;
-      const int ip = ic + (NBUF - 1) * DG_WARPS;        // chunk prefetched into the slot consumed one step ago
+      const int ip = ic + (NBUF - 1) * WARPS;        // chunk prefetched into the slot consumed one step ago
       if (ip < nchunks) load_w<TILES>(f[(b + NBUF - 1) % NBUF], wrow_lo, wrow_hi, (ip << 6) + 16 * t);
       mma_chunk<NB, TILES>(c, f[b], xrow, xlive, (ic << 6) + 16 * t);
     }
   }
 }
 
-template <int NB, int TILES>
-__global__ void __launch_bounds__(DG_THREADS, 2) k12_decode_gemm(const DecGemm p) {
+// WARPS = 8 (256 threads, 2 CTAs per SM) or 4 (128 threads, 4 CTAs per SM: the form for launches whose CTA count lies
+// between 296 and 592 -- the QKV projection's 384 -- which then run as ONE resident wave instead of 1.3)
+template <int NB, int TILES, int WARPS, int CTAS_PER_SM = (WARPS == 4 ? 4 : 2)>
+__global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) k12_decode_gemm(const DecGemm p) {
+  constexpr int DG_WARPS = WARPS, DG_THREADS = WARPS * 32;  // shadow the 8-warp defaults below
   __shared__ float red[DG_WARPS][TILES][NB][32][4];   // per-warp partial fragments
   __shared__ float fin[TILES][NB * 8][16];            // reduced [tile][batch row][feature]
   pdl_trigger();  // the next kernel of the step may be scheduled: its weight prefetch overlaps this kernel's stream
@@ -161,7 +167,7 @@ __global__ void __launch_bounds__(DG_THREADS, 2) k12_decode_gemm(const DecGemm p
     const __nv_bfloat16* lo[2] = {wa + static_cast<int64_t>(n_a + g) * p.ldw, wb + static_cast<int64_t>(n_b + g) * p.ldw};
     const __nv_bfloat16* hi[2] = {wa + static_cast<int64_t>(n_a + g + 8) * p.ldw,
                                   wb + static_cast<int64_t>(n_b + g + 8) * p.ldw};
-    accumulate<NB, TILES>(c, lo, hi, xrow, xlive, p.K, warp, t, /*wait_after_prefetch=*/true);
+    accumulate<NB, TILES, WARPS>(c, lo, hi, xrow, xlive, p.K, warp, t, /*wait_after_prefetch=*/true);
   }
   if (p.lora_r > 0) {  // K-extension: += T . lora_B^T  (r is a multiple of 64 here; r = 64 -> one chunk, warp 0)
     const __nv_bfloat16* trow[NB];
@@ -184,8 +190,8 @@ __global__ void __launch_bounds__(DG_THREADS, 2) k12_decode_gemm(const DecGemm p
       const __nv_bfloat16* hi_g[2] = {hi[0], hi[0]};
       const __nv_bfloat16* lo_u[2] = {lo[1], lo[1]};
       const __nv_bfloat16* hi_u[2] = {hi[1], hi[1]};
-      accumulate<NB, 1>(cg, lo_g, hi_g, trow, xlive, p.lora_r, warp, t);
-      accumulate<NB, 1>(cu, lo_u, hi_u, urow, xlive, p.lora_r, warp, t);
+      accumulate<NB, 1, WARPS>(cg, lo_g, hi_g, trow, xlive, p.lora_r, warp, t);
+      accumulate<NB, 1, WARPS>(cu, lo_u, hi_u, urow, xlive, p.lora_r, warp, t);
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
@@ -194,7 +200,7 @@ __global__ void __launch_bounds__(DG_THREADS, 2) k12_decode_gemm(const DecGemm p
           if (TILES == 2) c[1][nb][r] += cu[0][nb][r];
         }
     } else {
-      accumulate<NB, TILES>(c, lo, hi, trow, xlive, p.lora_r, warp, t);
+      accumulate<NB, TILES, WARPS>(c, lo, hi, trow, xlive, p.lora_r, warp, t);
     }
   }
 
@@ -266,7 +272,27 @@ __global__ void __launch_bounds__(DG_THREADS, 2) k12_decode_gemm(const DecGemm p
 
 template <int NB, int TILES>
 static int launch_dg(const DecGemm& p, int tasks, cudaStream_t s) {
-  VEX_CUDA_TRY(launch_pdl(k12_decode_gemm<NB, TILES>, dim3(tasks), dim3(DG_THREADS), 0, s, p));
+  // one resident wave if 4-warp CTAs (4 per SM) make it possible and 8-warp CTAs (2 per SM) do not
+  static const bool narrow_ok = [] {  // VEX_K12_NARROW=0: always 8 warps (A/B timing)
+    const char* e = std::getenv("VEX_K12_NARROW");
+    return !(e && e[0] == '0');
+  }();
+  const int sms = num_sms();
+  if (narrow_ok && NB <= 2 && tasks > 2 * sms && tasks <= 4 * sms) {
+    VEX_CUDA_TRY(launch_pdl(k12_decode_gemm<NB, TILES, 4>, dim3(tasks), dim3(128), 0, s, p));
+    return VEX_OK;
+  }
+  if constexpr (NB == 1) {  // 5 CTAs of 4 warps per SM (<= 102 registers): gate / up's 688 CTAs in one wave
+    static const bool five_ok = [] {
+      const char* e = std::getenv("VEX_K12_FIVE");
+      return !(e && e[0] == '0');
+    }();
+    if (narrow_ok && five_ok && tasks > 4 * sms && tasks <= 5 * sms) {
+      VEX_CUDA_TRY(launch_pdl(k12_decode_gemm<NB, TILES, 4, 5>, dim3(tasks), dim3(128), 0, s, p));
+      return VEX_OK;
+    }
+  }
+  VEX_CUDA_TRY(launch_pdl(k12_decode_gemm<NB, TILES, 8>, dim3(tasks), dim3(DG_THREADS), 0, s, p));
   return VEX_OK;
 }
 

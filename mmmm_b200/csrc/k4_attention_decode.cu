@@ -14,11 +14,14 @@
 // Per CTA (256 threads): both passes read the cache with LDG.256, 8 lanes per 256-byte row (two full 128-byte lines),
 // 4 rows per warp instruction; a lane owns 16 of the 128 dims (scores: shuffle-reduced inside the 8-lane group; values:
 // the 4 groups of a warp are folded with shuffles, the 8 warps through shared memory).
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
 
 namespace vex {
+
+int num_sms();
 
 constexpr int DEC_THREADS = 256;
 constexpr int DEC_WARPS = DEC_THREADS / 32;
@@ -199,9 +202,22 @@ static int launch_decode(const void* q, int64_t ldq, const void* k, const void* 
                          float scale, cudaStream_t s) {
   if (!q || !k || !v || !mask || !out || B <= 0 || heads <= 0 || L <= 0 || cap < L) return VEX_E_INVALID;
   if (B > 65535) return VEX_E_UNSUPPORTED;
-  // KV splits (= cluster size, a power of two <= 8): enough CTAs for ~4 per SM, chunks of at least 64 positions
+  // KV splits (= cluster size, a power of two <= 8): as many as keep the WHOLE grid resident at once (3 CTAs per SM at
+  // 78 registers), chunks of at least 64 positions.  A grid that needs a second wave loses more than the split gains:
+  // the last, partial wave streams with too few CTAs to keep DRAM busy (batch 8 x 32 heads, ~1 500 positions: 1 024
+  // CTAs in 2.3 waves 4.26 ms per decode step, 256 CTAs in one wave 4.07 ms; profiles/r2_decode_experiments.md).
+  // Very long caches are split anyway so that the score buffer stays small enough for 3 CTAs per SM.
   int nsplit = 1;
-  while (nsplit < 8 && static_cast<int64_t>(B) * heads * nsplit < 4 * 148 && L / (2 * nsplit) >= 64) nsplit *= 2;
+  const int64_t resident = 3 * static_cast<int64_t>(num_sms());
+  while (nsplit < 8 && static_cast<int64_t>(B) * heads * nsplit * 2 <= resident && L / (2 * nsplit) >= 64) nsplit *= 2;
+  while (nsplit < 8 && L / nsplit > 16384) nsplit *= 2;
+  {
+    static const int forced = [] {  // VEX_K4D_NSPLIT: tuning override (1, 2, 4 or 8)
+      const char* e = std::getenv("VEX_K4D_NSPLIT");
+      return e ? std::atoi(e) : 0;
+    }();
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8) nsplit = forced;
+  }
   const int chunk_cap = ceil_div(L, nsplit);
   if (chunk_cap > DEC_MAX_L) return VEX_E_UNSUPPORTED;
   static bool configured = false;
