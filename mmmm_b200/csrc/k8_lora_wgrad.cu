@@ -15,12 +15,15 @@
 // uninitialised, so the last k-block of a chunk zeroes them in shared memory before the MMA reads it.
 #include <cuda.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
 
 namespace vex {
 
+int num_sms();
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
 constexpr int WG_CHUNK = 1024;  // tokens per CTA
@@ -42,17 +45,32 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
   // ---- which (expert, token chunk) is this CTA's? ----
   const int cnt0 = min(max(counts[0], 0), rows_cap);
   const int cnt1 = min(max(counts[1], 0), rows_cap - cnt0);
-  const int nc0 = (cnt0 + WG_CHUNK - 1) / WG_CHUNK, nc1 = (cnt1 + WG_CHUNK - 1) / WG_CHUNK;
+  // gridDim.y token chunks are dealt to the two expert segments in proportion to their rows (an expert without an adapter
+  // gets none), each segment is cut into equal chunks of whole k-blocks.  The host sizes gridDim.y so that the whole
+  // grid is resident at once (2 CTAs per SM): with fixed 1 024-token chunks the F = 4096 launches ran 416 CTAs in 1.4
+  // waves, and the partial wave of an HBM-bound launch streams at a fraction of the bandwidth (the decode kernels'
+  // lesson, profiles/r2_decode_experiments.md).
+  const int G = gridDim.y;
+  const int w0 = out0 ? cnt0 : 0, w1 = out1 ? cnt1 : 0;
+  int n0;
+  if (w0 == 0) n0 = 0;
+  else if (w1 == 0) n0 = G;
+  else n0 = min(G - 1, max(1, static_cast<int>((static_cast<int64_t>(w0) * G + (w0 + w1) / 2) / (w0 + w1))));
+  const int n1 = G - n0;
   int c = blockIdx.y, e = 0, lo, hi;
-  if (c < nc0) {
-    lo = c * WG_CHUNK;
-    hi = min(cnt0, lo + WG_CHUNK);
+  if (c < n0) {
+    const int ch = ((cnt0 + n0 - 1) / n0 + WG_BK - 1) / WG_BK * WG_BK;
+    if (c * ch >= cnt0) return;
+    lo = c * ch;
+    hi = min(cnt0, lo + ch);
   } else {
-    c -= nc0;
-    if (c >= nc1) return;
+    c -= n0;
+    if (n1 == 0 || w1 == 0) return;
+    const int ch = ((cnt1 + n1 - 1) / n1 + WG_BK - 1) / WG_BK * WG_BK;
+    if (c * ch >= cnt1) return;
     e = 1;
-    lo = cnt0 + c * WG_CHUNK;
-    hi = min(cnt0 + cnt1, lo + WG_CHUNK);
+    lo = cnt0 + c * ch;
+    hi = min(cnt0 + cnt1, lo + ch);
   }
   float* out = e ? out1 : out0;
   if (out == nullptr) return;  // this expert has no adapter
@@ -209,8 +227,17 @@ extern "C" int vex_lora_wgrad(const void* x, int64_t ldx, const void* y, int64_t
   int rc;
   if ((rc = make_tmap_2d(&tm.x, x, rows_cap, F, ldx, WG_BK)) != VEX_OK) return rc;
   if ((rc = make_tmap_2d(&tm.y, y, rows_cap, r, ldy, WG_BK)) != VEX_OK) return rc;
-  // every expert segment adds at most one partial chunk
-  dim3 grid(ceil_div(F, 128), ceil_div(rows_cap, WG_CHUNK) + 1);
+  // token chunks: as many as keep the whole grid resident (2 CTAs per SM), at least 2 (one per expert segment), no
+  // smaller than one k-block; VEX_K8_CHUNKS overrides (tuning)
+  static const int forced_chunks = [] {
+    const char* e = std::getenv("VEX_K8_CHUNKS");
+    return e ? std::atoi(e) : 0;
+  }();
+  const int f_tiles = ceil_div(F, 128);
+  int chunks = std::max(2, (2 * num_sms()) / f_tiles);
+  chunks = std::min(chunks, ceil_div(rows_cap, WG_BK) + 1);
+  if (forced_chunks > 0) chunks = std::max(2, forced_chunks);
+  dim3 grid(f_tiles, chunks);
   k8_lora_wgrad<<<grid, WG_THREADS, WG_SMEM, static_cast<cudaStream_t>(stream)>>>(
       tm, counts, out_vision, out_language, ldo, transpose_out, F, r, rows_cap);
   VEX_LAUNCH_CHECK();
