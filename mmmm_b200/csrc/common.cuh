@@ -198,6 +198,20 @@ __device__ __forceinline__ uint4 ld_coherent_stream(const void* p) {
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Grid size of a grid-stride / persistent launch: every CTA resident at once (occupancy x SM count).  An HBM-bound
+// launch whose grid needs a second, partial wave streams that wave with too few CTAs to keep DRAM busy (round 2:
+// profiles/r2_decode_experiments.md), and one whose grid is a multiple of the resident count pays the ramp-up twice.
+int num_sms();
+template <typename Kernel>
+inline int resident_ctas(Kernel kernel, int threads, size_t dyn_smem = 0) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem) != cudaSuccess || per_sm < 1) {
+    (void)cudaGetLastError();
+    per_sm = 1;
+  }
+  return per_sm * num_sms();
+}
+
 inline bool pdl_enabled() {  // VEX_PDL=0: plain launches (A/B timing, debugging)
   static const bool on = [] {
     const char* e = std::getenv("VEX_PDL");

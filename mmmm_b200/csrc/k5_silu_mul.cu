@@ -35,7 +35,7 @@ extern "C" int vex_silu_mul(const void* gate, const void* up, void* out, const i
   if (!gate || !up || !out || !n_rows || rows_cap <= 0 || I <= 0) return VEX_E_INVALID;
   if (I % 8 != 0) return VEX_E_UNSUPPORTED;
   const int64_t total = static_cast<int64_t>(rows_cap) * (I / 8);
-  const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 16));
+  const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 16));  // see vex_silu_mul_backward
   vex::k5_silu_mul<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(gate), static_cast<const uint4*>(up), static_cast<uint4*>(out), n_rows, rows_cap,
       I / 8);

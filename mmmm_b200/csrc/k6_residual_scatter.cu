@@ -88,7 +88,8 @@ extern "C" int vex_residual_scatter(const void* y, const void* residual, const i
                                     const int32_t* n_rows, void* out, int rows_cap, int H, vexStream stream) {
   if (!y || !residual || !n_rows || !out || rows_cap <= 0 || H <= 0) return VEX_E_INVALID;
   if (H % 8 != 0) return VEX_E_UNSUPPORTED;
-  const int grid = std::min(vex::ceil_div(rows_cap, 8), 148 * 8);
+  static const int resident = vex::resident_ctas(vex::k6_residual_scatter, 256);
+  const int grid = std::min(vex::ceil_div(rows_cap, 8), resident);
   vex::k6_residual_scatter<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(y), static_cast<const __nv_bfloat16*>(residual), row_dst, n_rows,
       static_cast<__nv_bfloat16*>(out), rows_cap, H);
